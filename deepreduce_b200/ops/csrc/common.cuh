@@ -1,0 +1,123 @@
+// Shared device/host helpers for the DeepReduce-B200 kernels (sm_100a).
+// Hash family and bit layout are normative: see deepreduce_b200/spec.py.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "plan.h"
+
+#define DR_HD __host__ __device__ __forceinline__
+#define DR_D __device__ __forceinline__
+
+namespace dr {
+
+constexpr uint32_t kGolden = 0x9E3779B1u;
+constexpr uint32_t kBAdd = 0x7F4A7C15u;
+constexpr int kThreads = 512;         // threads per CTA in the engine kernels
+constexpr int kPerThread = kTile / kThreads;   // 8
+constexpr int kWarps = kThreads / 32;          // 16
+
+DR_HD uint32_t fmix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h;
+}
+
+struct HashAB { uint32_t a, b; };
+
+DR_HD HashAB hash_ab(uint32_t x, uint32_t seed) {
+  uint32_t y = x ^ seed;
+  HashAB r;
+  r.a = fmix32(y);
+  r.b = fmix32(y * kGolden + kBAdd) | 1u;
+  return r;
+}
+
+DR_HD uint32_t mulhi32(uint32_t h, uint32_t m) {
+#ifdef __CUDA_ARCH__
+  return __umulhi(h, m);
+#else
+  return (uint32_t)(((uint64_t)h * (uint64_t)m) >> 32);
+#endif
+}
+
+DR_HD uint32_t policy_hash(uint32_t x, uint32_t seed) {
+  return fmix32((x * kGolden + seed) ^ 0x5BD1E995u);
+}
+
+// Membership test with early exit.  `filter` is a bit-packed uint32 array.
+template <typename LoadFn>
+DR_D bool bloom_test(uint32_t x, uint32_t seed, uint32_t n_hash, uint32_t m_bits, LoadFn ld) {
+  HashAB h = hash_ab(x, seed);
+  uint32_t v = h.a;
+  for (uint32_t j = 0; j < n_hash; ++j) {
+    uint32_t pos = mulhi32(v, m_bits);
+    if (!((ld(pos >> 5) >> (pos & 31u)) & 1u)) return false;
+    v += h.b;
+  }
+  return true;
+}
+
+DR_D void bloom_set(uint32_t* filter, uint32_t x, uint32_t seed, uint32_t n_hash, uint32_t m_bits) {
+  HashAB h = hash_ab(x, seed);
+  uint32_t v = h.a;
+  for (uint32_t j = 0; j < n_hash; ++j) {
+    uint32_t pos = mulhi32(v, m_bits);
+    atomicOr(filter + (pos >> 5), 1u << (pos & 31u));
+    v += h.b;
+  }
+}
+
+// ---- memory-model helpers -------------------------------------------------
+DR_D uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+DR_D uint64_t ld_acquire_gpu64(const uint64_t* p) {
+  uint64_t v; asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+}
+DR_D void st_release_gpu64(uint64_t* p, uint64_t v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+DR_D uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+DR_D void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+DR_D uint32_t ld_relaxed_sys(const uint32_t* p) {
+  uint32_t v; asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+// streaming 128-bit load that does not allocate in L1 (data touched once per pass)
+DR_D float4 ld_stream_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+DR_D uint4 ld_stream_u4(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
+// Grid-wide barrier for a co-resident (cooperative-launch) grid.  `counter`
+// is zeroed by the host before launch; `*epoch` is a per-thread-0 register
+// copy counting barriers passed.
+DR_D void grid_barrier(uint32_t* counter, uint32_t& epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    epoch += 1;
+    const uint32_t target = epoch * gridDim.x;
+    __threadfence();
+    atomicAdd(counter, 1u);
+    while (ld_acquire_gpu(counter) < target) { __nanosleep(32); }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// launch accounting (bench.py's "gpu_launches")
+void count_launch(int n = 1);
+long long launch_count();
+
+}  // namespace dr

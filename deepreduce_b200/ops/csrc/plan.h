@@ -1,0 +1,115 @@
+// Bucket plan + engine parameter block shared by host (binding.cpp) and device
+// (engine.cu).  The plan is built in Python (parallel/plan.py) and uploaded as
+// int32 tensors; field order here is normative for that builder.
+#pragma once
+#include <stdint.h>
+
+namespace dr {
+
+constexpr int kMaxWorld = 16;
+constexpr int kTile = 4096;           // elements per tile (wire-visible: per-tile prefix table)
+constexpr uint32_t kDefaultSeed = 0x9747B28Cu;
+
+enum TensorMode : uint32_t {
+  kModeRaw = 0,     // plain (value, index) pairs — small-tensor bypass / plain top-k
+  kModeBloom = 1,   // bloom-filter index codec, fp32 values
+};
+
+enum Policy : int { kPolicyLeftmost = 0, kPolicyRandom = 1, kPolicyP0 = 2 };
+
+// 16 x uint32 per tensor
+struct TensorDesc {
+  uint32_t elem_off;     // offset into the flat grad/residual buffers (elements, multiple of 4)
+  uint32_t numel;        // d_i
+  uint32_t k;            // K_i = max(1, int(d_i * ratio)), <= numel
+  uint32_t tile_begin;   // first global tile id
+  uint32_t n_tiles;      // ceil(numel / kTile)
+  uint32_t mode;         // TensorMode
+  uint32_t m_bits;       // bloom bits (multiple of 32)
+  uint32_t n_hash;       // bloom hash count
+  uint32_t off_vals;     // payload word offsets (within a slot)
+  uint32_t off_filter;
+  uint32_t off_prefix;   // per-tile exclusive prefix of selected counts (n_tiles words)
+  uint32_t off_idx;      // raw mode: indices
+  uint32_t val_cap;      // capacity of the value region (K, or K+slack for p0)
+  uint32_t salt;         // tensor id (policy seeds)
+  uint32_t n_filter_words;
+  uint32_t reserved;
+};
+static_assert(sizeof(TensorDesc) == 64, "TensorDesc must be 16 words");
+
+// payload slot layout (uint32 words):
+//   [0..8)                      : magic, epoch, n_tensors, payload_words, rank, 0,0,0
+//   [8 .. 8+4*n_tensors)        : DynHeader per tensor
+//   then per-tensor regions at the TensorDesc offsets
+constexpr uint32_t kSlotHeaderWords = 8;
+constexpr uint32_t kDynWords = 4;
+constexpr uint32_t kMagic = 0xD33B2000u;
+struct DynHeader {
+  uint32_t n_sel;      // number of values actually shipped
+  uint32_t cutoff;     // largest selected index (leftmost); 0xFFFFFFFF = no cut
+  uint32_t thr_bits;   // |g| threshold bits chosen by the select
+  uint32_t n_pos;      // filter positives in the universe (diagnostics / FP count)
+};
+
+// per-tensor select state (persists across steps; thr history drives the
+// pass-1 lower bound): 8 words
+struct SelState {
+  uint32_t bin1, krem1, bin2, krem2;
+  uint32_t thr;         // final 31-bit threshold key T
+  uint32_t need;        // ties (key == T) to take
+  uint32_t ties_total;  // ties present
+  uint32_t prev_thr;    // T of the previous step (0 = none)
+};
+
+constexpr int kHistBins = 2048;
+// hist arrays: [4][n_tensors][kHistBins]  (pass1, pass1-fallback, pass2, pass3)
+// hist_total:  [4][n_tensors]
+
+// arena layout per rank (uint32 words): [flags: 64][status: 64][slots: 2 * world * slot_words]
+constexpr uint32_t kArenaFlagWords = 64;
+constexpr uint32_t kArenaHdrWords = 128;
+
+enum Phase : int {
+  kPhAccum = 0,      // r = beta*r + gamma*g ; zero slot ; hist pass 1 (with history lower bound)
+  kPhFallback = 1,   // hist pass 1 redone without bound for tensors whose bound was unsafe
+  kPhHist2 = 2,
+  kPhHist3 = 3,
+  kPhInsert = 4,     // threshold resolve, bloom insert (tie ranks by look-back when needed)
+  kPhEmit = 5,       // universe query + ordered compaction + value gather + residual zeroing
+  kPhPush = 6,       // copy the finished slot into every peer's arena (P2P stores)
+  kPhSignal = 7,     // release flags to peers, acquire peers' flags
+  kPhDecode = 8,     // membership test on every rank's filter, rank->value, sum, scale, dense write
+  kPhEnd = 9
+};
+
+struct EngineParams {
+  const TensorDesc* tensors;
+  const uint32_t* tile_tensor;   // [n_tiles] tile -> tensor id
+  uint32_t n_tensors;
+  uint32_t n_tiles;
+  uint32_t slot_words;           // words reserved per slot
+  uint32_t payload_words;        // words actually used (pushed)
+  float* grad;                   // in: local dense grad; out: aggregated dense grad
+  float* resid;                  // residual accumulator (persists across steps)
+  uint32_t* hist;                // [4][n_tensors][kHistBins]
+  uint32_t* hist_total;          // [4][n_tensors]
+  SelState* sel;                 // [n_tensors]
+  uint64_t* tie_desc;            // [n_tiles] look-back descriptors (epoch tagged)
+  uint64_t* pos_desc;            // [n_tiles]
+  uint32_t* tie_prefix;          // [n_tiles] exclusive tie rank at tile start
+  uint32_t* barrier;             // grid barrier counter (zeroed by host per launch)
+  uint32_t* status;              // [8] error / watchdog words (device-local)
+  uint32_t* arena[kMaxWorld];    // peer-mapped arena base of every rank (arena[rank] is local)
+  int rank;
+  int world;
+  uint32_t epoch;                // 1-based step counter; slot parity = epoch & 1
+  float beta, gamma, scale;
+  uint32_t seed;
+  int policy;
+  int use_history;               // pass-1 lower bound from prev_thr
+  int phase_begin, phase_end;
+  uint32_t spin_limit;           // watchdog for flag / look-back spins
+};
+
+}  // namespace dr

@@ -1,0 +1,266 @@
+"""Python driver + torch oracle for the fused bucket engine (``ops/csrc/engine.cu``).
+
+``BucketEngine`` owns the flat gradient / residual buffers of one bucket, the
+select/look-back state, the symmetric arena (CUDA IPC for W>1) and the C++
+``Engine`` context; ``step()`` launches the single persistent kernel that does
+sparsify → encode → P2P push → decode for the whole bucket.
+
+``engine_oracle`` is the plain-PyTorch specification of the same step,
+including the wire format of the slot, used by the tests (GPU kernels vs
+oracle: slots bit-exact, dense output allclose) and as the CPU/gloo fallback of
+the bucketed API.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .. import spec
+from ..codecs.bloom import bloom_insert_oracle, bloom_query_oracle
+from .plan import (ARENA_HDR_WORDS, DYN_WORDS, HIST_BINS, MODE_BLOOM, MODE_RAW, POLICY_ID, SLOT_HEADER_WORDS,
+                   BucketPlan)
+
+PH_ACCUM, PH_FALLBACK, PH_HIST2, PH_HIST3, PH_INSERT, PH_EMIT, PH_PUSH, PH_SIGNAL, PH_DECODE, PH_END = range(10)
+MAGIC = 0xD33B2000
+STATUS_NAMES = {0: "ok", 1: "look-back watchdog", 2: "peer flag watchdog", 3: "select resolve failed"}
+
+
+# ---------------------------------------------------------------------------
+# oracle
+# ---------------------------------------------------------------------------
+def _abs_keys(x: torch.Tensor) -> torch.Tensor:
+    return x.contiguous().view(torch.int32).to(torch.int64) & 0x7FFFFFFF
+
+
+def select_topk_oracle(acc: torch.Tensor, k: int):
+    """Exact top-k by |x| with deterministic ties (smallest index first).
+    Returns (ascending indices, threshold key T)."""
+    keys = _abs_keys(acc)
+    T = int(torch.topk(keys, k, sorted=True).values[-1].item())
+    gt = torch.nonzero(keys > T).flatten()
+    need = k - gt.numel()
+    eq = torch.nonzero(keys == T).flatten()[:need]
+    return torch.sort(torch.cat([gt, eq])).values, T
+
+
+def encode_tensor_oracle(tp, acc: torch.Tensor, slot: np.ndarray, t_index: int, policy: str, seed: int):
+    """Encode one tensor into `slot` (uint32 numpy view); returns new residual."""
+    sel_topk, T = select_topk_oracle(acc, tp.k)
+    dyn = SLOT_HEADER_WORDS + DYN_WORDS * t_index
+    resid = acc.clone()
+    if tp.mode == MODE_BLOOM:
+        words = bloom_insert_oracle(sel_topk, tp.n_hash, tp.m_bits, seed)
+        pos = bloom_query_oracle(words, tp.numel, tp.n_hash, tp.m_bits, seed)
+        limit = tp.val_cap if policy == "p0" else min(tp.k, tp.val_cap)
+        sel = pos[:limit]
+        n_pos = int(pos.numel())
+        slot[tp.off_filter:tp.off_filter + tp.n_filter_words] = words.cpu().numpy().view(np.uint32)
+        starts = torch.arange(tp.n_tiles, dtype=torch.int64) * spec.TILE
+        slot[tp.off_prefix:tp.off_prefix + tp.n_tiles] = torch.searchsorted(sel.cpu(), starts).numpy().astype(np.uint32)
+        cutoff = int(sel[-1].item()) if n_pos >= limit and limit > 0 else 0xFFFFFFFF
+    else:
+        sel = sel_topk
+        n_pos = int(sel.numel())
+        limit = tp.val_cap
+        slot[tp.off_idx:tp.off_idx + sel.numel()] = sel.cpu().numpy().astype(np.uint32)
+        cutoff = int(sel[-1].item()) if n_pos >= limit else 0xFFFFFFFF
+    vals = acc[sel].float()
+    slot[tp.off_vals:tp.off_vals + sel.numel()] = vals.cpu().numpy().view(np.uint32)
+    resid[sel] = 0
+    slot[dyn + 0] = sel.numel()
+    slot[dyn + 1] = cutoff
+    slot[dyn + 2] = T
+    slot[dyn + 3] = n_pos
+    return resid, sel, vals
+
+
+def engine_oracle(plan: BucketPlan, grads: Sequence[torch.Tensor], resids: Sequence[torch.Tensor], *, beta=1.0,
+                  gamma=1.0, average=True, seed=spec.DEFAULT_SEED, epoch=1):
+    """One bucket step for W ranks on the CPU.  grads/resids: per-rank flat
+    buffers (plan.total_elems).  Returns (dense_out, new_resids, slots)."""
+    W = len(grads)
+    out = torch.zeros(plan.total_elems, dtype=torch.float32)
+    new_resids, slots = [], []
+    for r in range(W):
+        g = grads[r].detach().cpu().float()
+        res = resids[r].detach().cpu().float()
+        acc_flat = beta * res + gamma * g if beta != 0.0 else gamma * g
+        slot = np.zeros(plan.payload_words, dtype=np.uint32)
+        slot[0:5] = [MAGIC, epoch, len(plan.tensors), plan.payload_words, r]
+        nres = acc_flat.clone()
+        for ti, tp in enumerate(plan.tensors):
+            seg = slice(tp.elem_off, tp.elem_off + tp.numel)
+            resid_t, sel, vals = encode_tensor_oracle(tp, acc_flat[seg], slot, ti, plan.policy, seed)
+            nres[seg] = resid_t
+            out[seg].index_add_(0, sel, vals)
+        new_resids.append(nres)
+        slots.append(slot)
+    if average:
+        out = out / W
+    return out, new_resids, slots
+
+
+# ---------------------------------------------------------------------------
+# engine
+# ---------------------------------------------------------------------------
+class BucketEngine:
+    """One flat bucket + its fused exchange kernel."""
+
+    def __init__(self, plan: BucketPlan, device=None, group=None, *, beta: float = 1.0, gamma: float = 1.0,
+                 average: bool = True, use_history: bool = True, blocks_per_sm: int = 2,
+                 seed: int = spec.DEFAULT_SEED, spin_limit: int = 20_000_000, world: Optional[int] = None,
+                 rank: Optional[int] = None):
+        from .. import ops
+        self.mod = ops.cuda_module()
+        self.plan = plan
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.group = group
+        if world is None:
+            world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+            rank = dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
+        self.world, self.rank = int(world), int(rank or 0)
+        self.beta, self.gamma, self.average = float(beta), float(gamma), bool(average)
+        self.epoch = 0
+        dev = self.device
+        nT, nt = len(plan.tensors), plan.n_tiles
+        with torch.cuda.device(dev):
+            self.grad = torch.zeros(plan.total_elems, dtype=torch.float32, device=dev)
+            self.resid = torch.zeros(plan.total_elems, dtype=torch.float32, device=dev)
+            self.tensor_table = plan.tensor_table().to(dev)
+            self.tile_table = plan.tile_table().to(dev)
+            self.hist = torch.zeros(4 * nT * HIST_BINS, dtype=torch.int32, device=dev)
+            self.hist_total = torch.zeros(4 * nT, dtype=torch.int32, device=dev)
+            self.sel = torch.zeros(nT * 8, dtype=torch.int32, device=dev)
+            self.tie_desc = torch.zeros(nt, dtype=torch.int64, device=dev)
+            self.pos_desc = torch.zeros(nt, dtype=torch.int64, device=dev)
+            self.tie_prefix = torch.zeros(nt, dtype=torch.int32, device=dev)
+            self.barrier = torch.zeros(16, dtype=torch.int32, device=dev)
+            self.status = torch.zeros(8, dtype=torch.int32, device=dev)
+            self._setup_arena()
+            self.ctx = self.mod.Engine(
+                self.tensor_table.data_ptr(), self.tile_table.data_ptr(), nT, nt, plan.slot_words, plan.payload_words,
+                self.grad.data_ptr(), self.resid.data_ptr(), self.hist.data_ptr(), self.hist_total.data_ptr(),
+                self.sel.data_ptr(), self.tie_desc.data_ptr(), self.pos_desc.data_ptr(), self.tie_prefix.data_ptr(),
+                self.barrier.data_ptr(), self.status.data_ptr(), self.arena_ptrs, self.rank, self.world)
+            scale = (1.0 / self.world) if average else 1.0
+            self.ctx.configure(self.beta, self.gamma, scale, int(seed), POLICY_ID[plan.policy], int(use_history),
+                               int(spin_limit), int(blocks_per_sm))
+        self.grad_views = plan.views(self.grad)
+
+    # ---- arena -------------------------------------------------------------
+    def _setup_arena(self):
+        words = self.plan.arena_words(self.world)
+        self._ipc = self.world > 1
+        if not self._ipc:
+            self.arena = torch.zeros(words, dtype=torch.int32, device=self.device)
+            self.arena_ptrs = [self.arena.data_ptr()]
+            return
+        self.mod.enable_peer_access(torch.cuda.device_count())
+        self._arena_ptr = self.mod.arena_alloc(words * 4)
+        self.arena = self.mod.arena_as_tensor(self._arena_ptr, words, self.device.index or 0)
+        handle = self.mod.arena_export(self._arena_ptr)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle, group=self.group)
+        self.arena_ptrs = []
+        self._imported = []
+        for r in range(self.world):
+            if r == self.rank:
+                self.arena_ptrs.append(self._arena_ptr)
+            else:
+                p = self.mod.arena_import(handles[r])
+                self._imported.append(p)
+                self.arena_ptrs.append(p)
+        dist.barrier(group=self.group)
+
+    def close(self):
+        if getattr(self, "_ipc", False):
+            torch.cuda.synchronize(self.device)
+            if dist.is_initialized():
+                dist.barrier(group=self.group)
+            for p in self._imported:
+                self.mod.arena_close(p)
+            self._imported = []
+            self.mod.arena_free(self._arena_ptr)
+            self._ipc = False
+
+    # ---- run ---------------------------------------------------------------
+    def step(self, epoch: Optional[int] = None):
+        """Launch the fused kernel on the current stream.  In: ``self.grad``
+        (local dense grads).  Out: ``self.grad`` (aggregated), ``self.resid``."""
+        self.epoch = self.epoch + 1 if epoch is None else int(epoch)
+        self.ctx.run(self.epoch, PH_ACCUM, PH_END)
+
+    def run_phases(self, begin: int, end: int, epoch: Optional[int] = None):
+        """Debug / unfused chain: run a sub-range of phases (one launch)."""
+        if epoch is not None:
+            self.epoch = int(epoch)
+        self.ctx.run(self.epoch, begin, end)
+
+    def run_unfused(self, epoch: Optional[int] = None):
+        self.epoch = self.epoch + 1 if epoch is None else int(epoch)
+        for ph in range(PH_ACCUM, PH_END):
+            self.ctx.run(self.epoch, ph, ph + 1)
+
+    def slot(self, src_rank: Optional[int] = None, epoch: Optional[int] = None) -> torch.Tensor:
+        """int32 view of the local copy of `src_rank`'s slot for `epoch`."""
+        e = self.epoch if epoch is None else epoch
+        r = self.rank if src_rank is None else src_rank
+        off = ARENA_HDR_WORDS + ((e & 1) * self.world + r) * self.plan.slot_words
+        return self.arena[off:off + self.plan.payload_words]
+
+    def check_status(self):
+        st = self.status.cpu().tolist()
+        if st[0] != 0:
+            raise RuntimeError(f"deepreduce engine error: {STATUS_NAMES.get(st[0], st[0])} (aux={st[1]})")
+
+    def grid(self) -> int:
+        return int(self.ctx.grid())
+
+    # ---- state (checkpoint / resume) ----------------------------
+    def state_dict(self):
+        return {"resid": self.resid.detach().cpu().clone(), "epoch": self.epoch,
+                "sel": self.sel.detach().cpu().clone()}
+
+    def load_state_dict(self, state):
+        self.resid.copy_(state["resid"].to(self.device))
+        self.sel.copy_(state["sel"].to(self.device))
+        self.epoch = int(state["epoch"])
+
+
+# ---------------------------------------------------------------------------
+# exact top-k via the engine's radix select (used by TopKCompressor on CUDA)
+# ---------------------------------------------------------------------------
+_TOPK_CACHE: "OrderedDict[tuple, BucketEngine]" = OrderedDict()
+_TOPK_CACHE_MAX = 64
+
+
+def topk_select_cuda(flat: torch.Tensor, k: int):
+    """(values fp32[k], indices int64[k] ascending) of the k largest |x|."""
+    d = flat.numel()
+    k = max(1, min(int(k), d))
+    key = (d, k, flat.device.index)
+    eng = _TOPK_CACHE.get(key)
+    if eng is None:
+        plan = BucketPlan([d], index=None, ks=[k])
+        eng = BucketEngine(plan, device=flat.device, beta=0.0, gamma=1.0, average=False, use_history=False,
+                           world=1, rank=0)
+        _TOPK_CACHE[key] = eng
+        if len(_TOPK_CACHE) > _TOPK_CACHE_MAX:
+            _TOPK_CACHE.popitem(last=False)
+    else:
+        _TOPK_CACHE.move_to_end(key)
+    tp = eng.plan.tensors[0]
+    with torch.cuda.device(flat.device):
+        eng.grad[:d].copy_(flat.detach().float().flatten())
+        eng.hist.zero_()
+        eng.hist_total.zero_()
+        eng.epoch += 1
+        eng.ctx.run(eng.epoch, PH_ACCUM, PH_EMIT + 1)
+        slot = eng.slot()
+        vals = slot[tp.off_vals:tp.off_vals + k].view(torch.float32).clone()
+        idxs = slot[tp.off_idx:tp.off_idx + k].to(torch.int64)
+    return vals.to(flat.dtype), idxs

@@ -1,0 +1,149 @@
+"""Bucket plan: static layout of a flat gradient bucket and of its compressed slot.
+
+A bucket is a list of tensors flattened back to back (each start aligned to 32
+floats) and cut into ``spec.TILE``-element tiles that never cross a tensor.  The
+"per tensor" semantics of the reference (top-k ratio, bloom sizing ``fpr =
+0.1*K/d``, the ≤1000-element bypass — reference pytorch/deepreduce.py:68,115,
+495-500,511) are preserved per segment; only the launch granularity changes.
+Field order of ``TensorDesc`` mirrors ``ops/csrc/plan.h``.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .. import spec
+
+MODE_RAW, MODE_BLOOM = 0, 1
+POLICY_ID = {"leftmost": 0, "random": 1, "p0": 2}
+SLOT_HEADER_WORDS = 8
+DYN_WORDS = 4
+ARENA_HDR_WORDS = 128
+HIST_BINS = 2048
+ALIGN_ELEMS = 32
+
+
+def _align(x: int, a: int) -> int:
+    return (x + a - 1) // a * a
+
+
+@dataclass
+class TensorPlan:
+    name: str
+    numel: int
+    shape: tuple
+    elem_off: int
+    k: int
+    tile_begin: int
+    n_tiles: int
+    mode: int
+    m_bits: int = 0
+    n_hash: int = 0
+    off_vals: int = 0
+    off_filter: int = 0
+    off_prefix: int = 0
+    off_idx: int = 0
+    val_cap: int = 0
+    salt: int = 0
+    n_filter_words: int = 0
+
+    def words(self) -> List[int]:
+        return [self.elem_off, self.numel, self.k, self.tile_begin, self.n_tiles, self.mode, self.m_bits,
+                self.n_hash, self.off_vals, self.off_filter, self.off_prefix, self.off_idx, self.val_cap,
+                self.salt, self.n_filter_words, 0]
+
+
+@dataclass
+class BucketPlan:
+    numels: Sequence[int]
+    names: Optional[Sequence[str]] = None
+    shapes: Optional[Sequence[tuple]] = None
+    compress_ratio: float = 0.01
+    index: Optional[str] = "bloom"        # 'bloom' or None (plain top-k pairs)
+    fpr: Optional[float] = None
+    policy: str = "leftmost"
+    min_numel: int = spec.SMALL_TENSOR_NUMEL
+    max_hash: int = 16
+    ks: Optional[Sequence[int]] = None    # explicit per-tensor K (overrides compress_ratio)
+    tensors: List[TensorPlan] = field(default_factory=list, init=False)
+
+    def __post_init__(self):
+        if self.policy not in POLICY_ID:
+            raise ValueError(f"fused engine supports policies {list(POLICY_ID)}; got {self.policy!r}")
+        if self.policy == "random":
+            raise NotImplementedError("policy 'random' is served by the per-tensor path, not the fused engine yet")
+        names = list(self.names) if self.names is not None else [f"t{i}" for i in range(len(self.numels))]
+        shapes = list(self.shapes) if self.shapes is not None else [(int(n),) for n in self.numels]
+        elem = 0
+        tile = 0
+        word = SLOT_HEADER_WORDS + DYN_WORDS * len(self.numels)
+        word = _align(word, 4)
+        for i, d in enumerate(self.numels):
+            d = int(d)
+            assert d > 0
+            k = min(d, spec.topk_k(d, self.compress_ratio)) if self.ks is None else max(1, min(d, int(self.ks[i])))
+            n_tiles = (d + spec.TILE - 1) // spec.TILE
+            tp = TensorPlan(name=names[i], numel=d, shape=tuple(shapes[i]), elem_off=elem, k=k, tile_begin=tile,
+                            n_tiles=n_tiles, mode=MODE_RAW, salt=i)
+            if self.index == "bloom" and d > self.min_numel:
+                n_hash, m_bits, n_words = spec.bloom_layout(k, d, self.fpr, self.max_hash)
+                tp.mode = MODE_BLOOM
+                tp.m_bits, tp.n_hash, tp.n_filter_words = m_bits, n_hash, n_words
+                if self.policy == "p0":
+                    fpr = self.fpr if self.fpr is not None else spec.default_fpr(k, d)
+                    tp.val_cap = min(d, k + int(math.ceil(2.0 * fpr * d)) + 64)
+                else:
+                    tp.val_cap = k
+                tp.off_vals = word
+                word = _align(word + tp.val_cap, 4)
+                tp.off_filter = word
+                word = _align(word + n_words, 4)
+                tp.off_prefix = word
+                word = _align(word + n_tiles, 4)
+            else:
+                tp.val_cap = k
+                tp.off_vals = word
+                word = _align(word + k, 4)
+                tp.off_idx = word
+                word = _align(word + k, 4)
+            self.tensors.append(tp)
+            elem = _align(elem + d, ALIGN_ELEMS)
+            tile += n_tiles
+        self.total_elems = _align(elem, ALIGN_ELEMS)
+        self.n_tiles = tile
+        self.payload_words = word
+        self.slot_words = _align(word, 64)
+
+    # ---- device tables -----------------------------------------------------
+    def tensor_table(self) -> torch.Tensor:
+        arr = np.array([t.words() for t in self.tensors], dtype=np.int64).astype(np.uint32).view(np.int32)
+        return torch.from_numpy(arr.reshape(-1).copy())
+
+    def tile_table(self) -> torch.Tensor:
+        out = np.empty(self.n_tiles, dtype=np.int32)
+        for i, t in enumerate(self.tensors):
+            out[t.tile_begin:t.tile_begin + t.n_tiles] = i
+        return torch.from_numpy(out)
+
+    def arena_words(self, world: int) -> int:
+        return ARENA_HDR_WORDS + 2 * world * self.slot_words
+
+    # ---- accounting --------------------------------------------------------
+    def wire_bytes(self) -> int:
+        """Bytes a rank ships per step (the pushed payload)."""
+        return self.payload_words * 4
+
+    def dense_bytes(self) -> int:
+        return sum(t.numel for t in self.tensors) * 4
+
+    def topk_pair_bytes(self) -> int:
+        """What plain top-k (fp32 value + int64 index, GRACE) would ship."""
+        return sum(t.k * 12 for t in self.tensors)
+
+    def views(self, flat: torch.Tensor):
+        """Per-tensor views into a flat bucket buffer."""
+        return [flat[t.elem_off:t.elem_off + t.numel].view(t.shape) for t in self.tensors]
