@@ -131,8 +131,8 @@ def apply_policy_oracle(positives: torch.Tensor, K: int, policy: str, pseed: int
         return positives[:K]
     if policy == "random":
         keys = spec.policy_hash(positives, pseed)
-        comp = (keys << 32) | positives
-        sel = torch.sort(comp).values[:K] & spec.MASK32
+        comp = (keys << 31) | positives          # key-major, index-minor; fits int64 (idx < 2^31)
+        sel = torch.sort(comp).values[:K] & 0x7FFFFFFF
         return torch.sort(sel).values
     return conflict_sets_oracle(positives, K, k, m_bits, seed, pseed)
 

@@ -88,8 +88,8 @@ class RandomKCompressor(Compressor):
         self.global_step += 1
         keys = spec.policy_hash(torch.arange(d, device=flat.device), seed)
         # K smallest keys, ties broken by index: sort on (key << 32 | idx)
-        comp = (keys << 32) | torch.arange(d, device=flat.device)
-        indices = torch.sort(comp).values[:k] & spec.MASK32
+        comp = (keys << 31) | torch.arange(d, device=flat.device)
+        indices = torch.sort(comp).values[:k] & 0x7FFFFFFF
         indices = torch.sort(indices).values
         return (flat[indices], indices), tensor.size()
 

@@ -1,0 +1,212 @@
+"""Bucketed, overlapped data-parallel wrapper — the new entry point next to the
+per-tensor ``grc.step(grad, name)``.
+
+The reference runs strictly after backward, one Python call and 2-3 NCCL
+all_gathers per tensor.  Here parameters are laid out in flat
+fp32 buckets (``p.grad`` are views), autograd post-accumulate hooks mark
+buckets ready during backward, and each ready bucket is handed to a C++
+background thread that launches the fused exchange kernel on a high-priority
+side stream; ``finish()`` makes the optimizer's stream wait on the done events.
+
+CUDA + ('topk' [+ 'index': 'bloom' | plain])  -> fused engine (one kernel/bucket)
+CUDA + 'none'/'allreduce'                     -> dense NCCL all-reduce of the flat bucket
+anything else (CPU/gloo, other codecs)        -> GRACE-compatible per-tensor path
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from .. import spec
+from ..wrappers import deepreduce_from_params
+from .engine import BucketEngine
+from .plan import BucketPlan
+
+
+def _fused_supported(params: dict) -> bool:
+    if params.get('compressor') != 'topk' or params.get('communicator', 'allgather') != 'allgather':
+        return False
+    dr = params.get('deepreduce', None)
+    if dr is None:
+        return True
+    if dr == 'index' and params.get('index', 'bloom') == 'bloom':
+        from ..codecs.bloom import canonical_policy
+        return canonical_policy(params.get('policy', 'leftmost')) in ('leftmost', 'p0')
+    return False
+
+
+class DeepReduceDDP:
+    def __init__(self, module: nn.Module, params: dict, *, bucket_cap_mb: float = 1e9, overlap: bool = True,
+                 group=None, blocks_per_sm: int = 2, use_history: bool = True, background_thread: bool = True):
+        self.module = module
+        self.params = dict(params)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
+        self.device = self.named[0][1].device
+        self.is_cuda = self.device.type == "cuda"
+        self.dense = self.params.get('compressor', 'none') in ('none', None)
+        self.fused = self.is_cuda and not self.dense and _fused_supported(self.params)
+        self.overlap = overlap and self.is_cuda
+        self.step_count = 0
+        self.engines: List[BucketEngine] = []
+        self.flat: List[torch.Tensor] = []
+        self.bucket_of: Dict[int, int] = {}
+        self.pending: List[int] = []
+        self.sched = None
+        self.grc = None
+        self._handles = []
+        if self.fused or (self.dense and self.is_cuda):
+            self._build_buckets(bucket_cap_mb, blocks_per_sm, use_history)
+            if self.fused and self.overlap and background_thread:
+                from .. import ops
+                self.sched = ops.cuda_module().Scheduler(len(self.buckets))
+            if self.overlap:
+                self._install_hooks()
+        else:
+            self.grc = deepreduce_from_params(self.params)
+
+    # ---- bucket construction ------------------------------------------------
+    def _build_buckets(self, cap_mb, blocks_per_sm, use_history):
+        cap = int(cap_mb * 1024 * 1024 / 4)
+        order = list(reversed(self.named))           # roughly the order gradients become ready
+        self.buckets: List[List] = []
+        cur, cur_n = [], 0
+        for n, p in order:
+            if cur and cur_n + p.numel() > cap:
+                self.buckets.append(cur)
+                cur, cur_n = [], 0
+            cur.append((n, p))
+            cur_n += p.numel()
+        if cur:
+            self.buckets.append(cur)
+        from ..codecs.bloom import canonical_policy
+        for b, items in enumerate(self.buckets):
+            numels = [p.numel() for _, p in items]
+            names = [n for n, _ in items]
+            shapes = [tuple(p.shape) for _, p in items]
+            if self.fused:
+                plan = BucketPlan(numels, names, shapes, compress_ratio=self.params.get('compress_ratio', 0.01),
+                                  index='bloom' if self.params.get('deepreduce') == 'index' else None,
+                                  fpr=self.params.get('fpr', None),
+                                  policy=canonical_policy(self.params.get('policy', 'leftmost')),
+                                  min_numel=int(self.params.get('min_numel', spec.SMALL_TENSOR_NUMEL)))
+                residual = self.params.get('memory', 'none') == 'residual'
+                eng = BucketEngine(plan, device=self.device, group=self.group,
+                                   beta=float(self.params.get('beta', 1.0)) if residual else 0.0,
+                                   gamma=float(self.params.get('gamma', 1.0)), average=self.params.get('average', True),
+                                   use_history=use_history, blocks_per_sm=blocks_per_sm)
+                self.engines.append(eng)
+                flat, views = eng.grad, eng.grad_views
+            else:
+                plan = BucketPlan(numels, names, shapes, index=None)
+                flat = torch.zeros(plan.total_elems, dtype=torch.float32, device=self.device)
+                views = plan.views(flat)
+            self.flat.append(flat)
+            for (n, p), v in zip(items, views):
+                assert p.dtype == torch.float32, "flat buckets hold fp32 master gradients"
+                p.grad = v
+                self.bucket_of[id(p)] = b
+        self._ready_count = [0] * len(self.buckets)
+        self._bucket_size = [len(it) for it in self.buckets]
+
+    def _install_hooks(self):
+        for n, p in self.named:
+            self._handles.append(p.register_post_accumulate_grad_hook(self._hook))
+
+    def _hook(self, p):
+        b = self.bucket_of[id(p)]
+        self._ready_count[b] += 1
+        if self._ready_count[b] == self._bucket_size[b]:
+            self._launch_bucket(b)
+
+    def _launch_bucket(self, b):
+        self._ready_count[b] = 0
+        if self.fused:
+            eng = self.engines[b]
+            eng.epoch = self.step_count + 1
+            if self.sched is not None:
+                self.sched.submit(b, eng.ctx, eng.epoch)
+            else:
+                eng.ctx.run(eng.epoch, 0, 9)
+        else:
+            if self.world > 1:
+                self.pending.append(dist.all_reduce(self.flat[b], group=self.group, async_op=True))
+
+    # ---- per-step API ---------------------------------------------------------
+    def zero_grad(self):
+        if self.flat:
+            for f in self.flat:
+                f.zero_()
+        else:
+            for _, p in self.named:
+                p.grad = None
+
+    def finish(self):
+        """Call after backward, before optimizer.step(): gradients become the
+        cross-rank aggregate."""
+        if self.grc is not None:
+            for n, p in self.named:
+                if p.grad is not None:
+                    p.grad = self.grc.step(p.grad, n).view_as(p)
+        elif self.fused:
+            if not self.overlap:
+                for b in range(len(self.buckets)):
+                    self._launch_bucket(b)
+            if self.sched is not None:
+                self.sched.wait_all()
+        else:
+            if not self.overlap:
+                for b in range(len(self.buckets)):
+                    self._launch_bucket(b)
+            for w in self.pending:
+                w.wait()
+            self.pending = []
+            if self.world > 1 and self.params.get('average', True):
+                for f in self.flat:
+                    f.div_(self.world)
+        self.step_count += 1
+
+    def check(self):
+        for e in self.engines:
+            e.check_status()
+
+    # ---- accounting -------------------------------------------------------------
+    def wire_bytes_per_step(self) -> int:
+        if self.fused:
+            return sum(e.plan.wire_bytes() for e in self.engines)
+        if self.dense:
+            return sum(f.numel() * 4 for f in self.flat)
+        return int(self.grc.bytes_sent / max(self.step_count, 1))
+
+    def dense_bytes(self) -> int:
+        return sum(p.numel() * 4 for _, p in self.named)
+
+    # ---- checkpoint / resume -------------------------------------------
+    def state_dict(self):
+        if self.fused:
+            return {"step": self.step_count, "engines": [e.state_dict() for e in self.engines]}
+        if self.grc is not None:
+            return {"step": self.step_count, "memory": self.grc.memory.state_dict()}
+        return {"step": self.step_count}
+
+    def load_state_dict(self, state):
+        self.step_count = int(state.get("step", 0))
+        if self.fused:
+            for e, s in zip(self.engines, state["engines"]):
+                e.load_state_dict(s)
+        elif self.grc is not None and "memory" in state:
+            self.grc.memory.load_state_dict(state["memory"], device=self.device)
+
+    def close(self):
+        for h in self._handles:
+            h.remove()
+        if self.sched is not None:
+            self.sched.shutdown()
+            self.sched = None
+        for e in self.engines:
+            e.close()

@@ -1,0 +1,53 @@
+"""torchrun script: fused P2P engine on W GPUs vs the oracle and vs an NCCL all_gather of the same slots."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    from deepreduce_b200.parallel import BucketEngine, BucketPlan, engine_oracle
+    sizes = [64, 1001, 4097, 36864, 147456, 10, 589824, 2359296]
+    ok = True
+    for index, policy in (("bloom", "leftmost"), ("bloom", "p0"), (None, "leftmost")):
+        plan = BucketPlan(sizes, compress_ratio=0.01, index=index, policy=policy)
+        eng = BucketEngine(plan, device=f"cuda:{local}", spin_limit=4_000_000)
+        resid_refs = [torch.zeros(plan.total_elems) for _ in range(world)]
+        for step in range(3):
+            grads = []
+            for r in range(world):
+                gen = torch.Generator().manual_seed(1000 * step + r)
+                g = torch.zeros(plan.total_elems)
+                for v in plan.views(g):
+                    v.copy_(torch.randn(v.shape, generator=gen))
+                grads.append(g)
+            eng.grad.copy_(grads[rank].cuda())
+            eng.step()
+            torch.cuda.synchronize()
+            eng.check_status()
+            out_ref, resid_refs, slots = engine_oracle(plan, grads, resid_refs, epoch=eng.epoch)
+            same_out = torch.allclose(eng.grad.cpu(), out_ref, atol=1e-6, rtol=1e-6)
+            same_res = torch.equal(eng.resid.cpu(), resid_refs[rank])
+            same_slots = all(np.array_equal(eng.slot(r).cpu().numpy().view(np.uint32), slots[r]) for r in range(world))
+            if not (same_out and same_res and same_slots):
+                ok = False
+                print(f"[rank {rank}] MISMATCH index={index} policy={policy} step={step} out={same_out} res={same_res} slots={same_slots}",
+                      flush=True)
+        eng.close()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0 and int(flag.item()) == 1:
+        print("MULTIGPU_OK", flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

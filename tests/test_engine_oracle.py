@@ -1,0 +1,94 @@
+"""Bucket plan + engine oracle (CPU): the specification the fused kernel is tested against."""
+import numpy as np
+import torch
+
+from deepreduce_b200 import spec
+from deepreduce_b200.parallel import BucketPlan, engine_oracle
+from deepreduce_b200.parallel.engine import select_topk_oracle
+from deepreduce_b200.parallel.plan import MODE_BLOOM, MODE_RAW, SLOT_HEADER_WORDS, DYN_WORDS
+import deepreduce_b200 as dr
+
+SIZES = [64, 1000, 1001, 4096, 4097, 36864, 147456, 10]
+
+
+def test_plan_layout():
+    plan = BucketPlan(SIZES, compress_ratio=0.01)
+    assert [t.mode for t in plan.tensors] == [MODE_RAW, MODE_RAW, MODE_BLOOM, MODE_BLOOM, MODE_BLOOM, MODE_BLOOM, MODE_BLOOM, MODE_RAW]
+    assert plan.n_tiles == sum((d + spec.TILE - 1) // spec.TILE for d in SIZES)
+    tt = plan.tile_table().tolist()
+    for i, t in enumerate(plan.tensors):
+        assert t.elem_off % 32 == 0 and t.k == max(1, int(t.numel * 0.01))
+        assert tt[t.tile_begin:t.tile_begin + t.n_tiles] == [i] * t.n_tiles
+    # regions do not overlap and fit in the payload
+    regions = []
+    for t in plan.tensors:
+        regions.append((t.off_vals, t.val_cap))
+        if t.mode == MODE_BLOOM:
+            regions += [(t.off_filter, t.n_filter_words), (t.off_prefix, t.n_tiles)]
+        else:
+            regions.append((t.off_idx, t.k))
+    regions.sort()
+    assert regions[0][0] >= SLOT_HEADER_WORDS + DYN_WORDS * len(SIZES)
+    for (a, n), (b, _) in zip(regions[:-1], regions[1:]):
+        assert a + n <= b
+    assert regions[-1][0] + regions[-1][1] <= plan.payload_words <= plan.slot_words
+    assert plan.tensor_table().numel() == 16 * len(SIZES)
+    # bloom wire is smaller than plain (fp32,int64) pairs: the paper's headline for index compression
+    assert plan.wire_bytes() < plan.topk_pair_bytes()
+
+
+def test_select_topk_ties_deterministic():
+    x = torch.tensor([0.0, 1.0, -1.0, 1.0, 0.5, -1.0, 2.0])
+    idx, T = select_topk_oracle(x, 3)
+    assert idx.tolist() == [1, 2, 6]                 # 2.0 first, then the two left-most |1.0|
+    x = torch.zeros(100); x[7] = 3.0
+    idx, T = select_topk_oracle(x, 5)
+    assert idx.tolist() == [0, 1, 2, 3, 7] and T == 0
+
+
+def test_oracle_matches_grace_path_single_rank():
+    torch.manual_seed(0)
+    plan = BucketPlan([36864, 500, 9408], compress_ratio=0.01)
+    g = torch.zeros(plan.total_elems)
+    for v in plan.views(g):
+        v.copy_(torch.randn_like(v))
+    out, resids, slots = engine_oracle(plan, [g], [torch.zeros_like(g)])
+    grc = dr.deepreduce_from_params({'compressor': 'topk', 'memory': 'residual', 'communicator': 'allgather',
+                                     'compress_ratio': 0.01, 'deepreduce': 'index', 'index': 'bloom'})
+    for t, v, o, r in zip(plan.tensors, plan.views(g), plan.views(out), plan.views(resids[0])):
+        ref = grc.step(v.clone().flatten(), t.name)
+        assert torch.equal(o.flatten(), ref), t.name              # same S~, same values as the per-tensor API
+        assert torch.equal(r.flatten(), grc.memory.residuals[t.name])
+    assert slots[0][0] == 0xD33B2000 and slots[0].dtype == np.uint32
+
+
+def test_oracle_multi_rank_average_and_residual():
+    torch.manual_seed(1)
+    plan = BucketPlan([20000, 300], compress_ratio=0.02)
+    W = 3
+    grads = [torch.randn(plan.total_elems) for _ in range(W)]
+    for g in grads:                                     # padding must stay zero
+        mask = torch.zeros(plan.total_elems, dtype=torch.bool)
+        for t in plan.tensors:
+            mask[t.elem_off:t.elem_off + t.numel] = True
+        g[~mask] = 0
+    res = [torch.zeros(plan.total_elems) for _ in range(W)]
+    out, new_res, slots = engine_oracle(plan, grads, res)
+    total = sum(g - r for g, r in zip(grads, new_res)) / W
+    assert torch.allclose(out, total, atol=1e-6)        # what was shipped == grad - residual, averaged
+    out2, _, _ = engine_oracle(plan, grads, new_res)
+    assert not torch.equal(out, out2)                   # residual feeds the next step
+
+
+def test_p0_capacity_and_header():
+    torch.manual_seed(2)
+    plan = BucketPlan([50000], compress_ratio=0.01, policy="p0")
+    t = plan.tensors[0]
+    assert t.val_cap > t.k
+    g = torch.randn(plan.total_elems)
+    out, res, slots = engine_oracle(plan, [g], [torch.zeros_like(g)])
+    dyn = SLOT_HEADER_WORDS
+    n_sel, cutoff, thr, n_pos = slots[0][dyn:dyn + 4].tolist()
+    assert n_sel == n_pos and n_sel >= t.k and cutoff == 0xFFFFFFFF
+    true = set(torch.topk(g[:50000].abs(), t.k).indices.tolist())
+    assert true <= set(out[:50000].nonzero().flatten().tolist())        # P0 is lossless w.r.t. top-k

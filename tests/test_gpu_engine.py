@@ -1,0 +1,219 @@
+"""sm_100a kernels vs the plain-torch oracle (GPU).  SURVEY §4 "Golden parity":
+set equality for S~ / bit-exact slots, allclose for values."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from deepreduce_b200 import spec
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "gpurun_out")
+
+
+def _diag(name, text):
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, f"diag_{name}.txt"), "a") as f:
+        f.write(text + "\n")
+
+
+def _fill(plan, gen, kind="randn"):
+    g = torch.zeros(plan.total_elems)
+    for v in plan.views(g):
+        if kind == "randn":
+            v.copy_(torch.randn(v.shape, generator=gen))
+        elif kind == "sparse":          # mostly zeros -> threshold 0, massive ties
+            x = torch.randn(v.shape, generator=gen)
+            x[torch.rand(v.shape, generator=gen) < 0.997] = 0
+            v.copy_(x)
+        elif kind == "ties":            # few distinct magnitudes
+            v.copy_(torch.randint(-3, 4, v.shape, generator=gen).float())
+    return g
+
+
+def _compare_slot(plan, slot_gpu, slot_ref, tag):
+    bad = []
+    a = slot_gpu.cpu().numpy().view(np.uint32)
+    b = slot_ref
+    from deepreduce_b200.parallel.plan import SLOT_HEADER_WORDS, DYN_WORDS, MODE_BLOOM
+    if not np.array_equal(a[:5], b[:5]):
+        bad.append(f"header {a[:5]} vs {b[:5]}")
+    for ti, t in enumerate(plan.tensors):
+        d0 = SLOT_HEADER_WORDS + DYN_WORDS * ti
+        if not np.array_equal(a[d0:d0 + 4], b[d0:d0 + 4]):
+            bad.append(f"{t.name} dyn gpu={a[d0:d0+4].tolist()} ref={b[d0:d0+4].tolist()} (d={t.numel},k={t.k},mode={t.mode})")
+        n_sel = int(b[d0])
+        if t.mode == MODE_BLOOM:
+            fa, fb = a[t.off_filter:t.off_filter + t.n_filter_words], b[t.off_filter:t.off_filter + t.n_filter_words]
+            if not np.array_equal(fa, fb):
+                bad.append(f"{t.name} filter differs in {int((fa != fb).sum())}/{t.n_filter_words} words; popcount gpu={int(np.unpackbits(fa.view(np.uint8)).sum())} ref={int(np.unpackbits(fb.view(np.uint8)).sum())}")
+            pa, pb = a[t.off_prefix:t.off_prefix + t.n_tiles], b[t.off_prefix:t.off_prefix + t.n_tiles]
+            if not np.array_equal(pa, pb):
+                bad.append(f"{t.name} prefix gpu={pa[:8].tolist()} ref={pb[:8].tolist()}")
+        else:
+            ia, ib = a[t.off_idx:t.off_idx + n_sel], b[t.off_idx:t.off_idx + n_sel]
+            if not np.array_equal(ia, ib):
+                bad.append(f"{t.name} raw idx gpu={ia[:8].tolist()} ref={ib[:8].tolist()}")
+        va, vb = a[t.off_vals:t.off_vals + n_sel], b[t.off_vals:t.off_vals + n_sel]
+        if not np.array_equal(va, vb):
+            bad.append(f"{t.name} vals differ in {int((va != vb).sum())}/{n_sel}")
+    if bad:
+        _diag(tag, "\n".join(bad))
+    return bad
+
+
+SIZES = [64, 1000, 1001, 4096, 4097, 36864, 147456, 10, 589824]
+
+
+@pytest.mark.parametrize("kind", ["randn", "sparse", "ties"])
+@pytest.mark.parametrize("index,policy", [("bloom", "leftmost"), ("bloom", "p0"), (None, "leftmost")])
+def test_engine_vs_oracle_single_rank(kind, index, policy):
+    from deepreduce_b200.parallel import BucketEngine, BucketPlan, engine_oracle
+    plan = BucketPlan(SIZES, compress_ratio=0.01, index=index, policy=policy)
+    eng = BucketEngine(plan, device="cuda:0", world=1, rank=0, spin_limit=2_000_000)
+    gen = torch.Generator().manual_seed(0)
+    resid_ref = torch.zeros(plan.total_elems)
+    for step in range(3):                       # step 0: no history; steps 1,2: history lower bound (+fallback)
+        g = _fill(plan, gen, kind) * (0.2 if step == 2 else 1.0)    # step 2 shrinks -> exercises the fallback
+        eng.grad.copy_(g.cuda())
+        if step == 1:
+            eng.run_unfused()                   # the debug chain must agree with the fused launch
+        else:
+            eng.step()
+        torch.cuda.synchronize()
+        eng.check_status()
+        out_ref, new_res, slots = engine_oracle(plan, [g], [resid_ref], epoch=eng.epoch)
+        tag = f"single_{kind}_{index}_{policy}_s{step}"
+        bad = _compare_slot(plan, eng.slot(), slots[0], tag)
+        assert not bad, bad[:4]
+        assert torch.equal(eng.resid.cpu(), new_res[0]), tag
+        assert torch.allclose(eng.grad.cpu(), out_ref, atol=0, rtol=0), tag
+        resid_ref = new_res[0]
+    eng.close()
+
+
+def test_engine_resnet50_shapes_and_volume():
+    from deepreduce_b200.models import resnet50
+    from deepreduce_b200.parallel import BucketEngine, BucketPlan, engine_oracle
+    m = resnet50()
+    named = list(reversed([(n, p) for n, p in m.named_parameters()]))
+    plan = BucketPlan([p.numel() for _, p in named], [n for n, _ in named], compress_ratio=0.01)
+    eng = BucketEngine(plan, device="cuda:0", world=1, rank=0)
+    gen = torch.Generator().manual_seed(1)
+    g = _fill(plan, gen)
+    eng.grad.copy_(g.cuda())
+    eng.step()
+    torch.cuda.synchronize()
+    eng.check_status()
+    out_ref, new_res, slots = engine_oracle(plan, [g], [torch.zeros_like(g)], epoch=1)
+    assert not _compare_slot(plan, eng.slot(), slots[0], "resnet50")
+    assert torch.equal(eng.grad.cpu(), out_ref)
+    assert plan.wire_bytes() < 0.02 * plan.dense_bytes()
+    eng.close()
+
+
+def test_per_tensor_ops_vs_oracle():
+    from deepreduce_b200 import ops
+    from deepreduce_b200.codecs import bloom as B, bitpack, polyfit, qsgd
+    torch.manual_seed(0)
+    d, K = 300000, 3000
+    idx = torch.randperm(d)[:K].sort().values
+    k, m_bits, _ = spec.bloom_layout(K, d)
+    w_ref = B.bloom_insert_oracle(idx, k, m_bits)
+    w = ops.bloom_insert(idx.cuda(), k, m_bits)
+    assert torch.equal(w.cpu(), w_ref)
+    pos_ref = B.bloom_query_oracle(w_ref, d, k, m_bits)
+    assert torch.equal(ops.bloom_select(w, d, K, k, m_bits, "p0").cpu(), pos_ref)
+    assert torch.equal(ops.bloom_select(w, d, K, k, m_bits, "leftmost").cpu(), pos_ref[:K])
+    assert torch.equal(ops.bloom_select(w, d, K, k, m_bits, "random", 9).cpu(),
+                       B.apply_policy_oracle(pos_ref, K, "random", 9))
+    # top-k
+    x = torch.randn(1_000_003)
+    v, i = ops.topk_select(x.cuda(), 5000)
+    ref_i = torch.topk(x.abs(), 5000).indices.sort().values
+    assert torch.equal(i.cpu(), ref_i) and torch.equal(v.cpu(), x[ref_i])
+    # bit packing
+    vals = torch.randint(0, 2 ** 13, (10001,))
+    p = ops.pack_bits(vals.cuda(), 13)
+    assert torch.equal(p.cpu(), bitpack.pack_bits_oracle(vals, 13))
+    assert torch.equal(ops.unpack_bits(p, 10001, 13).cpu(), vals)
+    # qsgd
+    y = torch.randn(5000)
+    lvl, nrm = ops.qsgd_encode(y.cuda(), 127, 512, 77)
+    lvl_ref, nrm_ref = qsgd.qsgd_encode_oracle(y, 127, 512, 77)
+    assert torch.allclose(nrm.cpu(), nrm_ref, rtol=1e-5)
+    assert (lvl.cpu().float() != lvl_ref).sum() <= 5          # rounding-boundary flips from reduction order only
+    assert torch.allclose(ops.qsgd_decode(lvl, nrm, 127, 512).cpu(), qsgd.qsgd_decode_oracle(lvl.cpu(), nrm.cpu(), 127, 512))
+    # polyfit
+    ys = torch.sort(torch.randn(23592), descending=True).values
+    seg = polyfit.get_segments(23592, int((ys > 0).sum()))
+    c = ops.polyfit_fit(ys.cuda(), seg, 5)
+    c_ref = polyfit.polyfit_fit_oracle(ys, seg, 5)
+    fit = ops.polyfit_eval(c, seg, 5, 23592).cpu()
+    fit_ref = polyfit.polyfit_eval_oracle(c_ref, seg, 5)
+    assert torch.allclose(fit, fit_ref, atol=2e-3), float((fit - fit_ref).abs().max())
+    # delta + bp128
+    enc = ops.delta_bp128_encode(idx.cuda())
+    assert torch.equal(ops.delta_bp128_decode(enc, K).cpu(), idx)
+    from deepreduce_b200.codecs.integer import int_encode
+    ref = int_encode(np.diff(idx.numpy().astype(np.uint32), prepend=np.uint32(0)).astype(np.uint32), "bp128")
+    assert np.array_equal(enc.cpu().numpy().view(np.uint32), ref)
+    # input normalisation kernel
+    img = torch.randint(0, 256, (4, 32, 32, 3), dtype=torch.uint8)
+    o = ops.u8_to_nhwc_norm(img.cuda()).float().cpu()
+    m = torch.tensor([0.485, 0.456, 0.406]); s = torch.tensor([0.229, 0.224, 0.225])
+    assert torch.allclose(o, (img.float() / 255 - m) / s, atol=2e-2)
+    assert ops.launch_count() > 0
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(deepreduce='index', index='bloom'), dict(deepreduce='index', index='bloom', policy='p0'),
+    dict(deepreduce='both'), dict(deepreduce='value', value='polyfit'), dict(deepreduce='value', value='qsgd'),
+    dict(deepreduce='index', index='rle'), dict(deepreduce='index', index='integer'), dict()])
+def test_grace_path_cuda_matches_cpu(cfg):
+    import deepreduce_b200 as dr
+    base = {'compressor': 'topk', 'memory': 'residual', 'communicator': 'allgather', 'compress_ratio': 0.01}
+    torch.manual_seed(0)
+    g = torch.randn(147456)
+    out_cpu = dr.deepreduce_from_params(dict(base, **cfg)).step(g.clone(), 'w')
+    out_gpu = dr.deepreduce_from_params(dict(base, **cfg)).step(g.cuda(), 'w').cpu()
+    nz_c, nz_g = out_cpu.nonzero().flatten(), out_gpu.nonzero().flatten()
+    assert torch.equal(nz_c, nz_g)
+    assert torch.allclose(out_cpu, out_gpu, atol=5e-3, rtol=1e-3)
+
+
+def test_trainer_cuda_resnet20_overlap():
+    from deepreduce_b200.models import resnet20
+    from deepreduce_b200.trainer import Trainer
+    torch.manual_seed(0)
+    cfg = {'compressor': 'topk', 'memory': 'residual', 'communicator': 'allgather', 'compress_ratio': 0.01,
+           'deepreduce': 'index', 'index': 'bloom'}
+    tr = Trainer(resnet20().cuda(), cfg, lr=0.05, bucket_cap_mb=0.25)        # several buckets + background thread
+    assert len(tr.ddp.engines) > 1
+    x = torch.randn(32, 3, 32, 32, device="cuda"); y = torch.randint(0, 10, (32,), device="cuda")
+    losses = [float(tr.step(x, target=y)) for _ in range(8)]
+    tr.ddp.check()
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+    xh = torch.randn(32, 3, 32, 32).pin_memory(); yh = torch.randint(0, 10, (32,)).pin_memory()
+    l = tr.step_host((xh,), yh)
+    assert np.isfinite(l) and tr.h2d_bytes == xh.numel() * 4 + yh.numel() * 8
+    tr.close()
+
+
+@pytest.mark.timeout(600)
+def test_multi_gpu_engine():
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    W = min(n, 8)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={W}",
+           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "run_multigpu.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=550)
+    _diag("multigpu", r.stdout[-4000:] + r.stderr[-4000:])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "MULTIGPU_OK" in r.stdout
