@@ -103,14 +103,18 @@ DR_D uint4 ld_stream_u4(const uint4* p) {
 // Grid-wide barrier for a co-resident (cooperative-launch) grid.  `counter`
 // is zeroed by the host before launch; `*epoch` is a per-thread-0 register
 // copy counting barriers passed.
-DR_D void grid_barrier(uint32_t* counter, uint32_t& epoch) {
+DR_D void grid_barrier(uint32_t* counter, uint32_t& epoch, uint32_t* status, uint32_t spin_limit) {
   __syncthreads();
   if (threadIdx.x == 0) {
     epoch += 1;
     const uint32_t target = epoch * gridDim.x;
     __threadfence();
     atomicAdd(counter, 1u);
-    while (ld_acquire_gpu(counter) < target) { __nanosleep(32); }
+    uint32_t spins = 0;
+    while (ld_acquire_gpu(counter) < target) {
+      __nanosleep(32);
+      if (++spins > spin_limit) { atomicExch(status, 4u); break; }   // watchdog: never hang the GPU
+    }
     __threadfence();
   }
   __syncthreads();

@@ -440,7 +440,7 @@ DR_D void phase_emit(const EngineParams& P, Smem& sm) {
 #pragma unroll
       for (int c = 0; c < kPerThread; ++c) {
         const uint32_t e = c * kThreads + threadIdx.x;
-        if (e < n && bloom_test(local0 + e, P.seed, n_hash, m_bits, [&](uint32_t w) { return __ldg(filter + w); }))
+        if (e < n && bloom_test(local0 + e, P.seed, n_hash, m_bits, [&](uint32_t w) { return filter[w]; }))
           flags |= 1u << c;
       }
     } else {
@@ -573,16 +573,15 @@ DR_D void phase_decode(const EngineParams& P, Smem& sm) {
         const uint32_t pre = __ldcg(slot + sm.td.off_prefix + tile_local);
         const uint32_t* filter = slot + sm.td.off_filter;
         const float* vals = reinterpret_cast<const float*>(slot + sm.td.off_vals);
+        if (!(pre < n_sel && local0 <= cutoff)) continue;   // tile-uniform: nothing of rank r lands in this tile
         uint32_t flags = 0;
-        if (pre < n_sel && local0 <= cutoff) {      // tile-uniform: anything left to place here?
 #pragma unroll
-          for (int c = 0; c < kPerThread; ++c) {
-            const uint32_t e = c * kThreads + threadIdx.x;
-            const uint32_t gi = local0 + e;
-            if (e < n && gi <= cutoff &&
-                bloom_test(gi, P.seed, n_hash, m_bits, [&](uint32_t w) { return __ldg(filter + w); }))
-              flags |= 1u << c;
-          }
+        for (int c = 0; c < kPerThread; ++c) {
+          const uint32_t e = c * kThreads + threadIdx.x;
+          const uint32_t gi = local0 + e;
+          if (e < n && gi <= cutoff &&
+              bloom_test(gi, P.seed, n_hash, m_bits, [&](uint32_t w) { return filter[w]; }))
+            flags |= 1u << c;
         }
         uint32_t rank[kPerThread], total;
         tile_rank(flags, sm.s, rank, total);
@@ -640,7 +639,7 @@ __global__ void __launch_bounds__(kThreads, 2) dr_engine_kernel(const __grid_con
       default: ran = false; break;
     }
     // a barrier separates dependent phases; signal->decode needs none (every CTA waits itself)
-    if (ran && ph + 1 < P.phase_end && ph != kPhSignal) grid_barrier(P.barrier, bar_epoch);
+    if (ran && ph + 1 < P.phase_end && ph != kPhSignal) grid_barrier(P.barrier, bar_epoch, P.status, P.spin_limit);
   }
 }
 

@@ -26,7 +26,7 @@ from .plan import (ARENA_HDR_WORDS, DYN_WORDS, HIST_BINS, MODE_BLOOM, MODE_RAW, 
 
 PH_ACCUM, PH_FALLBACK, PH_HIST2, PH_HIST3, PH_INSERT, PH_EMIT, PH_PUSH, PH_SIGNAL, PH_DECODE, PH_END = range(10)
 MAGIC = 0xD33B2000
-STATUS_NAMES = {0: "ok", 1: "look-back watchdog", 2: "peer flag watchdog", 3: "select resolve failed"}
+STATUS_NAMES = {0: "ok", 1: "look-back watchdog", 2: "peer flag watchdog", 3: "select resolve failed", 4: "grid barrier watchdog"}
 
 
 # ---------------------------------------------------------------------------
