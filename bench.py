@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--no-thread", action="store_true")
     ap.add_argument("--bucket-mb", type=float, default=32.0)
-    ap.add_argument("--blocks-per-sm", type=int, default=2)
+    ap.add_argument("--blocks-per-sm", type=int, default=1)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="also time the exchange kernel alone (extra keys)")
     return ap.parse_args()
@@ -341,7 +341,7 @@ def run_reference(args, rank, world, local):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic (fp32 224x224x3, random-init weights)", "impl": "reference",
         "config": {"model": "resnet50 (torchvision)", "global_batch": B * world, "per_gpu_batch": B,
-                   "parallelism": f"dp{world}", "gradient_exchange": args.config, "params": {k: v for k, v in cfg.items() if k != "hash_table"},
+                   "parallelism": f"dp{world}", "gradient_exchange": args.config, "params": {k: v for k, v in cfg.items() if isinstance(v, (str, int, float, bool, type(None)))},
                    "harness": "unmodified reference pytorch/deepreduce.py + GRACE/cupy shims (baseline/), per-tensor grc.step after backward"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": 0, "wall_ms_per_step": wall / args.steps,
     }

@@ -179,35 +179,36 @@ struct Engine {
   EngineParams P{};
   int grid = 0;
   int blocks_per_sm = 2;
+  int dyn_smem = 64 * 1024;
   int device = 0;
 
-  Engine(int64_t tensors, int64_t tile_tensor, int64_t n_tensors, int64_t n_tiles, int64_t slot_words,
+  Engine(int64_t tensors, int64_t tiles, int64_t n_tensors, int64_t n_tiles, int64_t slot_words,
          int64_t payload_words, int64_t grad, int64_t resid, int64_t hist, int64_t hist_total, int64_t sel,
-         int64_t tie_desc, int64_t pos_desc, int64_t tie_prefix, int64_t barrier, int64_t status,
-         std::vector<int64_t> arenas, int rank, int world) {
+         int64_t pos_desc, int64_t barrier, int64_t status, std::vector<int64_t> arenas, int rank, int world) {
     TORCH_CHECK(world <= dr::kMaxWorld && (int)arenas.size() == world, "bad world/arenas");
     P.tensors = reinterpret_cast<const dr::TensorDesc*>(tensors);
-    P.tile_tensor = reinterpret_cast<const uint32_t*>(tile_tensor);
+    P.tiles = reinterpret_cast<const dr::TileInfo*>(tiles);
     P.n_tensors = (uint32_t)n_tensors; P.n_tiles = (uint32_t)n_tiles;
     P.slot_words = (uint32_t)slot_words; P.payload_words = (uint32_t)payload_words;
     P.grad = reinterpret_cast<float*>(grad); P.resid = reinterpret_cast<float*>(resid);
     P.hist = reinterpret_cast<uint32_t*>(hist); P.hist_total = reinterpret_cast<uint32_t*>(hist_total);
     P.sel = reinterpret_cast<dr::SelState*>(sel);
-    P.tie_desc = reinterpret_cast<uint64_t*>(tie_desc); P.pos_desc = reinterpret_cast<uint64_t*>(pos_desc);
-    P.tie_prefix = reinterpret_cast<uint32_t*>(tie_prefix);
+    P.pos_desc = reinterpret_cast<uint64_t*>(pos_desc);
     P.barrier = reinterpret_cast<uint32_t*>(barrier); P.status = reinterpret_cast<uint32_t*>(status);
     for (int i = 0; i < world; ++i) P.arena[i] = reinterpret_cast<uint32_t*>(arenas[i]);
     P.rank = rank; P.world = world;
     P.beta = 1.f; P.gamma = 1.f; P.scale = 1.f / world; P.seed = dr::kDefaultSeed; P.policy = 0; P.use_history = 1;
     P.spin_limit = 20u * 1000u * 1000u;
+    P.filter_smem_words = (uint32_t)(dyn_smem / 4);
     cudaGetDevice(&device);
   }
 
   void configure(double beta, double gamma, double scale, int64_t seed, int policy, int use_history, int64_t spin_limit,
-                 int bps) {
+                 int bps, int64_t filter_smem_bytes) {
     P.beta = (float)beta; P.gamma = (float)gamma; P.scale = (float)scale; P.seed = (uint32_t)seed;
     P.policy = policy; P.use_history = use_history; P.spin_limit = (uint32_t)spin_limit;
     blocks_per_sm = bps; grid = 0;
+    dyn_smem = (int)filter_smem_bytes; P.filter_smem_words = (uint32_t)(dyn_smem / 4);
   }
 
   void set_buffers(int64_t grad, int64_t resid) {
@@ -215,14 +216,14 @@ struct Engine {
   }
 
   int get_grid() {
-    if (grid == 0) grid = dr::engine_max_grid(blocks_per_sm);
+    if (grid == 0) grid = dr::engine_max_grid(blocks_per_sm, dyn_smem);
     return grid;
   }
 
   void run_on(uint32_t epoch, int phase_begin, int phase_end, cudaStream_t st) {
     EngineParams Q = P;
     Q.epoch = epoch; Q.phase_begin = phase_begin; Q.phase_end = phase_end;
-    cudaError_t e = dr::engine_launch(Q, get_grid(), st);
+    cudaError_t e = dr::engine_launch(Q, get_grid(), blocks_per_sm, dyn_smem, st);
     TORCH_CHECK(e == cudaSuccess, "engine launch failed: ", cudaGetErrorString(e));
   }
 
@@ -374,10 +375,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.attr("ARENA_HDR_WORDS") = dr::kArenaHdrWords;
   m.attr("SLOT_HEADER_WORDS") = dr::kSlotHeaderWords;
   m.attr("HIST_BINS") = dr::kHistBins;
+  m.attr("NUM_HIST") = dr::kNumHist;
+  m.attr("PH_END") = (int)dr::kPhEnd;
 
   py::class_<Engine>(m, "Engine")
       .def(py::init<int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t,
-                    int64_t, int64_t, int64_t, int64_t, int64_t, std::vector<int64_t>, int, int>())
+                    int64_t, int64_t, int64_t, std::vector<int64_t>, int, int>())
       .def("configure", &Engine::configure)
       .def("set_buffers", &Engine::set_buffers)
       .def("grid", &Engine::get_grid)

@@ -3,12 +3,12 @@
 // One persistent, cooperatively-launched kernel runs the whole per-bucket
 // gradient exchange:
 //
-//   accumulate residual -> exact per-tensor top-k threshold (3-digit radix
-//   select on |g| bits, history-guided lower bound) -> bloom insert ->
-//   universe query + ordered compaction + FP-aware value gather + residual
-//   update -> P2P store of the compressed slot into every peer's arena over
-//   NVLink -> release/acquire flags -> membership-test decode of all W slots,
-//   rank->value, sum, scale, one dense write.
+//   accumulate residual -> per-tensor top-k threshold (2-digit radix select on
+//   |g| bits, history-guided lower bound) -> bloom insert -> universe query +
+//   ordered compaction + FP-aware value gather + residual update -> P2P store
+//   of the compressed slot into every peer's arena over NVLink -> release /
+//   acquire flags -> membership-test decode of all W slots, rank->value, sum,
+//   scale, dense write.
 //
 // It replaces, per tensor, the reference's chain: GRACE residual add, torch.topk,
 // Bloomfilter.add/query/policy (reference pytorch/deepreduce.py:457-492,506-533),
@@ -17,9 +17,16 @@
 // one at a time (phase_begin/phase_end) — the "unfused chain" debug mode.
 //
 // Work decomposition: the bucket is cut into 4096-element tiles that never
-// cross a tensor; CTA b owns tiles b, b+G, b+2G, ... (increasing order, grid
-// co-resident), which makes the decoupled look-back used for ordered ranks
-// deadlock-free.
+// cross a tensor.  Encode phases give CTA b the tiles b, b+G, b+2G, ...
+// (increasing order, grid co-resident => the decoupled look-back used for
+// ordered ranks is deadlock-free and has a short window); the decode phase
+// gives every CTA a contiguous tile range so a staged filter is reused.
+//
+// Latency structure (from the first ncu capture, profiles/): the streaming
+// passes software-prefetch the next tile while the current one is binned;
+// bloom filters are staged in shared memory (<= 64 KB covers every ResNet-50
+// tensor) and probed 8 elements at a time so 8 independent LDS are in flight
+// per thread instead of one dependent L1 gather.
 #include "common.cuh"
 #include "plan.h"
 
@@ -36,6 +43,7 @@ namespace {
 
 constexpr uint32_t kFlagAgg = 1u, kFlagInc = 2u;
 constexpr uint32_t kErrLookback = 1u, kErrPeerWait = 2u, kErrResolve = 3u;
+constexpr uint32_t kNoTensor = 0xFFFFFFFFu;
 
 struct ScanSmem {
   uint32_t cnt[2][kPerThread * kWarps + 4];   // double-buffered tile_rank scratch (+ total)
@@ -54,6 +62,8 @@ struct Smem {
   TensorDesc td;                              // current tensor
 };
 
+extern __shared__ __align__(16) uint32_t g_filter_smem[];   // dynamic: staged bloom filter
+
 DR_D uint32_t* slot_ptr(uint32_t* arena, const EngineParams& P, uint32_t parity, int src) {
   return arena + kArenaHdrWords + (size_t)(parity * (uint32_t)P.world + (uint32_t)src) * P.slot_words;
 }
@@ -62,12 +72,17 @@ DR_D uint64_t pack_desc(uint32_t epoch, uint32_t flag, uint32_t value) {
   return ((uint64_t)(epoch & 0x3FFFFFFFu) << 34) | ((uint64_t)flag << 32) | (uint64_t)value;
 }
 
+DR_D TileInfo load_tile(const EngineParams& P, uint32_t tile) {
+  const uint4 q = __ldg(reinterpret_cast<const uint4*>(P.tiles) + tile);
+  TileInfo t; t.tensor = q.x; t.base = q.y; t.n = q.z; t.local0 = q.w;
+  return t;
+}
+
 DR_D void load_tensor(const EngineParams& P, uint32_t t, Smem& sm) {
-  // 16 threads copy the 16-word descriptor
   __syncthreads();
   if (threadIdx.x < 16) {
     reinterpret_cast<uint32_t*>(&sm.td)[threadIdx.x] =
-        reinterpret_cast<const uint32_t*>(P.tensors + t)[threadIdx.x];
+        __ldg(reinterpret_cast<const uint32_t*>(P.tensors + t) + threadIdx.x);
   }
   __syncthreads();
 }
@@ -89,8 +104,7 @@ DR_D void tile_rank(uint32_t flags, ScanSmem& s, uint32_t (&rank)[kPerThread], u
   }
   __syncthreads();
   if (warp == 0) {
-    // 128 counters, 4 per lane
-    uint32_t v[4], sum = 0;
+    uint32_t v[4], sum = 0;                   // 128 counters, 4 per lane
 #pragma unroll
     for (int i = 0; i < 4; ++i) { v[i] = s.cnt[buf][lane * 4 + i]; sum += v[i]; }
     uint32_t incl = sum;
@@ -168,9 +182,8 @@ DR_D uint32_t lookback(const EngineParams& P, uint64_t* desc, uint32_t tile, uin
 
 // ---------------------------------------------------------------------------
 // radix-select digit resolve: find the bin holding the k-th largest key.
-// H has `nbins` counters (bin index = digit value).  Result in s.res:
-//   res[0] = bin (0xFFFFFFFF if total < k), res[1] = k remaining inside bin,
-//   res[2] = count in bin.
+// Result in s.res: [0] bin (0xFFFFFFFF if total < k), [1] k remaining inside
+// the bin, [2] count in the bin.
 // ---------------------------------------------------------------------------
 DR_D void resolve_bins(const uint32_t* __restrict__ H, int nbins, uint32_t k, ScanSmem& s) {
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -206,10 +219,10 @@ DR_D void resolve_bins(const uint32_t* __restrict__ H, int nbins, uint32_t k, Sc
   __syncthreads();
 }
 
-DR_D void flush_hist(uint32_t* __restrict__ gh, uint32_t* __restrict__ gtotal, Smem& sm, int nbins) {
+DR_D void flush_hist(uint32_t* __restrict__ gh, uint32_t* __restrict__ gtotal, Smem& sm) {
   __syncthreads();
   uint32_t part = 0;
-  for (int j = threadIdx.x; j < nbins; j += kThreads) {
+  for (int j = threadIdx.x; j < kHistBins; j += kThreads) {
     const uint32_t v = sm.u.hist[j];
     if (v) { atomicAdd(gh + j, v); part += v; sm.u.hist[j] = 0; }
   }
@@ -228,189 +241,240 @@ DR_D uint32_t* hist_ptr(const EngineParams& P, int which, uint32_t t) {
   return P.hist + ((size_t)which * P.n_tensors + t) * kHistBins;
 }
 
+// stage a bloom filter (global, 16-byte aligned) into the dynamic SMEM buffer
+DR_D void stage_filter(const uint32_t* __restrict__ filter, uint32_t n_words) {
+  __syncthreads();                              // previous users of the buffer are done
+  const uint4* src = reinterpret_cast<const uint4*>(filter);
+  uint4* dst = reinterpret_cast<uint4*>(g_filter_smem);
+  const uint32_t n4 = (n_words + 3u) >> 2;
+  for (uint32_t i = threadIdx.x; i < n4; i += kThreads) dst[i] = src[i];
+  __syncthreads();
+}
+
+// Membership test of 8 elements per thread with the probes of all live
+// elements issued together (8 independent loads in flight).  `valid` marks the
+// elements to test; returns the mask of positives.
+template <typename LoadFn>
+DR_D uint32_t bloom_test8(uint32_t idx0, uint32_t valid, uint32_t seed, uint32_t n_hash, uint32_t m_bits, LoadFn ld) {
+  uint32_t a[kPerThread], b[kPerThread];
+#pragma unroll
+  for (int c = 0; c < kPerThread; ++c) {
+    const HashAB h = hash_ab(idx0 + c * kThreads, seed);
+    a[c] = h.a; b[c] = h.b;
+  }
+  uint32_t alive = valid;
+  for (uint32_t j = 0; j < n_hash && alive; ++j) {
+    uint32_t w[kPerThread];
+#pragma unroll
+    for (int c = 0; c < kPerThread; ++c) {
+      const uint32_t pos = mulhi32(a[c], m_bits);
+      w[c] = ((alive >> c) & 1u) ? (ld(pos >> 5) >> (pos & 31u)) : 0u;
+      a[c] += b[c];
+    }
+#pragma unroll
+    for (int c = 0; c < kPerThread; ++c)
+      if (!(w[c] & 1u)) alive &= ~(1u << c);
+  }
+  return alive;
+}
+
 // ===========================================================================
-// phase 0: accumulate + hist pass 1
+// phase 0: accumulate + hist digit 1
 // ===========================================================================
 DR_D void phase_accum(const EngineParams& P, Smem& sm) {
   const uint32_t parity = P.epoch & 1u;
   uint32_t* my_slot = slot_ptr(P.arena[P.rank], P, parity, P.rank);
-  // zero the outgoing slot (filters, headers, prefix tables)
-  {
+  {  // zero the outgoing slot (filters, headers, prefix tables)
     uint4* p = reinterpret_cast<uint4*>(my_slot);
     const uint32_t n4 = (P.payload_words + 3u) >> 2;
     const uint4 z = make_uint4(0, 0, 0, 0);
     for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n4; i += gridDim.x * kThreads) p[i] = z;
   }
   clear_hist(sm);
-  uint32_t cur = 0xFFFFFFFFu, lower = 0;
   const bool has_resid = (P.beta != 0.0f);
-  for (uint32_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-    const uint32_t t = P.tile_tensor[tile];
-    if (t != cur) {
-      if (cur != 0xFFFFFFFFu) flush_hist(hist_ptr(P, 0, cur), P.hist_total + cur, sm, kHistBins);
-      load_tensor(P, t, sm);
-      cur = t;
-      const uint32_t prev = P.use_history ? P.sel[t].prev_thr : 0u;
-      lower = (prev > (1u << 23)) ? prev - (1u << 23) : 0u;   // half of last step's threshold
-    }
-    const uint32_t local0 = (tile - sm.td.tile_begin) * kTile;
-    const uint32_t n = min((uint32_t)kTile, sm.td.numel - local0);
-    const size_t base = (size_t)sm.td.elem_off + local0;
+  uint32_t cur = kNoTensor, lower = 0;
+  uint32_t tile = blockIdx.x;
+  if (tile >= P.n_tiles) return;
+  TileInfo ti = load_tile(P, tile);
+  float4 g[2], r[2];
+  auto issue = [&](const TileInfo& t, float4 (&gg)[2], float4 (&rr)[2]) {
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       const uint32_t e = (c * kThreads + threadIdx.x) * 4u;
-      if (e < n) {
-        float4 g = ld_stream_f4(reinterpret_cast<const float4*>(P.grad + base + e));
+      if (e < t.n) {
+        gg[c] = ld_stream_f4(reinterpret_cast<const float4*>(P.grad + t.base + e));
+        if (has_resid) rr[c] = ld_stream_f4(reinterpret_cast<const float4*>(P.resid + t.base + e));
+      }
+    }
+  };
+  issue(ti, g, r);
+  while (true) {
+    const uint32_t next = tile + gridDim.x;
+    TileInfo tn = ti;
+    float4 gn[2], rn[2];
+    const bool has_next = next < P.n_tiles;
+    if (has_next) { tn = load_tile(P, next); issue(tn, gn, rn); }     // prefetch before binning the current tile
+    if (ti.tensor != cur) {
+      if (cur != kNoTensor) flush_hist(hist_ptr(P, 0, cur), P.hist_total + cur, sm);
+      cur = ti.tensor;
+      const uint32_t prev = P.use_history ? __ldcg(&P.sel[cur].prev_thr) : 0u;
+      lower = (prev > (1u << 23)) ? prev - (1u << 23) : 0u;           // half of last step's threshold
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const uint32_t e = (c * kThreads + threadIdx.x) * 4u;
+      if (e < ti.n) {
         float4 a;
         if (has_resid) {
-          const float4 r = ld_stream_f4(reinterpret_cast<const float4*>(P.resid + base + e));
-          a.x = P.beta * r.x + P.gamma * g.x; a.y = P.beta * r.y + P.gamma * g.y;
-          a.z = P.beta * r.z + P.gamma * g.z; a.w = P.beta * r.w + P.gamma * g.w;
+          a.x = P.beta * r[c].x + P.gamma * g[c].x; a.y = P.beta * r[c].y + P.gamma * g[c].y;
+          a.z = P.beta * r[c].z + P.gamma * g[c].z; a.w = P.beta * r[c].w + P.gamma * g[c].w;
         } else {
-          a.x = P.gamma * g.x; a.y = P.gamma * g.y; a.z = P.gamma * g.z; a.w = P.gamma * g.w;
+          a.x = P.gamma * g[c].x; a.y = P.gamma * g[c].y; a.z = P.gamma * g[c].z; a.w = P.gamma * g[c].w;
         }
-        *reinterpret_cast<float4*>(P.resid + base + e) = a;
+        *reinterpret_cast<float4*>(P.resid + ti.base + e) = a;
         const uint32_t k0 = __float_as_uint(a.x) & 0x7FFFFFFFu, k1 = __float_as_uint(a.y) & 0x7FFFFFFFu;
         const uint32_t k2 = __float_as_uint(a.z) & 0x7FFFFFFFu, k3 = __float_as_uint(a.w) & 0x7FFFFFFFu;
         if (k0 >= lower) atomicAdd(&sm.u.hist[k0 >> 20], 1u);
-        if (e + 1 < n && k1 >= lower) atomicAdd(&sm.u.hist[k1 >> 20], 1u);
-        if (e + 2 < n && k2 >= lower) atomicAdd(&sm.u.hist[k2 >> 20], 1u);
-        if (e + 3 < n && k3 >= lower) atomicAdd(&sm.u.hist[k3 >> 20], 1u);
+        if (e + 1 < ti.n && k1 >= lower) atomicAdd(&sm.u.hist[k1 >> 20], 1u);
+        if (e + 2 < ti.n && k2 >= lower) atomicAdd(&sm.u.hist[k2 >> 20], 1u);
+        if (e + 3 < ti.n && k3 >= lower) atomicAdd(&sm.u.hist[k3 >> 20], 1u);
       }
     }
+    if (!has_next) break;
+    tile = next; ti = tn;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) { g[c] = gn[c]; r[c] = rn[c]; }
   }
-  if (cur != 0xFFFFFFFFu) flush_hist(hist_ptr(P, 0, cur), P.hist_total + cur, sm, kHistBins);
+  if (cur != kNoTensor) flush_hist(hist_ptr(P, 0, cur), P.hist_total + cur, sm);
 }
 
-// generic "histogram one digit of the keys matching a prefix" pass over resid
+// generic "histogram one digit of the keys" pass over resid with tile prefetch
+//   kWhich 1: digit-1 fallback (all keys, digit = key>>20) for tensors whose history bound was unsafe
+//   kWhich 2: digit 2 (keys with key>>20 == bin1, digit = (key>>9) & 0x7FF)
 template <int kWhich>
 DR_D void hist_tiles(const EngineParams& P, Smem& sm) {
-  // kWhich: 1 = pass-1 fallback (all keys, digit = key>>20)
-  //         2 = pass 2 (keys with key>>20 == bin1, digit = (key>>9)&0x7FF)
-  //         3 = pass 3 (keys with key>>9 == prefix22, digit = key & 0x1FF)
   clear_hist(sm);
-  uint32_t cur = 0xFFFFFFFFu;
+  uint32_t cur = kNoTensor;
   bool active = false;
   uint32_t prefix = 0;
-  for (uint32_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-    const uint32_t t = P.tile_tensor[tile];
-    if (t != cur) {
-      if (cur != 0xFFFFFFFFu && active)
-        flush_hist(hist_ptr(P, kWhich, cur), P.hist_total + (size_t)kWhich * P.n_tensors + cur, sm,
-                   kWhich == 3 ? 512 : kHistBins);
-      load_tensor(P, t, sm);
-      cur = t;
-      const bool unsafe = P.use_history && (__ldcg(P.hist_total + t) < sm.td.k);
-      if (kWhich == 1) {
-        active = unsafe;
-      } else if (kWhich == 2) {
-        resolve_bins(hist_ptr(P, unsafe ? 1 : 0, t), kHistBins, sm.td.k, sm.s);
-        prefix = sm.s.res[0];
-        if (tile == sm.td.tile_begin && threadIdx.x == 0) {
-          P.sel[t].bin1 = sm.s.res[0]; P.sel[t].krem1 = sm.s.res[1];
-          if (sm.s.res[0] == 0xFFFFFFFFu) atomicExch(P.status, kErrResolve);
-        }
-        active = true;
-        __syncthreads();
-      } else {
-        const uint32_t bin1 = __ldcg(&P.sel[t].bin1), krem1 = __ldcg(&P.sel[t].krem1);
-        resolve_bins(hist_ptr(P, 2, t), kHistBins, krem1, sm.s);
-        prefix = (bin1 << 11) | sm.s.res[0];
-        if (tile == sm.td.tile_begin && threadIdx.x == 0) {
-          P.sel[t].bin2 = sm.s.res[0]; P.sel[t].krem2 = sm.s.res[1];
-          if (sm.s.res[0] == 0xFFFFFFFFu) atomicExch(P.status, kErrResolve);
-        }
-        active = true;
-        __syncthreads();
-      }
-    }
-    if (!active) continue;
-    const uint32_t local0 = (tile - sm.td.tile_begin) * kTile;
-    const uint32_t n = min((uint32_t)kTile, sm.td.numel - local0);
-    const size_t base = (size_t)sm.td.elem_off + local0;
+  uint32_t tile = blockIdx.x;
+  if (tile >= P.n_tiles) return;
+  TileInfo ti = load_tile(P, tile);
+  uint4 q[2];
+  auto issue = [&](const TileInfo& t, uint4 (&qq)[2]) {
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       const uint32_t e = (c * kThreads + threadIdx.x) * 4u;
-      if (e < n) {
-        const uint4 q = ld_stream_u4(reinterpret_cast<const uint4*>(P.resid + base + e));
-        const uint32_t key[4] = {q.x & 0x7FFFFFFFu, q.y & 0x7FFFFFFFu, q.z & 0x7FFFFFFFu, q.w & 0x7FFFFFFFu};
+      if (e < t.n) qq[c] = ld_stream_u4(reinterpret_cast<const uint4*>(P.resid + t.base + e));
+    }
+  };
+  if (kWhich == 2) issue(ti, q);
+  while (true) {
+    const uint32_t next = tile + gridDim.x;
+    const bool has_next = next < P.n_tiles;
+    TileInfo tn = ti;
+    uint4 qn[2];
+    if (has_next) { tn = load_tile(P, next); if (kWhich == 2) issue(tn, qn); }
+    if (ti.tensor != cur) {
+      if (cur != kNoTensor && active)
+        flush_hist(hist_ptr(P, kWhich, cur), P.hist_total + (size_t)kWhich * P.n_tensors + cur, sm);
+      cur = ti.tensor;
+      load_tensor(P, cur, sm);
+      const bool unsafe = P.use_history && (__ldcg(P.hist_total + cur) < sm.td.k);
+      if (kWhich == 1) {
+        active = unsafe;
+      } else {
+        resolve_bins(hist_ptr(P, unsafe ? 1 : 0, cur), kHistBins, sm.td.k, sm.s);
+        prefix = sm.s.res[0];
+        if (tile == sm.td.tile_begin && threadIdx.x == 0) {
+          P.sel[cur].bin1 = sm.s.res[0]; P.sel[cur].krem1 = sm.s.res[1];
+          if (sm.s.res[0] == 0xFFFFFFFFu) atomicExch(P.status, kErrResolve);
+        }
+        active = true;
+        __syncthreads();
+      }
+    }
+    if (active) {
+      if (kWhich == 1) issue(ti, q);            // rare path: no prefetch
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (e + i < n) {
-            if (kWhich == 1) atomicAdd(&sm.u.hist[key[i] >> 20], 1u);
-            else if (kWhich == 2) { if ((key[i] >> 20) == prefix) atomicAdd(&sm.u.hist[(key[i] >> 9) & 0x7FFu], 1u); }
-            else { if ((key[i] >> 9) == prefix) atomicAdd(&sm.u.hist[key[i] & 0x1FFu], 1u); }
+      for (int c = 0; c < 2; ++c) {
+        const uint32_t e = (c * kThreads + threadIdx.x) * 4u;
+        if (e < ti.n) {
+          const uint32_t key[4] = {q[c].x & 0x7FFFFFFFu, q[c].y & 0x7FFFFFFFu, q[c].z & 0x7FFFFFFFu, q[c].w & 0x7FFFFFFFu};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (e + i < ti.n) {
+              if (kWhich == 1) atomicAdd(&sm.u.hist[key[i] >> 20], 1u);
+              else if ((key[i] >> 20) == prefix) atomicAdd(&sm.u.hist[(key[i] >> 9) & 0x7FFu], 1u);
+            }
           }
         }
       }
     }
+    if (!has_next) break;
+    tile = next; ti = tn;
+    q[0] = qn[0]; q[1] = qn[1];
   }
-  if (cur != 0xFFFFFFFFu && active)
-    flush_hist(hist_ptr(P, kWhich, cur), P.hist_total + (size_t)kWhich * P.n_tensors + cur, sm,
-               kWhich == 3 ? 512 : kHistBins);
+  if (cur != kNoTensor && active)
+    flush_hist(hist_ptr(P, kWhich, cur), P.hist_total + (size_t)kWhich * P.n_tensors + cur, sm);
 }
 
 // ===========================================================================
-// phase 4: threshold resolve + bloom insert
+// phase 3: threshold resolve + bloom insert
 // ===========================================================================
 DR_D void phase_insert(const EngineParams& P, Smem& sm) {
   const uint32_t parity = P.epoch & 1u;
   uint32_t* my_slot = slot_ptr(P.arena[P.rank], P, parity, P.rank);
-  uint32_t cur = 0xFFFFFFFFu, T = 0, need = 0, ties_total = 0;
-  for (uint32_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-    const uint32_t t = P.tile_tensor[tile];
-    if (t != cur) {
-      load_tensor(P, t, sm);
-      cur = t;
-      const uint32_t bin1 = __ldcg(&P.sel[t].bin1), bin2 = __ldcg(&P.sel[t].bin2);
-      const uint32_t krem2 = __ldcg(&P.sel[t].krem2);
-      resolve_bins(hist_ptr(P, 3, t), 512, krem2, sm.s);
-      T = (((bin1 << 11) | bin2) << 9) | sm.s.res[0];
-      need = sm.s.res[1];
-      ties_total = sm.s.res[2];
+  uint32_t cur = kNoTensor, T22 = 1;
+  uint32_t tile = blockIdx.x;
+  if (tile >= P.n_tiles) return;
+  TileInfo ti = load_tile(P, tile);
+  uint32_t v[kPerThread];
+  auto issue = [&](const TileInfo& t, uint32_t (&vv)[kPerThread]) {
+#pragma unroll
+    for (int c = 0; c < kPerThread; ++c) {
+      const uint32_t e = c * kThreads + threadIdx.x;
+      vv[c] = (e < t.n) ? __float_as_uint(__ldcg(P.resid + t.base + e)) : 0u;
+    }
+  };
+  issue(ti, v);
+  while (true) {
+    const uint32_t next = tile + gridDim.x;
+    const bool has_next = next < P.n_tiles;
+    TileInfo tn = ti;
+    uint32_t vn[kPerThread];
+    if (has_next) { tn = load_tile(P, next); issue(tn, vn); }
+    if (ti.tensor != cur) {
+      cur = ti.tensor;
+      load_tensor(P, cur, sm);
+      const uint32_t bin1 = __ldcg(&P.sel[cur].bin1), krem1 = __ldcg(&P.sel[cur].krem1);
+      resolve_bins(hist_ptr(P, 2, cur), kHistBins, krem1, sm.s);
+      T22 = max((bin1 << 11) | sm.s.res[0], 1u);
       if (tile == sm.td.tile_begin && threadIdx.x == 0) {
-        P.sel[t].thr = T; P.sel[t].need = need; P.sel[t].ties_total = ties_total;
+        P.sel[cur].bin2 = sm.s.res[0]; P.sel[cur].krem2 = sm.s.res[1];
+        P.sel[cur].thr = T22 << 9; P.sel[cur].n_ge = sm.s.res[2];
         if (sm.s.res[0] == 0xFFFFFFFFu) atomicExch(P.status, kErrResolve);
       }
       __syncthreads();
     }
-    const uint32_t local0 = (tile - sm.td.tile_begin) * kTile;
-    const uint32_t n = min((uint32_t)kTile, sm.td.numel - local0);
-    const size_t base = (size_t)sm.td.elem_off + local0;
-    const bool ordered_ties = (ties_total != need);
-    uint32_t gt = 0, eq = 0;
-#pragma unroll
-    for (int c = 0; c < kPerThread; ++c) {
-      const uint32_t e = c * kThreads + threadIdx.x;
-      if (e < n) {
-        const uint32_t key = __float_as_uint(__ldcg(P.resid + base + e)) & 0x7FFFFFFFu;
-        if (key > T) gt |= 1u << c;
-        else if (key == T) eq |= 1u << c;
-      }
-    }
-    uint32_t take = gt;
-    if (!ordered_ties) {
-      take |= eq;
-    } else {
-      uint32_t rank[kPerThread], total;
-      tile_rank(eq, sm.s, rank, total);
-      const uint32_t excl = lookback(P, P.tie_desc, tile, sm.td.tile_begin, total, sm.s);
-      if (threadIdx.x == 0) P.tie_prefix[tile] = excl;
-#pragma unroll
-      for (int c = 0; c < kPerThread; ++c)
-        if (((eq >> c) & 1u) && excl + rank[c] < need) take |= 1u << c;
-    }
     if (sm.td.mode == kModeBloom) {
       uint32_t* filter = my_slot + sm.td.off_filter;
+      const uint32_t n_hash = sm.td.n_hash, m_bits = sm.td.m_bits;
 #pragma unroll
-      for (int c = 0; c < kPerThread; ++c)
-        if ((take >> c) & 1u) bloom_set(filter, local0 + c * kThreads + threadIdx.x, P.seed, sm.td.n_hash, sm.td.m_bits);
+      for (int c = 0; c < kPerThread; ++c) {
+        const uint32_t e = c * kThreads + threadIdx.x;
+        if (e < ti.n && ((v[c] & 0x7FFFFFFFu) >> 9) >= T22) bloom_set(filter, ti.local0 + e, P.seed, n_hash, m_bits);
+      }
     }
+    if (!has_next) break;
+    tile = next; ti = tn;
+#pragma unroll
+    for (int c = 0; c < kPerThread; ++c) v[c] = vn[c];
   }
 }
 
 // ===========================================================================
-// phase 5: universe query + ordered compaction + value gather + residual update
+// phase 4: universe query + ordered compaction + value gather + residual update
 // ===========================================================================
 DR_D void phase_emit(const EngineParams& P, Smem& sm) {
   const uint32_t parity = P.epoch & 1u;
@@ -419,50 +483,40 @@ DR_D void phase_emit(const EngineParams& P, Smem& sm) {
     my_slot[0] = kMagic; my_slot[1] = P.epoch; my_slot[2] = P.n_tensors; my_slot[3] = P.payload_words;
     my_slot[4] = (uint32_t)P.rank;
   }
-  uint32_t cur = 0xFFFFFFFFu, T = 0, need = 0, ties_total = 0;
+  uint32_t cur = kNoTensor, T22 = 1;
+  bool staged = false;
   for (uint32_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-    const uint32_t t = P.tile_tensor[tile];
-    if (t != cur) {
-      load_tensor(P, t, sm);
-      cur = t;
-      T = __ldcg(&P.sel[t].thr); need = __ldcg(&P.sel[t].need); ties_total = __ldcg(&P.sel[t].ties_total);
+    const TileInfo ti = load_tile(P, tile);
+    if (ti.tensor != cur) {
+      cur = ti.tensor;
+      load_tensor(P, cur, sm);
+      T22 = __ldcg(&P.sel[cur].thr) >> 9;
+      staged = false;
+      if (sm.td.mode == kModeBloom && sm.td.n_filter_words <= P.filter_smem_words) {
+        stage_filter(my_slot + sm.td.off_filter, sm.td.n_filter_words);
+        staged = true;
+      }
     }
     const uint32_t tile_local = tile - sm.td.tile_begin;
-    const uint32_t local0 = tile_local * kTile;
-    const uint32_t n = min((uint32_t)kTile, sm.td.numel - local0);
-    const size_t base = (size_t)sm.td.elem_off + local0;
-    DynHeader* dyn = reinterpret_cast<DynHeader*>(my_slot + kSlotHeaderWords) + t;
+    const uint32_t n = ti.n, local0 = ti.local0;
+    const size_t base = ti.base;
+    DynHeader* dyn = reinterpret_cast<DynHeader*>(my_slot + kSlotHeaderWords) + cur;
     const bool last_tile = (tile_local + 1 == sm.td.n_tiles);
+    uint32_t valid = 0;
+#pragma unroll
+    for (int c = 0; c < kPerThread; ++c) if (c * kThreads + threadIdx.x < n) valid |= 1u << c;
     uint32_t flags = 0;
     if (sm.td.mode == kModeBloom) {
       const uint32_t* filter = my_slot + sm.td.off_filter;
-      const uint32_t n_hash = sm.td.n_hash, m_bits = sm.td.m_bits;
-#pragma unroll
-      for (int c = 0; c < kPerThread; ++c) {
-        const uint32_t e = c * kThreads + threadIdx.x;
-        if (e < n && bloom_test(local0 + e, P.seed, n_hash, m_bits, [&](uint32_t w) { return filter[w]; }))
-          flags |= 1u << c;
-      }
+      if (staged) flags = bloom_test8(local0 + threadIdx.x, valid, P.seed, sm.td.n_hash, sm.td.m_bits,
+                                      [&](uint32_t w) { return g_filter_smem[w]; });
+      else flags = bloom_test8(local0 + threadIdx.x, valid, P.seed, sm.td.n_hash, sm.td.m_bits,
+                               [&](uint32_t w) { return filter[w]; });
     } else {
-      uint32_t eq = 0;
 #pragma unroll
       for (int c = 0; c < kPerThread; ++c) {
         const uint32_t e = c * kThreads + threadIdx.x;
-        if (e < n) {
-          const uint32_t key = __float_as_uint(__ldcg(P.resid + base + e)) & 0x7FFFFFFFu;
-          if (key > T) flags |= 1u << c;
-          else if (key == T) eq |= 1u << c;
-        }
-      }
-      if (ties_total == need) {
-        flags |= eq;
-      } else {
-        uint32_t trank[kPerThread], ttotal;
-        tile_rank(eq, sm.s, trank, ttotal);
-        const uint32_t texcl = __ldcg(P.tie_prefix + tile);
-#pragma unroll
-        for (int c = 0; c < kPerThread; ++c)
-          if (((eq >> c) & 1u) && texcl + trank[c] < need) flags |= 1u << c;
+        if (e < n && ((__float_as_uint(__ldcg(P.resid + base + e)) & 0x7FFFFFFFu) >> 9) >= T22) flags |= 1u << c;
       }
     }
     uint32_t rank[kPerThread], total;
@@ -491,16 +545,16 @@ DR_D void phase_emit(const EngineParams& P, Smem& sm) {
         const uint32_t incl = excl + total;
         dyn->n_sel = min(incl, limit);
         dyn->n_pos = incl;
-        dyn->thr_bits = T;
+        dyn->thr_bits = T22 << 9;
         if (incl < limit) dyn->cutoff = 0xFFFFFFFFu;
-        P.sel[t].prev_thr = T;
+        P.sel[cur].prev_thr = T22 << 9;
       }
     }
   }
 }
 
 // ===========================================================================
-// phase 6/7: push + flags
+// phase 5/6: push + flags
 // ===========================================================================
 DR_D void phase_push(const EngineParams& P) {
   const uint32_t parity = P.epoch & 1u;
@@ -533,7 +587,9 @@ DR_D void phase_signal(const EngineParams& P) {
 }
 
 // ===========================================================================
-// phase 8: decode every rank's slot for my tiles, sum, scale, dense write
+// phase 7: decode.  Contiguous tile range per CTA; rank-major so one staged
+// filter serves all of the CTA's tiles of that tensor; sparse RMW into the
+// zero-filled dense output.
 // ===========================================================================
 DR_D uint32_t lower_bound_u32(const uint32_t* a, uint32_t n, uint32_t x) {
   uint32_t lo = 0, hi = n;
@@ -544,82 +600,100 @@ DR_D uint32_t lower_bound_u32(const uint32_t* a, uint32_t n, uint32_t x) {
 DR_D void phase_decode(const EngineParams& P, Smem& sm) {
   const uint32_t parity = P.epoch & 1u;
   uint32_t* arena = P.arena[P.rank];
-  // hist arrays are free after the insert phase: zero them for the next step
-  {
+  {  // hist arrays are free after the insert phase: zero them for the next step
     uint4* h = reinterpret_cast<uint4*>(P.hist);
-    const size_t n4 = (size_t)4 * P.n_tensors * kHistBins / 4;
+    const size_t n4 = (size_t)kNumHist * P.n_tensors * kHistBins / 4;
     const uint4 z = make_uint4(0, 0, 0, 0);
     for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n4; i += (size_t)gridDim.x * kThreads) h[i] = z;
-    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < 4u * P.n_tensors; i += gridDim.x * kThreads)
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < (uint32_t)kNumHist * P.n_tensors; i += gridDim.x * kThreads)
       P.hist_total[i] = 0u;
   }
-  uint32_t cur = 0xFFFFFFFFu;
-  for (uint32_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-    const uint32_t t = P.tile_tensor[tile];
-    if (t != cur) { load_tensor(P, t, sm); cur = t; }
-    const uint32_t tile_local = tile - sm.td.tile_begin;
-    const uint32_t local0 = tile_local * kTile;
-    const uint32_t n = min((uint32_t)kTile, sm.td.numel - local0);
-    const size_t base = (size_t)sm.td.elem_off + local0;
+  const uint32_t t_begin = (uint32_t)(((uint64_t)P.n_tiles * blockIdx.x) / gridDim.x);
+  const uint32_t t_end = (uint32_t)(((uint64_t)P.n_tiles * (blockIdx.x + 1)) / gridDim.x);
+  uint32_t tile = t_begin;
+  while (tile < t_end) {
+    const TileInfo t0 = load_tile(P, tile);
+    const uint32_t t = t0.tensor;
+    load_tensor(P, t, sm);
+    const uint32_t seg_end = min(t_end, sm.td.tile_begin + sm.td.n_tiles);
     if (sm.td.mode == kModeBloom) {
-      float acc[kPerThread];
-#pragma unroll
-      for (int c = 0; c < kPerThread; ++c) acc[c] = 0.0f;
+      // 1) zero-fill my tiles of this tensor (contiguous in the flat buffer)
+      {
+        const TileInfo tl = load_tile(P, seg_end - 1);
+        const uint32_t n_elems = (tl.base + tl.n) - t0.base;
+        float4* dst = reinterpret_cast<float4*>(P.grad + t0.base);
+        const uint32_t n4 = n_elems >> 2;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (uint32_t i = threadIdx.x; i < n4; i += kThreads) dst[i] = z;
+        for (uint32_t i = (n4 << 2) + threadIdx.x; i < n_elems; i += kThreads) P.grad[t0.base + i] = 0.f;
+      }
+      __syncthreads();
       const uint32_t n_hash = sm.td.n_hash, m_bits = sm.td.m_bits;
+      const bool fits = sm.td.n_filter_words <= P.filter_smem_words;
       for (int r = 0; r < P.world; ++r) {
         const uint32_t* slot = slot_ptr(arena, P, parity, r);
         const DynHeader* dyn = reinterpret_cast<const DynHeader*>(slot + kSlotHeaderWords) + t;
         const uint32_t n_sel = __ldcg(&dyn->n_sel), cutoff = __ldcg(&dyn->cutoff);
-        const uint32_t pre = __ldcg(slot + sm.td.off_prefix + tile_local);
+        if (n_sel == 0) continue;
         const uint32_t* filter = slot + sm.td.off_filter;
         const float* vals = reinterpret_cast<const float*>(slot + sm.td.off_vals);
-        if (!(pre < n_sel && local0 <= cutoff)) continue;   // tile-uniform: nothing of rank r lands in this tile
-        uint32_t flags = 0;
+        if (fits) stage_filter(filter, sm.td.n_filter_words);
+        for (uint32_t tl = tile; tl < seg_end; ++tl) {
+          const TileInfo ti = load_tile(P, tl);
+          const uint32_t pre = __ldcg(slot + sm.td.off_prefix + (tl - sm.td.tile_begin));
+          if (!(pre < n_sel && ti.local0 <= cutoff)) continue;       // tile-uniform: nothing of rank r lands here
+          uint32_t valid = 0;
 #pragma unroll
-        for (int c = 0; c < kPerThread; ++c) {
-          const uint32_t e = c * kThreads + threadIdx.x;
-          const uint32_t gi = local0 + e;
-          if (e < n && gi <= cutoff &&
-              bloom_test(gi, P.seed, n_hash, m_bits, [&](uint32_t w) { return filter[w]; }))
-            flags |= 1u << c;
-        }
-        uint32_t rank[kPerThread], total;
-        tile_rank(flags, sm.s, rank, total);
+          for (int c = 0; c < kPerThread; ++c) {
+            const uint32_t e = c * kThreads + threadIdx.x;
+            if (e < ti.n && ti.local0 + e <= cutoff) valid |= 1u << c;
+          }
+          uint32_t flags;
+          if (fits) flags = bloom_test8(ti.local0 + threadIdx.x, valid, P.seed, n_hash, m_bits,
+                                        [&](uint32_t w) { return g_filter_smem[w]; });
+          else flags = bloom_test8(ti.local0 + threadIdx.x, valid, P.seed, n_hash, m_bits,
+                                   [&](uint32_t w) { return filter[w]; });
+          uint32_t rank[kPerThread], total;
+          tile_rank(flags, sm.s, rank, total);
 #pragma unroll
-        for (int c = 0; c < kPerThread; ++c) {
-          if ((flags >> c) & 1u) {
-            const uint32_t rp = pre + rank[c];
-            if (rp < n_sel) acc[c] += __ldcg(vals + rp);
+          for (int c = 0; c < kPerThread; ++c) {
+            if ((flags >> c) & 1u) {
+              const uint32_t rp = pre + rank[c];
+              if (rp < n_sel) {
+                float* o = P.grad + ti.base + c * kThreads + threadIdx.x;   // the same thread owns this element for every rank
+                *o = *o + __ldcg(vals + rp) * P.scale;
+              }
+            }
           }
         }
       }
-#pragma unroll
-      for (int c = 0; c < kPerThread; ++c) {
-        const uint32_t e = c * kThreads + threadIdx.x;
-        if (e < n) P.grad[base + e] = acc[c] * P.scale;
-      }
+      tile = seg_end;
     } else {
-      __syncthreads();
-      for (int j = threadIdx.x; j < kTile; j += kThreads) sm.u.acc[j] = 0.0f;
-      __syncthreads();
-      for (int r = 0; r < P.world; ++r) {
-        const uint32_t* slot = slot_ptr(arena, P, parity, r);
-        const DynHeader* dyn = reinterpret_cast<const DynHeader*>(slot + kSlotHeaderWords) + t;
-        const uint32_t n_sel = min(__ldcg(&dyn->n_sel), sm.td.val_cap);
-        const uint32_t* idxs = slot + sm.td.off_idx;
-        const float* vals = reinterpret_cast<const float*>(slot + sm.td.off_vals);
-        const uint32_t lo = lower_bound_u32(idxs, n_sel, local0);
-        const uint32_t hi = lower_bound_u32(idxs, n_sel, local0 + n);
-        for (uint32_t j = lo + threadIdx.x; j < hi; j += kThreads)
-          atomicAdd(&sm.u.acc[__ldcg(idxs + j) - local0], __ldcg(vals + j));
+      for (; tile < seg_end; ++tile) {
+        const TileInfo ti = load_tile(P, tile);
+        __syncthreads();
+        for (int j = threadIdx.x; j < kTile; j += kThreads) sm.u.acc[j] = 0.0f;
+        __syncthreads();
+        for (int r = 0; r < P.world; ++r) {
+          const uint32_t* slot = slot_ptr(arena, P, parity, r);
+          const DynHeader* dyn = reinterpret_cast<const DynHeader*>(slot + kSlotHeaderWords) + t;
+          const uint32_t n_sel = min(__ldcg(&dyn->n_sel), sm.td.val_cap);
+          const uint32_t* idxs = slot + sm.td.off_idx;
+          const float* vals = reinterpret_cast<const float*>(slot + sm.td.off_vals);
+          const uint32_t lo = lower_bound_u32(idxs, n_sel, ti.local0);
+          const uint32_t hi = lower_bound_u32(idxs, n_sel, ti.local0 + ti.n);
+          for (uint32_t j = lo + threadIdx.x; j < hi; j += kThreads)
+            atomicAdd(&sm.u.acc[__ldcg(idxs + j) - ti.local0], __ldcg(vals + j) * P.scale);
+        }
+        __syncthreads();
+        for (uint32_t e = threadIdx.x; e < ti.n; e += kThreads) P.grad[ti.base + e] = sm.u.acc[e];
       }
-      __syncthreads();
-      for (uint32_t e = threadIdx.x; e < n; e += kThreads) P.grad[base + e] = sm.u.acc[e] * P.scale;
     }
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 2) dr_engine_kernel(const __grid_constant__ EngineParams P) {
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) dr_engine_kernel(const __grid_constant__ EngineParams P) {
   __shared__ Smem sm;
   if (threadIdx.x == 0) sm.s.buf = 0;
   __syncthreads();
@@ -630,7 +704,6 @@ __global__ void __launch_bounds__(kThreads, 2) dr_engine_kernel(const __grid_con
       case kPhAccum: phase_accum(P, sm); break;
       case kPhFallback: if (P.use_history) hist_tiles<1>(P, sm); else ran = false; break;
       case kPhHist2: hist_tiles<2>(P, sm); break;
-      case kPhHist3: hist_tiles<3>(P, sm); break;
       case kPhInsert: phase_insert(P, sm); break;
       case kPhEmit: phase_emit(P, sm); break;
       case kPhPush: if (P.world > 1) phase_push(P); else ran = false; break;
@@ -648,22 +721,41 @@ __global__ void __launch_bounds__(kThreads, 2) dr_engine_kernel(const __grid_con
 // ---------------------------------------------------------------------------
 // host launcher
 // ---------------------------------------------------------------------------
-int engine_max_grid(int blocks_per_sm) {
+// Two register budgets of the same kernel: <1> = 128 regs, one CTA per SM, up to 200 KB of
+// filter staging; <2> = 64 regs, two CTAs per SM, up to 88 KB each.
+static bool g_attr_set = false;
+
+static const void* kernel_for(int blocks_per_sm) {
+  return blocks_per_sm >= 2 ? (const void*)dr_engine_kernel<2> : (const void*)dr_engine_kernel<1>;
+}
+
+static void ensure_attr() {
+  if (!g_attr_set) {
+    cudaFuncSetAttribute(dr_engine_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(dr_engine_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 88 * 1024);
+    g_attr_set = true;
+  }
+}
+
+int engine_max_grid(int blocks_per_sm, int dyn_smem_bytes) {
   int dev = 0, sms = 0, occ = 0;
+  ensure_attr();
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dr_engine_kernel, kThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel_for(blocks_per_sm), kThreads, (size_t)dyn_smem_bytes);
   if (occ < 1) occ = 1;
   if (blocks_per_sm > 0 && blocks_per_sm < occ) occ = blocks_per_sm;
   return occ * sms;
 }
 
-cudaError_t engine_launch(const EngineParams& P, int grid, cudaStream_t stream) {
+cudaError_t engine_launch(const EngineParams& P, int grid, int blocks_per_sm, int dyn_smem_bytes, cudaStream_t stream) {
+  ensure_attr();
   cudaError_t e = cudaMemsetAsync(P.barrier, 0, sizeof(uint32_t), stream);
   if (e != cudaSuccess) return e;
   void* args[] = {const_cast<EngineParams*>(&P)};
   count_launch(1);
-  return cudaLaunchCooperativeKernel((const void*)dr_engine_kernel, dim3(grid), dim3(kThreads), args, 0, stream);
+  return cudaLaunchCooperativeKernel(kernel_for(blocks_per_sm), dim3(grid), dim3(kThreads), args,
+                                     (size_t)dyn_smem_bytes, stream);
 }
 
 }  // namespace dr

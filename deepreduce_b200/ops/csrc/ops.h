@@ -8,8 +8,8 @@
 namespace dr {
 
 // engine.cu
-int engine_max_grid(int blocks_per_sm);
-cudaError_t engine_launch(const EngineParams& P, int grid, cudaStream_t stream);
+int engine_max_grid(int blocks_per_sm, int dyn_smem_bytes);
+cudaError_t engine_launch(const EngineParams& P, int grid, int blocks_per_sm, int dyn_smem_bytes, cudaStream_t stream);
 void count_launch(int n);
 long long launch_count();
 

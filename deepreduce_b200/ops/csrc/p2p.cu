@@ -79,11 +79,12 @@ __global__ void u8_to_nhwc_norm_kernel(const uint8_t* __restrict__ in, __nv_bflo
     __nv_bfloat16 o[12];
 #pragma unroll
     for (int j = 0; j < 12; ++j) o[j] = __float2bfloat16(((float)b[j] * (1.f / 255.f) - m[j % 3]) * s[j % 3]);
-    uint4* q = reinterpret_cast<uint4*>(out + i * 12);
     const uint32_t* ow = reinterpret_cast<const uint32_t*>(o);
-    // 24 bytes: one 16B + one 8B store
-    q[0] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-    reinterpret_cast<uint2*>(out + i * 12 + 8)[0] = make_uint2(ow[4], ow[5]);
+    // 24 bytes per thread: three 8-byte stores (24*i is only 8-byte aligned)
+    uint2* q = reinterpret_cast<uint2*>(out + i * 12);
+    q[0] = make_uint2(ow[0], ow[1]);
+    q[1] = make_uint2(ow[2], ow[3]);
+    q[2] = make_uint2(ow[4], ow[5]);
   }
   // tail pixels
   const int64_t start = n4 * 4;

@@ -56,48 +56,53 @@ struct DynHeader {
 // pass-1 lower bound): 8 words
 struct SelState {
   uint32_t bin1, krem1, bin2, krem2;
-  uint32_t thr;         // final 31-bit threshold key T
-  uint32_t need;        // ties (key == T) to take
-  uint32_t ties_total;  // ties present
-  uint32_t prev_thr;    // T of the previous step (0 = none)
+  uint32_t thr;         // selection threshold as a key lower bound: (T22 << 9), T22 = 22-bit prefix
+  uint32_t n_ge;        // diagnostics: keys in the threshold bin
+  uint32_t reserved;
+  uint32_t prev_thr;    // thr of the previous step (0 = none)
 };
 
 constexpr int kHistBins = 2048;
-// hist arrays: [4][n_tensors][kHistBins]  (pass1, pass1-fallback, pass2, pass3)
-// hist_total:  [4][n_tensors]
+constexpr int kNumHist = 3;
+// hist arrays: [3][n_tensors][kHistBins]  (pass1, pass1-fallback, pass2);  hist_total: [3][n_tensors]
 
 // arena layout per rank (uint32 words): [flags: 64][status: 64][slots: 2 * world * slot_words]
 constexpr uint32_t kArenaFlagWords = 64;
 constexpr uint32_t kArenaHdrWords = 128;
 
+// Selection rule (normative, mirrored by parallel/engine.py::select_topk_oracle):
+//   key  = |x| bit pattern (31 bits);  T22 = (key of the K-th largest |x|) >> 9
+//   selected  <=>  (key >> 9) >= max(T22, 1)
+// i.e. the threshold is resolved to 22 bits (8 exponent + 14 mantissa): at least K elements are
+// selected, plus the few that share the threshold's 22-bit prefix; exact zeros are never selected.
 enum Phase : int {
-  kPhAccum = 0,      // r = beta*r + gamma*g ; zero slot ; hist pass 1 (with history lower bound)
-  kPhFallback = 1,   // hist pass 1 redone without bound for tensors whose bound was unsafe
-  kPhHist2 = 2,
-  kPhHist3 = 3,
-  kPhInsert = 4,     // threshold resolve, bloom insert (tie ranks by look-back when needed)
-  kPhEmit = 5,       // universe query + ordered compaction + value gather + residual zeroing
-  kPhPush = 6,       // copy the finished slot into every peer's arena (P2P stores)
-  kPhSignal = 7,     // release flags to peers, acquire peers' flags
-  kPhDecode = 8,     // membership test on every rank's filter, rank->value, sum, scale, dense write
-  kPhEnd = 9
+  kPhAccum = 0,      // r = beta*r + gamma*g ; zero slot ; hist digit 1 (history lower bound)
+  kPhFallback = 1,   // digit 1 redone without the bound for tensors whose bound was unsafe
+  kPhHist2 = 2,      // digit 2 of the keys in the threshold bin
+  kPhInsert = 3,     // resolve T22, bloom insert of the selected set
+  kPhEmit = 4,       // universe query + ordered compaction + value gather + residual zeroing
+  kPhPush = 5,       // copy the finished slot into every peer's arena (P2P stores over NVLink)
+  kPhSignal = 6,     // release flags to peers, acquire peers' flags
+  kPhDecode = 7,     // membership test on every rank's filter, rank->value, sum, scale, dense write
+  kPhEnd = 8
 };
+
+// per-tile table (uint4): {tensor id, element offset of the tile in the flat buffers, valid count, offset inside tensor}
+struct TileInfo { uint32_t tensor, base, n, local0; };
 
 struct EngineParams {
   const TensorDesc* tensors;
-  const uint32_t* tile_tensor;   // [n_tiles] tile -> tensor id
+  const TileInfo* tiles;         // [n_tiles]
   uint32_t n_tensors;
   uint32_t n_tiles;
   uint32_t slot_words;           // words reserved per slot
   uint32_t payload_words;        // words actually used (pushed)
   float* grad;                   // in: local dense grad; out: aggregated dense grad
   float* resid;                  // residual accumulator (persists across steps)
-  uint32_t* hist;                // [4][n_tensors][kHistBins]
-  uint32_t* hist_total;          // [4][n_tensors]
+  uint32_t* hist;                // [3][n_tensors][kHistBins]
+  uint32_t* hist_total;          // [3][n_tensors]
   SelState* sel;                 // [n_tensors]
-  uint64_t* tie_desc;            // [n_tiles] look-back descriptors (epoch tagged)
-  uint64_t* pos_desc;            // [n_tiles]
-  uint32_t* tie_prefix;          // [n_tiles] exclusive tie rank at tile start
+  uint64_t* pos_desc;            // [n_tiles] look-back descriptors (epoch tagged)
   uint32_t* barrier;             // grid barrier counter (zeroed by host per launch)
   uint32_t* status;              // [8] error / watchdog words (device-local)
   uint32_t* arena[kMaxWorld];    // peer-mapped arena base of every rank (arena[rank] is local)
@@ -109,7 +114,8 @@ struct EngineParams {
   int policy;
   int use_history;               // pass-1 lower bound from prev_thr
   int phase_begin, phase_end;
-  uint32_t spin_limit;           // watchdog for flag / look-back spins
+  uint32_t spin_limit;           // watchdog for flag / look-back / barrier spins
+  uint32_t filter_smem_words;    // capacity of the dynamic-SMEM filter staging buffer
 };
 
 }  // namespace dr

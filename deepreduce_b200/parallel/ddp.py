@@ -22,7 +22,7 @@ import torch.nn as nn
 
 from .. import spec
 from ..wrappers import deepreduce_from_params
-from .engine import BucketEngine
+from .engine import PH_ACCUM, PH_END, BucketEngine
 from .plan import BucketPlan
 
 
@@ -40,7 +40,7 @@ def _fused_supported(params: dict) -> bool:
 
 class DeepReduceDDP:
     def __init__(self, module: nn.Module, params: dict, *, bucket_cap_mb: float = 1e9, overlap: bool = True,
-                 group=None, blocks_per_sm: int = 2, use_history: bool = True, background_thread: bool = True):
+                 group=None, blocks_per_sm: int = 1, use_history: bool = True, background_thread: bool = True):
         self.module = module
         self.params = dict(params)
         self.group = group
@@ -132,7 +132,7 @@ class DeepReduceDDP:
             if self.sched is not None:
                 self.sched.submit(b, eng.ctx, eng.epoch)
             else:
-                eng.ctx.run(eng.epoch, 0, 9)
+                eng.ctx.run(eng.epoch, PH_ACCUM, PH_END)
         else:
             if self.world > 1:
                 self.pending.append(dist.all_reduce(self.flat[b], group=self.group, async_op=True))

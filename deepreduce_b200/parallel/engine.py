@@ -21,10 +21,10 @@ import torch.distributed as dist
 
 from .. import spec
 from ..codecs.bloom import bloom_insert_oracle, bloom_query_oracle
-from .plan import (ARENA_HDR_WORDS, DYN_WORDS, HIST_BINS, MODE_BLOOM, MODE_RAW, POLICY_ID, SLOT_HEADER_WORDS,
-                   BucketPlan)
+from .plan import (ARENA_HDR_WORDS, DYN_WORDS, HIST_BINS, MODE_BLOOM, MODE_RAW, NUM_HIST, POLICY_ID,
+                   SLOT_HEADER_WORDS, BucketPlan)
 
-PH_ACCUM, PH_FALLBACK, PH_HIST2, PH_HIST3, PH_INSERT, PH_EMIT, PH_PUSH, PH_SIGNAL, PH_DECODE, PH_END = range(10)
+PH_ACCUM, PH_FALLBACK, PH_HIST2, PH_INSERT, PH_EMIT, PH_PUSH, PH_SIGNAL, PH_DECODE, PH_END = range(9)
 MAGIC = 0xD33B2000
 STATUS_NAMES = {0: "ok", 1: "look-back watchdog", 2: "peer flag watchdog", 3: "select resolve failed", 4: "grid barrier watchdog"}
 
@@ -37,14 +37,15 @@ def _abs_keys(x: torch.Tensor) -> torch.Tensor:
 
 
 def select_topk_oracle(acc: torch.Tensor, k: int):
-    """Exact top-k by |x| with deterministic ties (smallest index first).
-    Returns (ascending indices, threshold key T)."""
+    """The engine's selection rule (normative, see ops/csrc/plan.h): with key = |x| bit pattern and
+    T22 = (K-th largest key) >> 9, select every element with (key >> 9) >= max(T22, 1).  At least K
+    elements (when K non-zeros exist) plus the few sharing the threshold's 22-bit prefix; exact zeros
+    never.  Returns (ascending indices, threshold key lower bound)."""
     keys = _abs_keys(acc)
-    T = int(torch.topk(keys, k, sorted=True).values[-1].item())
-    gt = torch.nonzero(keys > T).flatten()
-    need = k - gt.numel()
-    eq = torch.nonzero(keys == T).flatten()[:need]
-    return torch.sort(torch.cat([gt, eq])).values, T
+    kth = int(torch.topk(keys, k, sorted=True).values[-1].item())
+    T22 = max(kth >> 9, 1)
+    sel = torch.nonzero((keys >> 9) >= T22).flatten()
+    return sel, T22 << 9
 
 
 def encode_tensor_oracle(tp, acc: torch.Tensor, slot: np.ndarray, t_index: int, policy: str, seed: int):
@@ -63,9 +64,9 @@ def encode_tensor_oracle(tp, acc: torch.Tensor, slot: np.ndarray, t_index: int, 
         slot[tp.off_prefix:tp.off_prefix + tp.n_tiles] = torch.searchsorted(sel.cpu(), starts).numpy().astype(np.uint32)
         cutoff = int(sel[-1].item()) if n_pos >= limit and limit > 0 else 0xFFFFFFFF
     else:
-        sel = sel_topk
-        n_pos = int(sel.numel())
+        n_pos = int(sel_topk.numel())
         limit = tp.val_cap
+        sel = sel_topk[:limit]                 # capacity K: the left-most of the (>= K) selected
         slot[tp.off_idx:tp.off_idx + sel.numel()] = sel.cpu().numpy().astype(np.uint32)
         cutoff = int(sel[-1].item()) if n_pos >= limit else 0xFFFFFFFF
     vals = acc[sel].float()
@@ -111,9 +112,9 @@ class BucketEngine:
     """One flat bucket + its fused exchange kernel."""
 
     def __init__(self, plan: BucketPlan, device=None, group=None, *, beta: float = 1.0, gamma: float = 1.0,
-                 average: bool = True, use_history: bool = True, blocks_per_sm: int = 2,
+                 average: bool = True, use_history: bool = True, blocks_per_sm: int = 1,
                  seed: int = spec.DEFAULT_SEED, spin_limit: int = 20_000_000, world: Optional[int] = None,
-                 rank: Optional[int] = None):
+                 rank: Optional[int] = None, filter_smem_bytes: Optional[int] = None):
         from .. import ops
         self.mod = ops.cuda_module()
         self.plan = plan
@@ -132,23 +133,23 @@ class BucketEngine:
             self.resid = torch.zeros(plan.total_elems, dtype=torch.float32, device=dev)
             self.tensor_table = plan.tensor_table().to(dev)
             self.tile_table = plan.tile_table().to(dev)
-            self.hist = torch.zeros(4 * nT * HIST_BINS, dtype=torch.int32, device=dev)
-            self.hist_total = torch.zeros(4 * nT, dtype=torch.int32, device=dev)
+            self.hist = torch.zeros(NUM_HIST * nT * HIST_BINS, dtype=torch.int32, device=dev)
+            self.hist_total = torch.zeros(NUM_HIST * nT, dtype=torch.int32, device=dev)
             self.sel = torch.zeros(nT * 8, dtype=torch.int32, device=dev)
-            self.tie_desc = torch.zeros(nt, dtype=torch.int64, device=dev)
             self.pos_desc = torch.zeros(nt, dtype=torch.int64, device=dev)
-            self.tie_prefix = torch.zeros(nt, dtype=torch.int32, device=dev)
             self.barrier = torch.zeros(16, dtype=torch.int32, device=dev)
             self.status = torch.zeros(8, dtype=torch.int32, device=dev)
             self._setup_arena()
             self.ctx = self.mod.Engine(
                 self.tensor_table.data_ptr(), self.tile_table.data_ptr(), nT, nt, plan.slot_words, plan.payload_words,
                 self.grad.data_ptr(), self.resid.data_ptr(), self.hist.data_ptr(), self.hist_total.data_ptr(),
-                self.sel.data_ptr(), self.tie_desc.data_ptr(), self.pos_desc.data_ptr(), self.tie_prefix.data_ptr(),
+                self.sel.data_ptr(), self.pos_desc.data_ptr(),
                 self.barrier.data_ptr(), self.status.data_ptr(), self.arena_ptrs, self.rank, self.world)
             scale = (1.0 / self.world) if average else 1.0
+            if filter_smem_bytes is None:      # <1>: 128 regs, 1 CTA/SM; <2>: 64 regs, 2 CTAs/SM
+                filter_smem_bytes = 160 * 1024 if blocks_per_sm < 2 else 64 * 1024
             self.ctx.configure(self.beta, self.gamma, scale, int(seed), POLICY_ID[plan.policy], int(use_history),
-                               int(spin_limit), int(blocks_per_sm))
+                               int(spin_limit), int(blocks_per_sm), int(filter_smem_bytes))
         self.grad_views = plan.views(self.grad)
 
     # ---- arena -------------------------------------------------------------

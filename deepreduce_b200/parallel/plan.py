@@ -24,6 +24,7 @@ SLOT_HEADER_WORDS = 8
 DYN_WORDS = 4
 ARENA_HDR_WORDS = 128
 HIST_BINS = 2048
+NUM_HIST = 3
 ALIGN_ELEMS = 32
 
 
@@ -124,10 +125,16 @@ class BucketPlan:
         return torch.from_numpy(arr.reshape(-1).copy())
 
     def tile_table(self) -> torch.Tensor:
-        out = np.empty(self.n_tiles, dtype=np.int32)
+        """[n_tiles, 4] int32: {tensor id, element offset in the flat buffers, valid count, offset inside the tensor}."""
+        out = np.empty((self.n_tiles, 4), dtype=np.int64)
         for i, t in enumerate(self.tensors):
-            out[t.tile_begin:t.tile_begin + t.n_tiles] = i
-        return torch.from_numpy(out)
+            loc = np.arange(t.n_tiles, dtype=np.int64) * spec.TILE
+            rows = out[t.tile_begin:t.tile_begin + t.n_tiles]
+            rows[:, 0] = i
+            rows[:, 1] = t.elem_off + loc
+            rows[:, 2] = np.minimum(spec.TILE, t.numel - loc)
+            rows[:, 3] = loc
+        return torch.from_numpy(out.astype(np.uint32).view(np.int32).copy())
 
     def arena_words(self, world: int) -> int:
         return ARENA_HDR_WORDS + 2 * world * self.slot_words

@@ -15,10 +15,13 @@ def test_plan_layout():
     plan = BucketPlan(SIZES, compress_ratio=0.01)
     assert [t.mode for t in plan.tensors] == [MODE_RAW, MODE_RAW, MODE_BLOOM, MODE_BLOOM, MODE_BLOOM, MODE_BLOOM, MODE_BLOOM, MODE_RAW]
     assert plan.n_tiles == sum((d + spec.TILE - 1) // spec.TILE for d in SIZES)
-    tt = plan.tile_table().tolist()
+    tt = plan.tile_table()
+    assert tuple(tt.shape) == (plan.n_tiles, 4)
     for i, t in enumerate(plan.tensors):
         assert t.elem_off % 32 == 0 and t.k == max(1, int(t.numel * 0.01))
-        assert tt[t.tile_begin:t.tile_begin + t.n_tiles] == [i] * t.n_tiles
+        rows = tt[t.tile_begin:t.tile_begin + t.n_tiles]
+        assert rows[:, 0].tolist() == [i] * t.n_tiles
+        assert rows[0, 1] == t.elem_off and int(rows[:, 2].sum()) == t.numel and rows[-1, 3] == (t.n_tiles - 1) * spec.TILE
     # regions do not overlap and fit in the payload
     regions = []
     for t in plan.tensors:
@@ -37,13 +40,20 @@ def test_plan_layout():
     assert plan.wire_bytes() < plan.topk_pair_bytes()
 
 
-def test_select_topk_ties_deterministic():
+def test_select_rule_22bit_threshold():
+    # rule: (key >> 9) >= max(T22, 1) with T22 = 22-bit prefix of the K-th largest |x|
     x = torch.tensor([0.0, 1.0, -1.0, 1.0, 0.5, -1.0, 2.0])
-    idx, T = select_topk_oracle(x, 3)
-    assert idx.tolist() == [1, 2, 6]                 # 2.0 first, then the two left-most |1.0|
+    idx, thr = select_topk_oracle(x, 3)
+    assert idx.tolist() == [1, 2, 3, 5, 6]           # everything sharing the threshold's prefix comes along
+    assert thr == (torch.tensor(1.0).view(torch.int32).item() >> 9) << 9
     x = torch.zeros(100); x[7] = 3.0
-    idx, T = select_topk_oracle(x, 5)
-    assert idx.tolist() == [0, 1, 2, 3, 7] and T == 0
+    idx, thr = select_topk_oracle(x, 5)
+    assert idx.tolist() == [7]                       # exact zeros are never shipped
+    torch.manual_seed(0)
+    x = torch.randn(100000)
+    idx, _ = select_topk_oracle(x, 1000)
+    ref = set(torch.topk(x.abs(), 1000).indices.tolist())
+    assert ref <= set(idx.tolist()) and idx.numel() <= 1010      # >= K, plus at most a handful at the threshold
 
 
 def test_oracle_matches_grace_path_single_rank():
