@@ -184,7 +184,8 @@ struct Engine {
 
   Engine(int64_t tensors, int64_t tiles, int64_t n_tensors, int64_t n_tiles, int64_t slot_words,
          int64_t payload_words, int64_t grad, int64_t resid, int64_t hist, int64_t hist_total, int64_t sel,
-         int64_t pos_desc, int64_t barrier, int64_t status, std::vector<int64_t> arenas, int rank, int world) {
+         int64_t tile_count, int64_t flag_buf, int64_t barrier, int64_t status, std::vector<int64_t> arenas, int rank,
+         int world) {
     TORCH_CHECK(world <= dr::kMaxWorld && (int)arenas.size() == world, "bad world/arenas");
     P.tensors = reinterpret_cast<const dr::TensorDesc*>(tensors);
     P.tiles = reinterpret_cast<const dr::TileInfo*>(tiles);
@@ -193,7 +194,8 @@ struct Engine {
     P.grad = reinterpret_cast<float*>(grad); P.resid = reinterpret_cast<float*>(resid);
     P.hist = reinterpret_cast<uint32_t*>(hist); P.hist_total = reinterpret_cast<uint32_t*>(hist_total);
     P.sel = reinterpret_cast<dr::SelState*>(sel);
-    P.pos_desc = reinterpret_cast<uint64_t*>(pos_desc);
+    P.tile_count = reinterpret_cast<uint32_t*>(tile_count);
+    P.flag_buf = reinterpret_cast<uint8_t*>(flag_buf);
     P.barrier = reinterpret_cast<uint32_t*>(barrier); P.status = reinterpret_cast<uint32_t*>(status);
     for (int i = 0; i < world; ++i) P.arena[i] = reinterpret_cast<uint32_t*>(arenas[i]);
     P.rank = rank; P.world = world;
@@ -380,7 +382,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
 
   py::class_<Engine>(m, "Engine")
       .def(py::init<int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t,
-                    int64_t, int64_t, int64_t, std::vector<int64_t>, int, int>())
+                    int64_t, int64_t, int64_t, int64_t, std::vector<int64_t>, int, int>())
       .def("configure", &Engine::configure)
       .def("set_buffers", &Engine::set_buffers)
       .def("grid", &Engine::get_grid)

@@ -17,16 +17,16 @@
 // one at a time (phase_begin/phase_end) — the "unfused chain" debug mode.
 //
 // Work decomposition: the bucket is cut into 4096-element tiles that never
-// cross a tensor.  Encode phases give CTA b the tiles b, b+G, b+2G, ...
-// (increasing order, grid co-resident => the decoupled look-back used for
-// ordered ranks is deadlock-free and has a short window); the decode phase
-// gives every CTA a contiguous tile range so a staged filter is reused.
+// cross a tensor; every phase gives CTA b the same contiguous tile range, so
+// per-tensor work (histogram flush, threshold resolve, filter staging) is paid
+// 1-3 times per CTA instead of once per tile (profiles/ v1->v3 notes).  Ordered
+// ranks need a prefix over tiles: the query phase stores per-thread element
+// flags + per-tile counts, and after one grid barrier the emit phase sums the
+// counts it needs locally — no look-back chain.
 //
-// Latency structure (from the first ncu capture, profiles/): the streaming
-// passes software-prefetch the next tile while the current one is binned;
-// bloom filters are staged in shared memory (<= 64 KB covers every ResNet-50
-// tensor) and probed 8 elements at a time so 8 independent LDS are in flight
-// per thread instead of one dependent L1 gather.
+// Latency structure: streaming passes software-prefetch the next tile while
+// the current one is binned; bloom filters are staged in shared memory (every
+// ResNet-50 tensor's filter fits) and probed from there.
 #include "common.cuh"
 #include "plan.h"
 
@@ -41,7 +41,6 @@ long long launch_count() { return g_launches.load(); }
 
 namespace {
 
-constexpr uint32_t kFlagAgg = 1u, kFlagInc = 2u;
 constexpr uint32_t kErrLookback = 1u, kErrPeerWait = 2u, kErrResolve = 3u;
 constexpr uint32_t kNoTensor = 0xFFFFFFFFu;
 
@@ -66,10 +65,6 @@ extern __shared__ __align__(16) uint32_t g_filter_smem[];   // dynamic: staged b
 
 DR_D uint32_t* slot_ptr(uint32_t* arena, const EngineParams& P, uint32_t parity, int src) {
   return arena + kArenaHdrWords + (size_t)(parity * (uint32_t)P.world + (uint32_t)src) * P.slot_words;
-}
-
-DR_D uint64_t pack_desc(uint32_t epoch, uint32_t flag, uint32_t value) {
-  return ((uint64_t)(epoch & 0x3FFFFFFFu) << 34) | ((uint64_t)flag << 32) | (uint64_t)value;
 }
 
 DR_D TileInfo load_tile(const EngineParams& P, uint32_t tile) {
@@ -124,60 +119,6 @@ DR_D void tile_rank(uint32_t flags, ScanSmem& s, uint32_t (&rank)[kPerThread], u
 #pragma unroll
   for (int c = 0; c < kPerThread; ++c) rank[c] = s.cnt[buf][c * kWarps + warp] + __popc(ball[c] & lt);
   total = s.cnt[buf][kPerThread * kWarps];
-}
-
-// ---------------------------------------------------------------------------
-// decoupled look-back over the tiles of one tensor.  Returns the exclusive
-// prefix (sum of `count` over earlier tiles of the same tensor).
-// ---------------------------------------------------------------------------
-DR_D uint32_t lookback(const EngineParams& P, uint64_t* desc, uint32_t tile, uint32_t first_tile,
-                       uint32_t count, ScanSmem& s) {
-  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  if (warp == 0) {
-    uint32_t excl = 0;
-    if (tile == first_tile) {
-      if (lane == 0) st_release_gpu64(desc + tile, pack_desc(P.epoch, kFlagInc, count));
-    } else {
-      if (lane == 0) st_release_gpu64(desc + tile, pack_desc(P.epoch, kFlagAgg, count));
-      int j = (int)tile - 1;
-      const uint32_t want = P.epoch & 0x3FFFFFFFu;
-      while (true) {
-        const int idx = j - (int)lane;
-        const bool valid = idx >= (int)first_tile;
-        uint32_t flag = 0, val = 0;
-        if (valid) {
-          uint64_t d;
-          uint32_t spins = 0;
-          while (true) {
-            d = ld_acquire_gpu64(desc + idx);
-            if ((uint32_t)(d >> 34) == want && ((uint32_t)(d >> 32) & 3u) != 0u) break;
-            if (++spins > P.spin_limit) { atomicExch(P.status, kErrLookback); d = pack_desc(want, kFlagInc, 0); break; }
-            __nanosleep(20);
-          }
-          flag = (uint32_t)(d >> 32) & 3u;
-          val = (uint32_t)d;
-        }
-        const uint32_t inc_mask = __ballot_sync(0xFFFFFFFFu, valid && flag == kFlagInc);
-        uint32_t contrib = valid ? val : 0u;
-        if (inc_mask) {
-          const uint32_t first = __ffs(inc_mask) - 1u;   // nearest tile holding an inclusive prefix
-          if (lane > first) contrib = 0u;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xFFFFFFFFu, contrib, o);
-        excl += contrib;
-        if (inc_mask) break;
-        j -= 32;
-        if (j < (int)first_tile) break;
-      }
-      if (lane == 0) st_release_gpu64(desc + tile, pack_desc(P.epoch, kFlagInc, excl + count));
-    }
-    if (lane == 0) s.lb = excl;
-  }
-  __syncthreads();
-  const uint32_t r = s.lb;
-  __syncthreads();
-  return r;
 }
 
 // ---------------------------------------------------------------------------
@@ -251,31 +192,19 @@ DR_D void stage_filter(const uint32_t* __restrict__ filter, uint32_t n_words) {
   __syncthreads();
 }
 
-// Membership test of 8 elements per thread with the probes of all live
-// elements issued together (8 independent loads in flight).  `valid` marks the
-// elements to test; returns the mask of positives.
+DR_D void tile_range(const EngineParams& P, uint32_t& t_begin, uint32_t& t_end) {
+  t_begin = (uint32_t)(((uint64_t)P.n_tiles * blockIdx.x) / gridDim.x);
+  t_end = (uint32_t)(((uint64_t)P.n_tiles * (blockIdx.x + 1)) / gridDim.x);
+}
+
+// 8 membership tests per thread (elements idx0 + c*kThreads), early exit per element
 template <typename LoadFn>
 DR_D uint32_t bloom_test8(uint32_t idx0, uint32_t valid, uint32_t seed, uint32_t n_hash, uint32_t m_bits, LoadFn ld) {
-  uint32_t a[kPerThread], b[kPerThread];
+  uint32_t flags = 0;
 #pragma unroll
-  for (int c = 0; c < kPerThread; ++c) {
-    const HashAB h = hash_ab(idx0 + c * kThreads, seed);
-    a[c] = h.a; b[c] = h.b;
-  }
-  uint32_t alive = valid;
-  for (uint32_t j = 0; j < n_hash && alive; ++j) {
-    uint32_t w[kPerThread];
-#pragma unroll
-    for (int c = 0; c < kPerThread; ++c) {
-      const uint32_t pos = mulhi32(a[c], m_bits);
-      w[c] = ((alive >> c) & 1u) ? (ld(pos >> 5) >> (pos & 31u)) : 0u;
-      a[c] += b[c];
-    }
-#pragma unroll
-    for (int c = 0; c < kPerThread; ++c)
-      if (!(w[c] & 1u)) alive &= ~(1u << c);
-  }
-  return alive;
+  for (int c = 0; c < kPerThread; ++c)
+    if (((valid >> c) & 1u) && bloom_test(idx0 + c * kThreads, seed, n_hash, m_bits, ld)) flags |= 1u << c;
+  return flags;
 }
 
 // ===========================================================================
@@ -293,8 +222,9 @@ DR_D void phase_accum(const EngineParams& P, Smem& sm) {
   clear_hist(sm);
   const bool has_resid = (P.beta != 0.0f);
   uint32_t cur = kNoTensor, lower = 0;
-  uint32_t tile = blockIdx.x;
-  if (tile >= P.n_tiles) return;
+  uint32_t tile, t_end;
+  tile_range(P, tile, t_end);
+  if (tile >= t_end) return;
   TileInfo ti = load_tile(P, tile);
   float4 g[2], r[2];
   auto issue = [&](const TileInfo& t, float4 (&gg)[2], float4 (&rr)[2]) {
@@ -309,10 +239,10 @@ DR_D void phase_accum(const EngineParams& P, Smem& sm) {
   };
   issue(ti, g, r);
   while (true) {
-    const uint32_t next = tile + gridDim.x;
+    const uint32_t next = tile + 1;
     TileInfo tn = ti;
     float4 gn[2], rn[2];
-    const bool has_next = next < P.n_tiles;
+    const bool has_next = next < t_end;
     if (has_next) { tn = load_tile(P, next); issue(tn, gn, rn); }     // prefetch before binning the current tile
     if (ti.tensor != cur) {
       if (cur != kNoTensor) flush_hist(hist_ptr(P, 0, cur), P.hist_total + cur, sm);
@@ -357,8 +287,9 @@ DR_D void hist_tiles(const EngineParams& P, Smem& sm) {
   uint32_t cur = kNoTensor;
   bool active = false;
   uint32_t prefix = 0;
-  uint32_t tile = blockIdx.x;
-  if (tile >= P.n_tiles) return;
+  uint32_t tile, t_end;
+  tile_range(P, tile, t_end);
+  if (tile >= t_end) return;
   TileInfo ti = load_tile(P, tile);
   uint4 q[2];
   auto issue = [&](const TileInfo& t, uint4 (&qq)[2]) {
@@ -370,8 +301,8 @@ DR_D void hist_tiles(const EngineParams& P, Smem& sm) {
   };
   if (kWhich == 2) issue(ti, q);
   while (true) {
-    const uint32_t next = tile + gridDim.x;
-    const bool has_next = next < P.n_tiles;
+    const uint32_t next = tile + 1;
+    const bool has_next = next < t_end;
     TileInfo tn = ti;
     uint4 qn[2];
     if (has_next) { tn = load_tile(P, next); if (kWhich == 2) issue(tn, qn); }
@@ -426,8 +357,9 @@ DR_D void phase_insert(const EngineParams& P, Smem& sm) {
   const uint32_t parity = P.epoch & 1u;
   uint32_t* my_slot = slot_ptr(P.arena[P.rank], P, parity, P.rank);
   uint32_t cur = kNoTensor, T22 = 1;
-  uint32_t tile = blockIdx.x;
-  if (tile >= P.n_tiles) return;
+  uint32_t tile, t_end;
+  tile_range(P, tile, t_end);
+  if (tile >= t_end) return;
   TileInfo ti = load_tile(P, tile);
   uint32_t v[kPerThread];
   auto issue = [&](const TileInfo& t, uint32_t (&vv)[kPerThread]) {
@@ -439,8 +371,8 @@ DR_D void phase_insert(const EngineParams& P, Smem& sm) {
   };
   issue(ti, v);
   while (true) {
-    const uint32_t next = tile + gridDim.x;
-    const bool has_next = next < P.n_tiles;
+    const uint32_t next = tile + 1;
+    const bool has_next = next < t_end;
     TileInfo tn = ti;
     uint32_t vn[kPerThread];
     if (has_next) { tn = load_tile(P, next); issue(tn, vn); }
@@ -474,18 +406,16 @@ DR_D void phase_insert(const EngineParams& P, Smem& sm) {
 }
 
 // ===========================================================================
-// phase 4: universe query + ordered compaction + value gather + residual update
+// phase 4: universe query — per-element flags + per-tile counts
 // ===========================================================================
-DR_D void phase_emit(const EngineParams& P, Smem& sm) {
+DR_D void phase_query(const EngineParams& P, Smem& sm) {
   const uint32_t parity = P.epoch & 1u;
   uint32_t* my_slot = slot_ptr(P.arena[P.rank], P, parity, P.rank);
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    my_slot[0] = kMagic; my_slot[1] = P.epoch; my_slot[2] = P.n_tensors; my_slot[3] = P.payload_words;
-    my_slot[4] = (uint32_t)P.rank;
-  }
   uint32_t cur = kNoTensor, T22 = 1;
   bool staged = false;
-  for (uint32_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+  uint32_t tile, t_end;
+  tile_range(P, tile, t_end);
+  for (; tile < t_end; ++tile) {
     const TileInfo ti = load_tile(P, tile);
     if (ti.tensor != cur) {
       cur = ti.tensor;
@@ -497,45 +427,91 @@ DR_D void phase_emit(const EngineParams& P, Smem& sm) {
         staged = true;
       }
     }
-    const uint32_t tile_local = tile - sm.td.tile_begin;
-    const uint32_t n = ti.n, local0 = ti.local0;
-    const size_t base = ti.base;
-    DynHeader* dyn = reinterpret_cast<DynHeader*>(my_slot + kSlotHeaderWords) + cur;
-    const bool last_tile = (tile_local + 1 == sm.td.n_tiles);
     uint32_t valid = 0;
 #pragma unroll
-    for (int c = 0; c < kPerThread; ++c) if (c * kThreads + threadIdx.x < n) valid |= 1u << c;
+    for (int c = 0; c < kPerThread; ++c) if (c * kThreads + threadIdx.x < ti.n) valid |= 1u << c;
     uint32_t flags = 0;
     if (sm.td.mode == kModeBloom) {
       const uint32_t* filter = my_slot + sm.td.off_filter;
-      if (staged) flags = bloom_test8(local0 + threadIdx.x, valid, P.seed, sm.td.n_hash, sm.td.m_bits,
+      if (staged) flags = bloom_test8(ti.local0 + threadIdx.x, valid, P.seed, sm.td.n_hash, sm.td.m_bits,
                                       [&](uint32_t w) { return g_filter_smem[w]; });
-      else flags = bloom_test8(local0 + threadIdx.x, valid, P.seed, sm.td.n_hash, sm.td.m_bits,
+      else flags = bloom_test8(ti.local0 + threadIdx.x, valid, P.seed, sm.td.n_hash, sm.td.m_bits,
                                [&](uint32_t w) { return filter[w]; });
     } else {
 #pragma unroll
       for (int c = 0; c < kPerThread; ++c) {
         const uint32_t e = c * kThreads + threadIdx.x;
-        if (e < n && ((__float_as_uint(__ldcg(P.resid + base + e)) & 0x7FFFFFFFu) >> 9) >= T22) flags |= 1u << c;
+        if (e < ti.n && ((__float_as_uint(__ldcg(P.resid + ti.base + e)) & 0x7FFFFFFFu) >> 9) >= T22) flags |= 1u << c;
       }
     }
+    P.flag_buf[(size_t)tile * kThreads + threadIdx.x] = (uint8_t)flags;
+    // block-wide popcount of the flags: warp reduce + one smem atomic per warp
+    uint32_t pc = __popc(flags);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pc += __shfl_xor_sync(0xFFFFFFFFu, pc, o);
+    if (threadIdx.x == 0) sm.s.lb = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31u) == 0 && pc) atomicAdd(&sm.s.lb, pc);
+    __syncthreads();
+    if (threadIdx.x == 0) P.tile_count[tile] = sm.s.lb;
+  }
+}
+
+// ===========================================================================
+// phase 5: ordered compaction + value gather + residual update
+// ===========================================================================
+DR_D void phase_emit(const EngineParams& P, Smem& sm) {
+  const uint32_t parity = P.epoch & 1u;
+  uint32_t* my_slot = slot_ptr(P.arena[P.rank], P, parity, P.rank);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    my_slot[0] = kMagic; my_slot[1] = P.epoch; my_slot[2] = P.n_tensors; my_slot[3] = P.payload_words;
+    my_slot[4] = (uint32_t)P.rank;
+  }
+  uint32_t cur = kNoTensor, T22 = 1, excl = 0;
+  uint32_t tile, t_end;
+  tile_range(P, tile, t_end);
+  for (; tile < t_end; ++tile) {
+    const TileInfo ti = load_tile(P, tile);
+    if (ti.tensor != cur) {
+      cur = ti.tensor;
+      load_tensor(P, cur, sm);
+      T22 = __ldcg(&P.sel[cur].thr) >> 9;
+      // exclusive prefix at my first tile of this tensor: sum of the counts of the tensor's earlier tiles
+      uint32_t part = 0;
+      for (uint32_t j = sm.td.tile_begin + threadIdx.x; j < tile; j += kThreads) part += __ldcg(P.tile_count + j);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
+      if (threadIdx.x == 0) sm.s.lb = 0;
+      __syncthreads();
+      if ((threadIdx.x & 31u) == 0 && part) atomicAdd(&sm.s.lb, part);
+      __syncthreads();
+      excl = sm.s.lb;
+      __syncthreads();
+    }
+    const uint32_t tile_local = tile - sm.td.tile_begin;
+    const uint32_t local0 = ti.local0;
+    const size_t base = ti.base;
+    DynHeader* dyn = reinterpret_cast<DynHeader*>(my_slot + kSlotHeaderWords) + cur;
+    const bool last_tile = (tile_local + 1 == sm.td.n_tiles);
+    const uint32_t flags = P.flag_buf[(size_t)tile * kThreads + threadIdx.x];
     uint32_t rank[kPerThread], total;
     tile_rank(flags, sm.s, rank, total);
-    const uint32_t excl = lookback(P, P.pos_desc, tile, sm.td.tile_begin, total, sm.s);
     const uint32_t limit = (sm.td.mode == kModeBloom && P.policy != kPolicyP0) ? min(sm.td.k, sm.td.val_cap)
                                                                                : sm.td.val_cap;
     float* vals = reinterpret_cast<float*>(my_slot + sm.td.off_vals);
     uint32_t* idxs = my_slot + sm.td.off_idx;
+    if (excl < limit) {
 #pragma unroll
-    for (int c = 0; c < kPerThread; ++c) {
-      if ((flags >> c) & 1u) {
-        const uint32_t rp = excl + rank[c];
-        if (rp < limit) {
-          const uint32_t e = c * kThreads + threadIdx.x;
-          vals[rp] = P.resid[base + e];
-          P.resid[base + e] = 0.0f;                      // residual is exactly 0 on the shipped set
-          if (sm.td.mode == kModeRaw) idxs[rp] = local0 + e;
-          if (rp == limit - 1u) dyn->cutoff = local0 + e;
+      for (int c = 0; c < kPerThread; ++c) {
+        if ((flags >> c) & 1u) {
+          const uint32_t rp = excl + rank[c];
+          if (rp < limit) {
+            const uint32_t e = c * kThreads + threadIdx.x;
+            vals[rp] = P.resid[base + e];
+            P.resid[base + e] = 0.0f;                      // residual is exactly 0 on the shipped set
+            if (sm.td.mode == kModeRaw) idxs[rp] = local0 + e;
+            if (rp == limit - 1u) dyn->cutoff = local0 + e;
+          }
         }
       }
     }
@@ -550,11 +526,12 @@ DR_D void phase_emit(const EngineParams& P, Smem& sm) {
         P.sel[cur].prev_thr = T22 << 9;
       }
     }
+    excl += total;
   }
 }
 
 // ===========================================================================
-// phase 5/6: push + flags
+// phase 6/7: push + flags
 // ===========================================================================
 DR_D void phase_push(const EngineParams& P) {
   const uint32_t parity = P.epoch & 1u;
@@ -587,7 +564,7 @@ DR_D void phase_signal(const EngineParams& P) {
 }
 
 // ===========================================================================
-// phase 7: decode.  Contiguous tile range per CTA; rank-major so one staged
+// phase 8: decode.  Contiguous tile range per CTA; rank-major so one staged
 // filter serves all of the CTA's tiles of that tensor; sparse RMW into the
 // zero-filled dense output.
 // ===========================================================================
@@ -608,9 +585,8 @@ DR_D void phase_decode(const EngineParams& P, Smem& sm) {
     for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < (uint32_t)kNumHist * P.n_tensors; i += gridDim.x * kThreads)
       P.hist_total[i] = 0u;
   }
-  const uint32_t t_begin = (uint32_t)(((uint64_t)P.n_tiles * blockIdx.x) / gridDim.x);
-  const uint32_t t_end = (uint32_t)(((uint64_t)P.n_tiles * (blockIdx.x + 1)) / gridDim.x);
-  uint32_t tile = t_begin;
+  uint32_t tile, t_end;
+  tile_range(P, tile, t_end);
   while (tile < t_end) {
     const TileInfo t0 = load_tile(P, tile);
     const uint32_t t = t0.tensor;
@@ -705,6 +681,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) dr_engine_kernel(const _
       case kPhFallback: if (P.use_history) hist_tiles<1>(P, sm); else ran = false; break;
       case kPhHist2: hist_tiles<2>(P, sm); break;
       case kPhInsert: phase_insert(P, sm); break;
+      case kPhQuery: phase_query(P, sm); break;
       case kPhEmit: phase_emit(P, sm); break;
       case kPhPush: if (P.world > 1) phase_push(P); else ran = false; break;
       case kPhSignal: if (P.world > 1) phase_signal(P); else ran = false; break;

@@ -80,11 +80,12 @@ enum Phase : int {
   kPhFallback = 1,   // digit 1 redone without the bound for tensors whose bound was unsafe
   kPhHist2 = 2,      // digit 2 of the keys in the threshold bin
   kPhInsert = 3,     // resolve T22, bloom insert of the selected set
-  kPhEmit = 4,       // universe query + ordered compaction + value gather + residual zeroing
-  kPhPush = 5,       // copy the finished slot into every peer's arena (P2P stores over NVLink)
-  kPhSignal = 6,     // release flags to peers, acquire peers' flags
-  kPhDecode = 7,     // membership test on every rank's filter, rank->value, sum, scale, dense write
-  kPhEnd = 8
+  kPhQuery = 4,      // universe query against my filter: per-element flags + per-tile counts
+  kPhEmit = 5,       // ordered compaction (local prefix of the counts) + value gather + residual zeroing
+  kPhPush = 6,       // copy the finished slot into every peer's arena (P2P stores over NVLink)
+  kPhSignal = 7,     // release flags to peers, acquire peers' flags
+  kPhDecode = 8,     // membership test on every rank's filter, rank->value, sum, scale, dense write
+  kPhEnd = 9
 };
 
 // per-tile table (uint4): {tensor id, element offset of the tile in the flat buffers, valid count, offset inside tensor}
@@ -102,7 +103,8 @@ struct EngineParams {
   uint32_t* hist;                // [3][n_tensors][kHistBins]
   uint32_t* hist_total;          // [3][n_tensors]
   SelState* sel;                 // [n_tensors]
-  uint64_t* pos_desc;            // [n_tiles] look-back descriptors (epoch tagged)
+  uint32_t* tile_count;          // [n_tiles] selected/positive count of every tile (query phase)
+  uint8_t* flag_buf;             // [n_tiles * 512] per-thread 8-bit element flags (query -> emit)
   uint32_t* barrier;             // grid barrier counter (zeroed by host per launch)
   uint32_t* status;              // [8] error / watchdog words (device-local)
   uint32_t* arena[kMaxWorld];    // peer-mapped arena base of every rank (arena[rank] is local)

@@ -26,6 +26,19 @@ from .engine import PH_ACCUM, PH_END, BucketEngine
 from .plan import BucketPlan
 
 
+def _is_dense(p: torch.Tensor) -> bool:
+    """True if p's strides describe a permutation-dense layout (contiguous / channels_last / ...)."""
+    sizes, strides = list(p.size()), list(p.stride())
+    expect = 1
+    for st, sz in sorted(zip(strides, sizes)):
+        if sz == 1:
+            continue
+        if st != expect:
+            return False
+        expect *= sz
+    return True
+
+
 def _fused_supported(params: dict) -> bool:
     if params.get('compressor') != 'topk' or params.get('communicator', 'allgather') != 'allgather':
         return False
@@ -107,9 +120,12 @@ class DeepReduceDDP:
                 flat = torch.zeros(plan.total_elems, dtype=torch.float32, device=self.device)
                 views = plan.views(flat)
             self.flat.append(flat)
-            for (n, p), v in zip(items, views):
+            for (n, p), t in zip(items, plan.tensors):
                 assert p.dtype == torch.float32, "flat buckets hold fp32 master gradients"
-                p.grad = v
+                seg = flat[t.elem_off:t.elem_off + t.numel]
+                # the gradient view mirrors the parameter's own (dense) layout — e.g. channels_last conv
+                # weights — so fused optimizers see identical strides; the bucket is in storage order
+                p.grad = seg.as_strided(p.size(), p.stride()) if _is_dense(p) else seg.view(p.shape)
                 self.bucket_of[id(p)] = b
         self._ready_count = [0] * len(self.buckets)
         self._bucket_size = [len(it) for it in self.buckets]

@@ -24,9 +24,9 @@ from ..codecs.bloom import bloom_insert_oracle, bloom_query_oracle
 from .plan import (ARENA_HDR_WORDS, DYN_WORDS, HIST_BINS, MODE_BLOOM, MODE_RAW, NUM_HIST, POLICY_ID,
                    SLOT_HEADER_WORDS, BucketPlan)
 
-PH_ACCUM, PH_FALLBACK, PH_HIST2, PH_INSERT, PH_EMIT, PH_PUSH, PH_SIGNAL, PH_DECODE, PH_END = range(9)
+PH_ACCUM, PH_FALLBACK, PH_HIST2, PH_INSERT, PH_QUERY, PH_EMIT, PH_PUSH, PH_SIGNAL, PH_DECODE, PH_END = range(10)
 MAGIC = 0xD33B2000
-STATUS_NAMES = {0: "ok", 1: "look-back watchdog", 2: "peer flag watchdog", 3: "select resolve failed", 4: "grid barrier watchdog"}
+STATUS_NAMES = {0: "ok", 1: "(unused)", 2: "peer flag watchdog", 3: "select resolve failed", 4: "grid barrier watchdog"}
 
 
 # ---------------------------------------------------------------------------
@@ -136,14 +136,15 @@ class BucketEngine:
             self.hist = torch.zeros(NUM_HIST * nT * HIST_BINS, dtype=torch.int32, device=dev)
             self.hist_total = torch.zeros(NUM_HIST * nT, dtype=torch.int32, device=dev)
             self.sel = torch.zeros(nT * 8, dtype=torch.int32, device=dev)
-            self.pos_desc = torch.zeros(nt, dtype=torch.int64, device=dev)
+            self.tile_count = torch.zeros(nt, dtype=torch.int32, device=dev)
+            self.flag_buf = torch.zeros(nt * 512, dtype=torch.uint8, device=dev)
             self.barrier = torch.zeros(16, dtype=torch.int32, device=dev)
             self.status = torch.zeros(8, dtype=torch.int32, device=dev)
             self._setup_arena()
             self.ctx = self.mod.Engine(
                 self.tensor_table.data_ptr(), self.tile_table.data_ptr(), nT, nt, plan.slot_words, plan.payload_words,
                 self.grad.data_ptr(), self.resid.data_ptr(), self.hist.data_ptr(), self.hist_total.data_ptr(),
-                self.sel.data_ptr(), self.pos_desc.data_ptr(),
+                self.sel.data_ptr(), self.tile_count.data_ptr(), self.flag_buf.data_ptr(),
                 self.barrier.data_ptr(), self.status.data_ptr(), self.arena_ptrs, self.rank, self.world)
             scale = (1.0 / self.world) if average else 1.0
             if filter_smem_bytes is None:      # <1>: 128 regs, 1 CTA/SM; <2>: 64 regs, 2 CTAs/SM

@@ -11,7 +11,7 @@ sys.path.insert(0, ROOT)
 from deepreduce_b200.models import resnet50  # noqa: E402
 from deepreduce_b200.parallel import BucketEngine, BucketPlan  # noqa: E402
 
-PHASES = ["accum+hist1", "fallback", "hist2", "insert", "emit", "push", "signal", "decode"]
+PHASES = ["accum+hist1", "fallback", "hist2", "insert", "query", "emit", "push", "signal", "decode"]
 
 
 def main():
