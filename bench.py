@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--no-thread", action="store_true")
     ap.add_argument("--bucket-mb", type=float, default=32.0)
-    ap.add_argument("--blocks-per-sm", type=int, default=1)
+    ap.add_argument("--blocks-per-sm", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="also time the exchange kernel alone (extra keys)")
     return ap.parse_args()

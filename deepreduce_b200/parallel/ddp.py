@@ -53,7 +53,7 @@ def _fused_supported(params: dict) -> bool:
 
 class DeepReduceDDP:
     def __init__(self, module: nn.Module, params: dict, *, bucket_cap_mb: float = 1e9, overlap: bool = True,
-                 group=None, blocks_per_sm: int = 1, use_history: bool = True, background_thread: bool = True):
+                 group=None, blocks_per_sm: int = 2, use_history: bool = True, background_thread: bool = True):
         self.module = module
         self.params = dict(params)
         self.group = group

@@ -112,7 +112,7 @@ class BucketEngine:
     """One flat bucket + its fused exchange kernel."""
 
     def __init__(self, plan: BucketPlan, device=None, group=None, *, beta: float = 1.0, gamma: float = 1.0,
-                 average: bool = True, use_history: bool = True, blocks_per_sm: int = 1,
+                 average: bool = True, use_history: bool = True, blocks_per_sm: int = 2,
                  seed: int = spec.DEFAULT_SEED, spin_limit: int = 20_000_000, world: Optional[int] = None,
                  rank: Optional[int] = None, filter_smem_bytes: Optional[int] = None):
         from .. import ops

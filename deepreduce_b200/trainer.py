@@ -24,7 +24,7 @@ class Trainer:
                  weight_decay: float = 1e-4, amp_dtype: Optional[torch.dtype] = torch.bfloat16,
                  channels_last: bool = False, loss_fn: Optional[Callable] = None, optimizer=None,
                  overlap: bool = True, bucket_cap_mb: float = 1e9, background_thread: bool = True,
-                 blocks_per_sm: int = 1, u8_input: bool = False):
+                 blocks_per_sm: int = 2, u8_input: bool = False):
         self.model = model
         self.device = next(model.parameters()).device
         self.is_cuda = self.device.type == "cuda"

@@ -187,7 +187,7 @@ def test_grace_path_cuda_matches_cpu(cfg):
     sc, sg = set(out_cpu.nonzero().flatten().tolist()), set(out_gpu.nonzero().flatten().tolist())
     assert len(sc ^ sg) <= 12, len(sc ^ sg)
     both = torch.tensor(sorted(sc & sg))
-    if cfg.get('index') != 'bloom' and cfg.get('deepreduce') != 'both':
+    if cfg.get('index') != 'bloom' and cfg.get('deepreduce') != 'both' and cfg.get('value') != 'qsgd':   # qsgd buckets follow value order
         assert torch.allclose(out_cpu[both], out_gpu[both], atol=5e-3, rtol=1e-3)
     assert torch.nn.functional.cosine_similarity(out_cpu, out_gpu, dim=0) > 0.98
 
