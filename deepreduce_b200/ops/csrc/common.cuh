@@ -44,15 +44,22 @@ DR_HD uint32_t policy_hash(uint32_t x, uint32_t seed) {
   return fmix32((x * kGolden + seed) ^ 0x5BD1E995u);
 }
 
-// Membership test with early exit.  `filter` is a bit-packed uint32 array.
+// Membership test with early exit, two probes per iteration (both loads in flight).
+// `filter` is a bit-packed uint32 array.
 template <typename LoadFn>
 DR_D bool bloom_test(uint32_t x, uint32_t seed, uint32_t n_hash, uint32_t m_bits, LoadFn ld) {
   HashAB h = hash_ab(x, seed);
   uint32_t v = h.a;
-  for (uint32_t j = 0; j < n_hash; ++j) {
-    uint32_t pos = mulhi32(v, m_bits);
-    if (!((ld(pos >> 5) >> (pos & 31u)) & 1u)) return false;
-    v += h.b;
+  uint32_t j = 0;
+  for (; j + 1 < n_hash; j += 2) {
+    const uint32_t p0 = mulhi32(v, m_bits), p1 = mulhi32(v + h.b, m_bits);
+    const uint32_t w0 = ld(p0 >> 5), w1 = ld(p1 >> 5);
+    if (!((w0 >> (p0 & 31u)) & (w1 >> (p1 & 31u)) & 1u)) return false;
+    v += 2u * h.b;
+  }
+  if (j < n_hash) {
+    const uint32_t p0 = mulhi32(v, m_bits);
+    if (!((ld(p0 >> 5) >> (p0 & 31u)) & 1u)) return false;
   }
   return true;
 }

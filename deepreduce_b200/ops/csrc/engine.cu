@@ -67,9 +67,11 @@ DR_D uint32_t* slot_ptr(uint32_t* arena, const EngineParams& P, uint32_t parity,
   return arena + kArenaHdrWords + (size_t)(parity * (uint32_t)P.world + (uint32_t)src) * P.slot_words;
 }
 
-DR_D TileInfo load_tile(const EngineParams& P, uint32_t tile) {
+struct Tile { uint32_t tensor, base, n, local0, single; };   // `single`: the tensor has exactly one tile
+
+DR_D Tile load_tile(const EngineParams& P, uint32_t tile) {
   const uint4 q = __ldg(reinterpret_cast<const uint4*>(P.tiles) + tile);
-  TileInfo t; t.tensor = q.x; t.base = q.y; t.n = q.z; t.local0 = q.w;
+  Tile t; t.tensor = q.x; t.base = q.y; t.n = q.z & 0xFFFFu; t.local0 = q.w; t.single = q.z >> 31;
   return t;
 }
 
@@ -126,14 +128,20 @@ DR_D void tile_rank(uint32_t flags, ScanSmem& s, uint32_t (&rank)[kPerThread], u
 // Result in s.res: [0] bin (0xFFFFFFFF if total < k), [1] k remaining inside
 // the bin, [2] count in the bin.
 // ---------------------------------------------------------------------------
-DR_D void resolve_bins(const uint32_t* __restrict__ H, int nbins, uint32_t k, ScanSmem& s) {
+DR_D uint32_t* hist_ptr(const EngineParams& P, int which, uint32_t t) {
+  return P.hist + ((size_t)which * P.n_tensors + t) * kHistBins;
+}
+
+template <typename LoadFn>
+DR_D void resolve_bins(LoadFn H, int nbins, uint32_t k, ScanSmem& s) {
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  __syncthreads();
   if (tid == 0) { s.res[0] = 0xFFFFFFFFu; s.res[1] = 0; s.res[2] = 0; }
   uint32_t c[4], sum = 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int rb = (int)tid * 4 + i;            // reversed position: 0 = largest digit
-    c[i] = (rb < nbins) ? __ldcg(H + (nbins - 1 - rb)) : 0u;
+    c[i] = (rb < nbins) ? H(nbins - 1 - rb) : 0u;
     sum += c[i];
   }
   uint32_t incl = sum;
@@ -160,26 +168,47 @@ DR_D void resolve_bins(const uint32_t* __restrict__ H, int nbins, uint32_t k, Sc
   __syncthreads();
 }
 
-DR_D void flush_hist(uint32_t* __restrict__ gh, uint32_t* __restrict__ gtotal, Smem& sm) {
-  __syncthreads();
-  uint32_t part = 0;
-  for (int j = threadIdx.x; j < kHistBins; j += kThreads) {
-    const uint32_t v = sm.u.hist[j];
-    if (v) { atomicAdd(gh + j, v); part += v; sm.u.hist[j] = 0; }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
-  if ((threadIdx.x & 31u) == 0 && part) atomicAdd(gtotal, part);
-  __syncthreads();
-}
-
 DR_D void clear_hist(Smem& sm) {
+  __syncthreads();
   for (int j = threadIdx.x; j < kHistBins; j += kThreads) sm.u.hist[j] = 0;
   __syncthreads();
 }
 
-DR_D uint32_t* hist_ptr(const EngineParams& P, int which, uint32_t t) {
-  return P.hist + ((size_t)which * P.n_tensors + t) * kHistBins;
+DR_D void flush_hist(uint32_t* __restrict__ gh, Smem& sm) {
+  __syncthreads();
+  for (int j = threadIdx.x; j < kHistBins; j += kThreads) {
+    const uint32_t v = sm.u.hist[j];
+    if (v) { atomicAdd(gh + j, v); sm.u.hist[j] = 0; }
+  }
+  __threadfence();                              // merged counts are visible before the ticket is taken
+  __syncthreads();
+}
+
+// Finish one digit of one tensor for this CTA.  If the CTA owns every tile of the tensor the digit is
+// resolved straight from the SMEM histogram; otherwise the histogram is merged into the global one and
+// the CTA whose merge completes the tensor (ticket count == n_tiles) resolves it — once per tensor,
+// inside the same phase, no extra grid barrier.  Returns true (CTA-uniform) if this CTA resolved; the
+// result is then in sm.s.res.
+DR_D bool finish_digit(const EngineParams& P, Smem& sm, int which, uint32_t t, uint32_t n_mine, uint32_t n_tiles,
+                       uint32_t k) {
+  if (n_mine == n_tiles) {
+    resolve_bins([&](int b) { return sm.u.hist[b]; }, kHistBins, k, sm.s);
+    clear_hist(sm);
+    return true;
+  }
+  uint32_t* gh = hist_ptr(P, which, t);
+  flush_hist(gh, sm);
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const uint32_t before = atomicAdd(P.hist_total + (size_t)which * P.n_tensors + t, n_mine);
+    sm.s.lb = (before + n_mine == n_tiles) ? 1u : 0u;
+    __threadfence();
+  }
+  __syncthreads();
+  const bool last = sm.s.lb != 0u;
+  __syncthreads();
+  if (last) resolve_bins([&](int b) { return __ldcg(gh + b); }, kHistBins, k, sm.s);
+  return last;
 }
 
 // stage a bloom filter (global, 16-byte aligned) into the dynamic SMEM buffer
@@ -208,8 +237,23 @@ DR_D uint32_t bloom_test8(uint32_t idx0, uint32_t valid, uint32_t seed, uint32_t
 }
 
 // ===========================================================================
-// phase 0: accumulate + hist digit 1
+// phase 0: accumulate + hist digit 1 (+ the whole select for single-tile tensors)
 // ===========================================================================
+constexpr uint32_t kUnsafe = 0xFFFFFFFFu;   // sel.bin1 marker: history bound hid the threshold -> fallback phase
+
+DR_D void write_digit1(const EngineParams& P, Smem& sm, uint32_t t) {
+  if (threadIdx.x == 0) { P.sel[t].bin1 = sm.s.res[0]; P.sel[t].krem1 = sm.s.res[1]; P.sel[t].done_epoch = 0; }
+}
+
+DR_D void write_final(const EngineParams& P, Smem& sm, uint32_t t, uint32_t bin1) {
+  if (threadIdx.x == 0) {
+    if (sm.s.res[0] == 0xFFFFFFFFu) atomicExch(P.status, kErrResolve);
+    const uint32_t T22 = max((bin1 << 11) | sm.s.res[0], 1u);
+    P.sel[t].bin2 = sm.s.res[0]; P.sel[t].krem2 = sm.s.res[1];
+    P.sel[t].thr = T22 << 9; P.sel[t].n_ge = sm.s.res[2];
+  }
+}
+
 DR_D void phase_accum(const EngineParams& P, Smem& sm) {
   const uint32_t parity = P.epoch & 1u;
   uint32_t* my_slot = slot_ptr(P.arena[P.rank], P, parity, P.rank);
@@ -221,13 +265,13 @@ DR_D void phase_accum(const EngineParams& P, Smem& sm) {
   }
   clear_hist(sm);
   const bool has_resid = (P.beta != 0.0f);
-  uint32_t cur = kNoTensor, lower = 0;
+  uint32_t cur = kNoTensor, lower = 0, n_mine = 0;
   uint32_t tile, t_end;
   tile_range(P, tile, t_end);
   if (tile >= t_end) return;
-  TileInfo ti = load_tile(P, tile);
+  Tile ti = load_tile(P, tile);
   float4 g[2], r[2];
-  auto issue = [&](const TileInfo& t, float4 (&gg)[2], float4 (&rr)[2]) {
+  auto issue = [&](const Tile& t, float4 (&gg)[2], float4 (&rr)[2]) {
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       const uint32_t e = (c * kThreads + threadIdx.x) * 4u;
@@ -237,24 +281,29 @@ DR_D void phase_accum(const EngineParams& P, Smem& sm) {
       }
     }
   };
+  auto finish = [&]() {      // digit 1 of tensor `cur` is complete for this CTA
+    const uint32_t k = __ldg(&P.tensors[cur].k), nt = __ldg(&P.tensors[cur].n_tiles);
+    if (finish_digit(P, sm, 0, cur, n_mine, nt, k)) write_digit1(P, sm, cur);
+  };
   issue(ti, g, r);
   while (true) {
     const uint32_t next = tile + 1;
-    TileInfo tn = ti;
+    Tile tn = ti;
     float4 gn[2], rn[2];
     const bool has_next = next < t_end;
     if (has_next) { tn = load_tile(P, next); issue(tn, gn, rn); }     // prefetch before binning the current tile
     if (ti.tensor != cur) {
-      if (cur != kNoTensor) flush_hist(hist_ptr(P, 0, cur), P.hist_total + cur, sm);
-      cur = ti.tensor;
+      if (cur != kNoTensor) finish();
+      cur = ti.tensor; n_mine = 0;
       const uint32_t prev = P.use_history ? __ldcg(&P.sel[cur].prev_thr) : 0u;
       lower = (prev > (1u << 23)) ? prev - (1u << 23) : 0u;           // half of last step's threshold
     }
+    uint32_t key[8];
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       const uint32_t e = (c * kThreads + threadIdx.x) * 4u;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
       if (e < ti.n) {
-        float4 a;
         if (has_resid) {
           a.x = P.beta * r[c].x + P.gamma * g[c].x; a.y = P.beta * r[c].y + P.gamma * g[c].y;
           a.z = P.beta * r[c].z + P.gamma * g[c].z; a.w = P.beta * r[c].w + P.gamma * g[c].w;
@@ -262,20 +311,40 @@ DR_D void phase_accum(const EngineParams& P, Smem& sm) {
           a.x = P.gamma * g[c].x; a.y = P.gamma * g[c].y; a.z = P.gamma * g[c].z; a.w = P.gamma * g[c].w;
         }
         *reinterpret_cast<float4*>(P.resid + ti.base + e) = a;
-        const uint32_t k0 = __float_as_uint(a.x) & 0x7FFFFFFFu, k1 = __float_as_uint(a.y) & 0x7FFFFFFFu;
-        const uint32_t k2 = __float_as_uint(a.z) & 0x7FFFFFFFu, k3 = __float_as_uint(a.w) & 0x7FFFFFFFu;
-        if (k0 >= lower) atomicAdd(&sm.u.hist[k0 >> 20], 1u);
-        if (e + 1 < ti.n && k1 >= lower) atomicAdd(&sm.u.hist[k1 >> 20], 1u);
-        if (e + 2 < ti.n && k2 >= lower) atomicAdd(&sm.u.hist[k2 >> 20], 1u);
-        if (e + 3 < ti.n && k3 >= lower) atomicAdd(&sm.u.hist[k3 >> 20], 1u);
       }
+      const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const bool ok = e + i < ti.n;
+        key[c * 4 + i] = ok ? (__float_as_uint(av[i]) & 0x7FFFFFFFu) : 0xFFFFFFFFu;   // 0xFFFFFFFF = not an element
+        if (ok && key[c * 4 + i] >= lower) atomicAdd(&sm.u.hist[key[c * 4 + i] >> 20], 1u);
+      }
+    }
+    n_mine += 1;
+    if (ti.single) {
+      // one-tile tensor: finish the whole 2-digit select here, from the keys still in registers
+      const uint32_t k = __ldg(&P.tensors[cur].k);
+      resolve_bins([&](int b) { return sm.u.hist[b]; }, kHistBins, k, sm.s);
+      const uint32_t bin1 = sm.s.res[0], krem1 = sm.s.res[1];
+      write_digit1(P, sm, cur);
+      clear_hist(sm);
+      if (bin1 != kUnsafe) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (key[i] != 0xFFFFFFFFu && (key[i] >> 20) == bin1) atomicAdd(&sm.u.hist[(key[i] >> 9) & 0x7FFu], 1u);
+        resolve_bins([&](int b) { return sm.u.hist[b]; }, kHistBins, krem1, sm.s);
+        write_final(P, sm, cur, bin1);
+        if (threadIdx.x == 0) P.sel[cur].done_epoch = P.epoch;
+        clear_hist(sm);
+      }
+      cur = kNoTensor; n_mine = 0;
     }
     if (!has_next) break;
     tile = next; ti = tn;
 #pragma unroll
     for (int c = 0; c < 2; ++c) { g[c] = gn[c]; r[c] = rn[c]; }
   }
-  if (cur != kNoTensor) flush_hist(hist_ptr(P, 0, cur), P.hist_total + cur, sm);
+  if (cur != kNoTensor) finish();
 }
 
 // generic "histogram one digit of the keys" pass over resid with tile prefetch
@@ -284,45 +353,53 @@ DR_D void phase_accum(const EngineParams& P, Smem& sm) {
 template <int kWhich>
 DR_D void hist_tiles(const EngineParams& P, Smem& sm) {
   clear_hist(sm);
-  uint32_t cur = kNoTensor;
+  uint32_t cur = kNoTensor, n_mine = 0, k_cur = 0, nt_cur = 0;
   bool active = false;
   uint32_t prefix = 0;
   uint32_t tile, t_end;
   tile_range(P, tile, t_end);
   if (tile >= t_end) return;
-  TileInfo ti = load_tile(P, tile);
+  Tile ti = load_tile(P, tile);
   uint4 q[2];
-  auto issue = [&](const TileInfo& t, uint4 (&qq)[2]) {
+  auto issue = [&](const Tile& t, uint4 (&qq)[2]) {
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       const uint32_t e = (c * kThreads + threadIdx.x) * 4u;
       if (e < t.n) qq[c] = ld_stream_u4(reinterpret_cast<const uint4*>(P.resid + t.base + e));
     }
   };
+  auto finish = [&]() {
+    if (!active) return;
+    if (finish_digit(P, sm, kWhich, cur, n_mine, nt_cur, k_cur)) {
+      if (kWhich == 1) {
+        if (threadIdx.x == 0 && sm.s.res[0] == 0xFFFFFFFFu) atomicExch(P.status, kErrResolve);
+        write_digit1(P, sm, cur);
+      } else {
+        write_final(P, sm, cur, prefix);
+      }
+    }
+  };
   if (kWhich == 2) issue(ti, q);
   while (true) {
     const uint32_t next = tile + 1;
     const bool has_next = next < t_end;
-    TileInfo tn = ti;
+    Tile tn = ti;
     uint4 qn[2];
     if (has_next) { tn = load_tile(P, next); if (kWhich == 2) issue(tn, qn); }
     if (ti.tensor != cur) {
-      if (cur != kNoTensor && active)
-        flush_hist(hist_ptr(P, kWhich, cur), P.hist_total + (size_t)kWhich * P.n_tensors + cur, sm);
-      cur = ti.tensor;
-      load_tensor(P, cur, sm);
-      const bool unsafe = P.use_history && (__ldcg(P.hist_total + cur) < sm.td.k);
+      if (cur != kNoTensor) finish();
+      cur = ti.tensor; n_mine = 0;
+      nt_cur = __ldg(&P.tensors[cur].n_tiles);
+      const uint32_t bin1 = __ldcg(&P.sel[cur].bin1);
+      const bool done = __ldcg(&P.sel[cur].done_epoch) == P.epoch;
       if (kWhich == 1) {
-        active = unsafe;
+        active = (bin1 == kUnsafe) && !done;
+        k_cur = __ldg(&P.tensors[cur].k);
       } else {
-        resolve_bins(hist_ptr(P, unsafe ? 1 : 0, cur), kHistBins, sm.td.k, sm.s);
-        prefix = sm.s.res[0];
-        if (tile == sm.td.tile_begin && threadIdx.x == 0) {
-          P.sel[cur].bin1 = sm.s.res[0]; P.sel[cur].krem1 = sm.s.res[1];
-          if (sm.s.res[0] == 0xFFFFFFFFu) atomicExch(P.status, kErrResolve);
-        }
-        active = true;
-        __syncthreads();
+        active = !done;
+        prefix = bin1;
+        k_cur = __ldcg(&P.sel[cur].krem1);
+        if (active && bin1 == kUnsafe && threadIdx.x == 0) atomicExch(P.status, kErrResolve);
       }
     }
     if (active) {
@@ -341,62 +418,76 @@ DR_D void hist_tiles(const EngineParams& P, Smem& sm) {
           }
         }
       }
+      n_mine += 1;
     }
     if (!has_next) break;
     tile = next; ti = tn;
     q[0] = qn[0]; q[1] = qn[1];
   }
-  if (cur != kNoTensor && active)
-    flush_hist(hist_ptr(P, kWhich, cur), P.hist_total + (size_t)kWhich * P.n_tensors + cur, sm);
+  if (cur != kNoTensor) finish();
 }
 
 // ===========================================================================
-// phase 3: threshold resolve + bloom insert
+// phase 3: bloom insert of the selected set (queue-compacted: the ~1 % selected elements of a tile are
+// gathered into an SMEM queue, then every thread sets one (element, hash) bit — no divergent tails)
 // ===========================================================================
 DR_D void phase_insert(const EngineParams& P, Smem& sm) {
   const uint32_t parity = P.epoch & 1u;
   uint32_t* my_slot = slot_ptr(P.arena[P.rank], P, parity, P.rank);
+  uint32_t* queue = sm.u.hist;                 // 4096 entries: reuses the histogram/acc union
   uint32_t cur = kNoTensor, T22 = 1;
   uint32_t tile, t_end;
   tile_range(P, tile, t_end);
   if (tile >= t_end) return;
-  TileInfo ti = load_tile(P, tile);
+  Tile ti = load_tile(P, tile);
   uint32_t v[kPerThread];
-  auto issue = [&](const TileInfo& t, uint32_t (&vv)[kPerThread]) {
+  auto issue = [&](const Tile& t, uint32_t (&vv)[kPerThread]) {
 #pragma unroll
     for (int c = 0; c < kPerThread; ++c) {
       const uint32_t e = c * kThreads + threadIdx.x;
-      vv[c] = (e < t.n) ? __float_as_uint(__ldcg(P.resid + t.base + e)) : 0u;
+      vv[c] = (e < t.n) ? (__float_as_uint(__ldcg(P.resid + t.base + e)) & 0x7FFFFFFFu) : 0u;
     }
   };
   issue(ti, v);
   while (true) {
     const uint32_t next = tile + 1;
     const bool has_next = next < t_end;
-    TileInfo tn = ti;
+    Tile tn = ti;
     uint32_t vn[kPerThread];
     if (has_next) { tn = load_tile(P, next); issue(tn, vn); }
     if (ti.tensor != cur) {
       cur = ti.tensor;
       load_tensor(P, cur, sm);
-      const uint32_t bin1 = __ldcg(&P.sel[cur].bin1), krem1 = __ldcg(&P.sel[cur].krem1);
-      resolve_bins(hist_ptr(P, 2, cur), kHistBins, krem1, sm.s);
-      T22 = max((bin1 << 11) | sm.s.res[0], 1u);
-      if (tile == sm.td.tile_begin && threadIdx.x == 0) {
-        P.sel[cur].bin2 = sm.s.res[0]; P.sel[cur].krem2 = sm.s.res[1];
-        P.sel[cur].thr = T22 << 9; P.sel[cur].n_ge = sm.s.res[2];
-        if (sm.s.res[0] == 0xFFFFFFFFu) atomicExch(P.status, kErrResolve);
-      }
-      __syncthreads();
+      T22 = __ldcg(&P.sel[cur].thr) >> 9;
     }
     if (sm.td.mode == kModeBloom) {
-      uint32_t* filter = my_slot + sm.td.off_filter;
-      const uint32_t n_hash = sm.td.n_hash, m_bits = sm.td.m_bits;
+      uint32_t mask = 0;
 #pragma unroll
-      for (int c = 0; c < kPerThread; ++c) {
-        const uint32_t e = c * kThreads + threadIdx.x;
-        if (e < ti.n && ((v[c] & 0x7FFFFFFFu) >> 9) >= T22) bloom_set(filter, ti.local0 + e, P.seed, n_hash, m_bits);
+      for (int c = 0; c < kPerThread; ++c) if ((v[c] >> 9) >= T22) mask |= 1u << c;   // padding lanes hold 0 (< T22 >= 1)
+      // slot allocation: warp scan of the per-thread counts + one SMEM atomic per warp
+      const uint32_t lane = threadIdx.x & 31u;
+      const uint32_t cnt = __popc(mask);
+      uint32_t incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t nb = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += nb; }
+      if (threadIdx.x == 0) sm.s.lb = 0;
+      __syncthreads();
+      uint32_t wbase = 0;
+      if (lane == 31 && incl) wbase = atomicAdd(&sm.s.lb, incl);
+      wbase = __shfl_sync(0xFFFFFFFFu, wbase, 31);
+      uint32_t slot = wbase + incl - cnt;
+#pragma unroll
+      for (int c = 0; c < kPerThread; ++c) if ((mask >> c) & 1u) queue[slot++] = ti.local0 + c * kThreads + threadIdx.x;
+      __syncthreads();
+      const uint32_t total = sm.s.lb, n_hash = sm.td.n_hash, m_bits = sm.td.m_bits;
+      uint32_t* filter = my_slot + sm.td.off_filter;
+      for (uint32_t i = threadIdx.x; i < total * n_hash; i += kThreads) {
+        const uint32_t ent = i / n_hash, j = i - ent * n_hash;
+        const HashAB h = hash_ab(queue[ent], P.seed);
+        const uint32_t pos = mulhi32(h.a + j * h.b, m_bits);
+        atomicOr(filter + (pos >> 5), 1u << (pos & 31u));
       }
+      __syncthreads();
     }
     if (!has_next) break;
     tile = next; ti = tn;
@@ -416,7 +507,7 @@ DR_D void phase_query(const EngineParams& P, Smem& sm) {
   uint32_t tile, t_end;
   tile_range(P, tile, t_end);
   for (; tile < t_end; ++tile) {
-    const TileInfo ti = load_tile(P, tile);
+    const Tile ti = load_tile(P, tile);
     if (ti.tensor != cur) {
       cur = ti.tensor;
       load_tensor(P, cur, sm);
@@ -471,7 +562,7 @@ DR_D void phase_emit(const EngineParams& P, Smem& sm) {
   uint32_t tile, t_end;
   tile_range(P, tile, t_end);
   for (; tile < t_end; ++tile) {
-    const TileInfo ti = load_tile(P, tile);
+    const Tile ti = load_tile(P, tile);
     if (ti.tensor != cur) {
       cur = ti.tensor;
       load_tensor(P, cur, sm);
@@ -588,14 +679,14 @@ DR_D void phase_decode(const EngineParams& P, Smem& sm) {
   uint32_t tile, t_end;
   tile_range(P, tile, t_end);
   while (tile < t_end) {
-    const TileInfo t0 = load_tile(P, tile);
+    const Tile t0 = load_tile(P, tile);
     const uint32_t t = t0.tensor;
     load_tensor(P, t, sm);
     const uint32_t seg_end = min(t_end, sm.td.tile_begin + sm.td.n_tiles);
     if (sm.td.mode == kModeBloom) {
       // 1) zero-fill my tiles of this tensor (contiguous in the flat buffer)
       {
-        const TileInfo tl = load_tile(P, seg_end - 1);
+        const Tile tl = load_tile(P, seg_end - 1);
         const uint32_t n_elems = (tl.base + tl.n) - t0.base;
         float4* dst = reinterpret_cast<float4*>(P.grad + t0.base);
         const uint32_t n4 = n_elems >> 2;
@@ -615,7 +706,7 @@ DR_D void phase_decode(const EngineParams& P, Smem& sm) {
         const float* vals = reinterpret_cast<const float*>(slot + sm.td.off_vals);
         if (fits) stage_filter(filter, sm.td.n_filter_words);
         for (uint32_t tl = tile; tl < seg_end; ++tl) {
-          const TileInfo ti = load_tile(P, tl);
+          const Tile ti = load_tile(P, tl);
           const uint32_t pre = __ldcg(slot + sm.td.off_prefix + (tl - sm.td.tile_begin));
           if (!(pre < n_sel && ti.local0 <= cutoff)) continue;       // tile-uniform: nothing of rank r lands here
           uint32_t valid = 0;
@@ -646,7 +737,7 @@ DR_D void phase_decode(const EngineParams& P, Smem& sm) {
       tile = seg_end;
     } else {
       for (; tile < seg_end; ++tile) {
-        const TileInfo ti = load_tile(P, tile);
+        const Tile ti = load_tile(P, tile);
         __syncthreads();
         for (int j = threadIdx.x; j < kTile; j += kThreads) sm.u.acc[j] = 0.0f;
         __syncthreads();

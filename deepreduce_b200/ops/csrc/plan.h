@@ -58,13 +58,13 @@ struct SelState {
   uint32_t bin1, krem1, bin2, krem2;
   uint32_t thr;         // selection threshold as a key lower bound: (T22 << 9), T22 = 22-bit prefix
   uint32_t n_ge;        // diagnostics: keys in the threshold bin
-  uint32_t reserved;
+  uint32_t done_epoch;  // == epoch when the accumulate phase already finished the select (one-tile tensors)
   uint32_t prev_thr;    // thr of the previous step (0 = none)
 };
 
 constexpr int kHistBins = 2048;
 constexpr int kNumHist = 3;
-// hist arrays: [3][n_tensors][kHistBins]  (pass1, pass1-fallback, pass2);  hist_total: [3][n_tensors]
+// hist arrays: [3][n_tensors][kHistBins]  (pass1, pass1-fallback, pass2);  hist_total: [3][n_tensors] merge tickets
 
 // arena layout per rank (uint32 words): [flags: 64][status: 64][slots: 2 * world * slot_words]
 constexpr uint32_t kArenaFlagWords = 64;
@@ -101,7 +101,7 @@ struct EngineParams {
   float* grad;                   // in: local dense grad; out: aggregated dense grad
   float* resid;                  // residual accumulator (persists across steps)
   uint32_t* hist;                // [3][n_tensors][kHistBins]
-  uint32_t* hist_total;          // [3][n_tensors]
+  uint32_t* hist_total;          // [3][n_tensors] merge tickets (#tiles whose histogram was merged)
   SelState* sel;                 // [n_tensors]
   uint32_t* tile_count;          // [n_tiles] selected/positive count of every tile (query phase)
   uint8_t* flag_buf;             // [n_tiles * 512] per-thread 8-bit element flags (query -> emit)

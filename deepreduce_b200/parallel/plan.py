@@ -132,7 +132,7 @@ class BucketPlan:
             rows = out[t.tile_begin:t.tile_begin + t.n_tiles]
             rows[:, 0] = i
             rows[:, 1] = t.elem_off + loc
-            rows[:, 2] = np.minimum(spec.TILE, t.numel - loc)
+            rows[:, 2] = np.minimum(spec.TILE, t.numel - loc) | ((1 << 31) if t.n_tiles == 1 else 0)
             rows[:, 3] = loc
         return torch.from_numpy(out.astype(np.uint32).view(np.int32).copy())
 
