@@ -202,15 +202,17 @@ struct Engine {
     P.beta = 1.f; P.gamma = 1.f; P.scale = 1.f / world; P.seed = dr::kDefaultSeed; P.policy = 0; P.use_history = 1;
     P.spin_limit = 20u * 1000u * 1000u;
     P.filter_smem_words = (uint32_t)(dyn_smem / 4);
+    P.use_tma = 1; P.hist_shift = 23;
     cudaGetDevice(&device);
   }
 
   void configure(double beta, double gamma, double scale, int64_t seed, int policy, int use_history, int64_t spin_limit,
-                 int bps, int64_t filter_smem_bytes) {
+                 int bps, int64_t filter_smem_bytes, int use_tma, int hist_shift) {
     P.beta = (float)beta; P.gamma = (float)gamma; P.scale = (float)scale; P.seed = (uint32_t)seed;
     P.policy = policy; P.use_history = use_history; P.spin_limit = (uint32_t)spin_limit;
     blocks_per_sm = bps; grid = 0;
     dyn_smem = (int)filter_smem_bytes; P.filter_smem_words = (uint32_t)(dyn_smem / 4);
+    P.use_tma = use_tma; P.hist_shift = (uint32_t)hist_shift;
   }
 
   void set_buffers(int64_t grad, int64_t resid) {

@@ -107,10 +107,38 @@ DR_D uint4 ld_stream_u4(const uint4* p) {
   return r;
 }
 
+// ---- TMA bulk copy (cp.async.bulk, 1-D) + mbarrier helpers ------------------------------------
+DR_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+DR_D void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+DR_D void mbar_inval(uint64_t* bar) {
+  asm volatile("mbarrier.inval.shared::cta.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+DR_D void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+DR_D void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+DR_D void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// global -> shared bulk copy executed by the TMA unit; completion is signalled on `bar` (complete_tx)
+DR_D void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+DR_D void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t* status = nullptr) {
+  uint32_t ok, spins = 0;
+  do {
+    if (++spins > (1u << 24)) { if (status) atomicExch(status, 5u); break; }   // watchdog: never hang the GPU
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+
 // Grid-wide barrier for a co-resident (cooperative-launch) grid.  `counter`
 // is zeroed by the host before launch; `*epoch` is a per-thread-0 register
 // copy counting barriers passed.
 DR_D void grid_barrier(uint32_t* counter, uint32_t& epoch, uint32_t* status, uint32_t spin_limit) {
+  fence_proxy_async();          // generic-proxy global writes of this phase vs. TMA (async-proxy) reads of the next
   __syncthreads();
   if (threadIdx.x == 0) {
     epoch += 1;

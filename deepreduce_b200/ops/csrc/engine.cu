@@ -59,6 +59,7 @@ struct Smem {
   } u;
   ScanSmem s;
   TensorDesc td;                              // current tensor
+  uint64_t bar[8];                            // mbarriers of the TMA tile ring
 };
 
 extern __shared__ __align__(16) uint32_t g_filter_smem[];   // dynamic: staged bloom filter
@@ -296,7 +297,7 @@ DR_D void phase_accum(const EngineParams& P, Smem& sm) {
       if (cur != kNoTensor) finish();
       cur = ti.tensor; n_mine = 0;
       const uint32_t prev = P.use_history ? __ldcg(&P.sel[cur].prev_thr) : 0u;
-      lower = (prev > (1u << 23)) ? prev - (1u << 23) : 0u;           // half of last step's threshold
+      lower = (prev > (1u << 23)) ? prev - (1u << P.hist_shift) : 0u;  // a fraction of last step's threshold
     }
     uint32_t key[8];
 #pragma unroll
@@ -493,6 +494,252 @@ DR_D void phase_insert(const EngineParams& P, Smem& sm) {
     tile = next; ti = tn;
 #pragma unroll
     for (int c = 0; c < kPerThread; ++c) v[c] = vn[c];
+  }
+}
+
+// ===========================================================================
+// TMA variants of the streaming phases.  The next tiles are fetched by the TMA unit
+// (cp.async.bulk global->shared, completion on an mbarrier) into a ring carved out of
+// the dynamic SMEM buffer, so the prefetch depth costs no registers (the 64-register
+// build spilled its register prefetch, see profiles/).  One elected thread issues.
+// ===========================================================================
+struct Ring {
+  uint8_t* buf;
+  uint32_t stage_bytes;
+  uint32_t n_stages;
+};
+
+DR_D Ring ring_setup(const EngineParams& P, Smem& sm, uint32_t stage_bytes, uint32_t max_stages) {
+  Ring r;
+  r.buf = reinterpret_cast<uint8_t*>(g_filter_smem);
+  r.stage_bytes = stage_bytes;
+  r.n_stages = min(max_stages, (P.filter_smem_words * 4u) / stage_bytes);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (uint32_t i = 0; i < r.n_stages; ++i) { mbar_inval(&sm.bar[i]); mbar_init(&sm.bar[i], 1); }
+    mbar_fence_init();
+    fence_proxy_async();
+  }
+  __syncthreads();
+  return r;
+}
+
+DR_D uint32_t round16(uint32_t bytes) { return (bytes + 15u) & ~15u; }
+
+DR_D void phase_accum_tma(const EngineParams& P, Smem& sm) {
+  const uint32_t parity_slot = P.epoch & 1u;
+  uint32_t* my_slot = slot_ptr(P.arena[P.rank], P, parity_slot, P.rank);
+  {
+    uint4* p = reinterpret_cast<uint4*>(my_slot);
+    const uint32_t n4 = (P.payload_words + 3u) >> 2;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n4; i += gridDim.x * kThreads) p[i] = z;
+  }
+  clear_hist(sm);
+  const bool has_resid = (P.beta != 0.0f);
+  const Ring ring = ring_setup(P, sm, 2u * kTile * 4u, 8u);      // stage = g tile | r tile
+  uint32_t t0, t_end;
+  tile_range(P, t0, t_end);
+  const uint32_t n_my = t_end - t0;
+  auto issue = [&](uint32_t i) {                                  // thread 0 only
+    const Tile t = load_tile(P, t0 + i);
+    const uint32_t s = i % ring.n_stages, bytes = round16(t.n * 4u);
+    uint8_t* dst = ring.buf + (size_t)s * ring.stage_bytes;
+    mbar_expect_tx(&sm.bar[s], has_resid ? 2u * bytes : bytes);
+    bulk_g2s(dst, P.grad + t.base, bytes, &sm.bar[s]);
+    if (has_resid) bulk_g2s(dst + kTile * 4u, P.resid + t.base, bytes, &sm.bar[s]);
+  };
+  if (threadIdx.x == 0) for (uint32_t i = 0; i < min(ring.n_stages, n_my); ++i) issue(i);
+  uint32_t cur = kNoTensor, lower = 0, n_mine = 0;
+  auto finish = [&]() {
+    const uint32_t k = __ldg(&P.tensors[cur].k), nt = __ldg(&P.tensors[cur].n_tiles);
+    if (finish_digit(P, sm, 0, cur, n_mine, nt, k)) write_digit1(P, sm, cur);
+  };
+  for (uint32_t i = 0; i < n_my; ++i) {
+    const Tile ti = load_tile(P, t0 + i);
+    if (ti.tensor != cur) {
+      if (cur != kNoTensor) finish();
+      cur = ti.tensor; n_mine = 0;
+      const uint32_t prev = P.use_history ? __ldcg(&P.sel[cur].prev_thr) : 0u;
+      lower = (prev > (1u << 23)) ? prev - (1u << P.hist_shift) : 0u;
+    }
+    const uint32_t s = i % ring.n_stages;
+    mbar_wait(&sm.bar[s], (i / ring.n_stages) & 1u, P.status);
+    const float4* sg = reinterpret_cast<const float4*>(ring.buf + (size_t)s * ring.stage_bytes);
+    const float4* sr = sg + kTile / 4;
+    uint32_t key[8];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const uint32_t v4 = c * kThreads + threadIdx.x, e = v4 * 4u;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (e < ti.n) {
+        const float4 g = sg[v4];
+        if (has_resid) {
+          const float4 r = sr[v4];
+          a.x = P.beta * r.x + P.gamma * g.x; a.y = P.beta * r.y + P.gamma * g.y;
+          a.z = P.beta * r.z + P.gamma * g.z; a.w = P.beta * r.w + P.gamma * g.w;
+        } else {
+          a.x = P.gamma * g.x; a.y = P.gamma * g.y; a.z = P.gamma * g.z; a.w = P.gamma * g.w;
+        }
+        *reinterpret_cast<float4*>(P.resid + ti.base + e) = a;
+      }
+      const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool ok = e + j < ti.n;
+        key[c * 4 + j] = ok ? (__float_as_uint(av[j]) & 0x7FFFFFFFu) : 0xFFFFFFFFu;
+        if (ok && key[c * 4 + j] >= lower) atomicAdd(&sm.u.hist[key[c * 4 + j] >> 20], 1u);
+      }
+    }
+    n_mine += 1;
+    __syncthreads();                                               // everyone is done with stage s
+    if (threadIdx.x == 0 && i + ring.n_stages < n_my) { fence_proxy_async(); issue(i + ring.n_stages); }
+    if (ti.single) {
+      const uint32_t k = __ldg(&P.tensors[cur].k);
+      resolve_bins([&](int b) { return sm.u.hist[b]; }, kHistBins, k, sm.s);
+      const uint32_t bin1 = sm.s.res[0], krem1 = sm.s.res[1];
+      write_digit1(P, sm, cur);
+      clear_hist(sm);
+      if (bin1 != kUnsafe) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (key[j] != 0xFFFFFFFFu && (key[j] >> 20) == bin1) atomicAdd(&sm.u.hist[(key[j] >> 9) & 0x7FFu], 1u);
+        resolve_bins([&](int b) { return sm.u.hist[b]; }, kHistBins, krem1, sm.s);
+        write_final(P, sm, cur, bin1);
+        if (threadIdx.x == 0) P.sel[cur].done_epoch = P.epoch;
+        clear_hist(sm);
+      }
+      cur = kNoTensor; n_mine = 0;
+    }
+  }
+  if (cur != kNoTensor) finish();
+}
+
+DR_D void phase_hist2_tma(const EngineParams& P, Smem& sm) {
+  clear_hist(sm);
+  const Ring ring = ring_setup(P, sm, kTile * 4u, 8u);
+  uint32_t t0, t_end;
+  tile_range(P, t0, t_end);
+  const uint32_t n_my = t_end - t0;
+  // tiles of tensors that are already done are never fetched: the issue order follows the list of active tiles
+  uint32_t cur = kNoTensor, n_mine = 0, k_cur = 0, nt_cur = 0, prefix = 0;
+  bool active = false;
+  auto tile_active = [&](uint32_t tensor) { return __ldcg(&P.sel[tensor].done_epoch) != P.epoch; };
+  // thread 0 keeps its own cursor over the active tiles to issue; consumers walk the same sequence
+  uint32_t issue_pos = 0, issued = 0;         // thread 0 state
+  auto issue_next = [&]() {                    // thread 0: fetch the next active tile, if any
+    while (issue_pos < n_my) {
+      const Tile t = load_tile(P, t0 + issue_pos);
+      ++issue_pos;
+      if (!tile_active(t.tensor)) continue;
+      const uint32_t s = issued % ring.n_stages, bytes = round16(t.n * 4u);
+      mbar_expect_tx(&sm.bar[s], bytes);
+      bulk_g2s(ring.buf + (size_t)s * ring.stage_bytes, P.resid + t.base, bytes, &sm.bar[s]);
+      ++issued;
+      return;
+    }
+  };
+  if (threadIdx.x == 0) for (uint32_t i = 0; i < ring.n_stages; ++i) issue_next();
+  auto finish = [&]() {
+    if (!active) return;
+    if (finish_digit(P, sm, 2, cur, n_mine, nt_cur, k_cur)) write_final(P, sm, cur, prefix);
+  };
+  uint32_t consumed = 0;
+  for (uint32_t i = 0; i < n_my; ++i) {
+    const Tile ti = load_tile(P, t0 + i);
+    if (ti.tensor != cur) {
+      if (cur != kNoTensor) finish();
+      cur = ti.tensor; n_mine = 0;
+      nt_cur = __ldg(&P.tensors[cur].n_tiles);
+      active = tile_active(cur);
+      prefix = __ldcg(&P.sel[cur].bin1);
+      k_cur = __ldcg(&P.sel[cur].krem1);
+      if (active && prefix == kUnsafe && threadIdx.x == 0) atomicExch(P.status, kErrResolve);
+    }
+    if (!active) continue;
+    const uint32_t s = consumed % ring.n_stages;
+    mbar_wait(&sm.bar[s], (consumed / ring.n_stages) & 1u, P.status);
+    const uint4* sq = reinterpret_cast<const uint4*>(ring.buf + (size_t)s * ring.stage_bytes);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const uint32_t v4 = c * kThreads + threadIdx.x, e = v4 * 4u;
+      if (e < ti.n) {
+        const uint4 q = sq[v4];
+        const uint32_t key[4] = {q.x & 0x7FFFFFFFu, q.y & 0x7FFFFFFFu, q.z & 0x7FFFFFFFu, q.w & 0x7FFFFFFFu};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (e + j < ti.n && (key[j] >> 20) == prefix) atomicAdd(&sm.u.hist[(key[j] >> 9) & 0x7FFu], 1u);
+      }
+    }
+    n_mine += 1;
+    ++consumed;
+    __syncthreads();
+    if (threadIdx.x == 0) { fence_proxy_async(); issue_next(); }
+  }
+  if (cur != kNoTensor) finish();
+}
+
+DR_D void phase_insert_tma(const EngineParams& P, Smem& sm) {
+  const uint32_t parity_slot = P.epoch & 1u;
+  uint32_t* my_slot = slot_ptr(P.arena[P.rank], P, parity_slot, P.rank);
+  uint32_t* queue = sm.u.hist;
+  const Ring ring = ring_setup(P, sm, kTile * 4u, 8u);
+  uint32_t t0, t_end;
+  tile_range(P, t0, t_end);
+  const uint32_t n_my = t_end - t0;
+  auto issue = [&](uint32_t i) {
+    const Tile t = load_tile(P, t0 + i);
+    const uint32_t s = i % ring.n_stages, bytes = round16(t.n * 4u);
+    mbar_expect_tx(&sm.bar[s], bytes);
+    bulk_g2s(ring.buf + (size_t)s * ring.stage_bytes, P.resid + t.base, bytes, &sm.bar[s]);
+  };
+  if (threadIdx.x == 0) for (uint32_t i = 0; i < min(ring.n_stages, n_my); ++i) issue(i);
+  uint32_t cur = kNoTensor, T22 = 1;
+  for (uint32_t i = 0; i < n_my; ++i) {
+    const Tile ti = load_tile(P, t0 + i);
+    if (ti.tensor != cur) {
+      cur = ti.tensor;
+      load_tensor(P, cur, sm);
+      T22 = __ldcg(&P.sel[cur].thr) >> 9;
+    }
+    const uint32_t s = i % ring.n_stages;
+    mbar_wait(&sm.bar[s], (i / ring.n_stages) & 1u, P.status);
+    const uint32_t* sv = reinterpret_cast<const uint32_t*>(ring.buf + (size_t)s * ring.stage_bytes);
+    uint32_t mask = 0;
+    if (sm.td.mode == kModeBloom) {
+#pragma unroll
+      for (int c = 0; c < kPerThread; ++c) {
+        const uint32_t e = c * kThreads + threadIdx.x;
+        if (e < ti.n && ((sv[e] & 0x7FFFFFFFu) >> 9) >= T22) mask |= 1u << c;
+      }
+    }
+    __syncthreads();                                               // stage s consumed
+    if (threadIdx.x == 0 && i + ring.n_stages < n_my) { fence_proxy_async(); issue(i + ring.n_stages); }
+    if (sm.td.mode == kModeBloom) {
+      const uint32_t lane = threadIdx.x & 31u;
+      const uint32_t cnt = __popc(mask);
+      uint32_t incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t nb = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += nb; }
+      if (threadIdx.x == 0) sm.s.lb = 0;
+      __syncthreads();
+      uint32_t wbase = 0;
+      if (lane == 31 && incl) wbase = atomicAdd(&sm.s.lb, incl);
+      wbase = __shfl_sync(0xFFFFFFFFu, wbase, 31);
+      uint32_t slot = wbase + incl - cnt;
+#pragma unroll
+      for (int c = 0; c < kPerThread; ++c) if ((mask >> c) & 1u) queue[slot++] = ti.local0 + c * kThreads + threadIdx.x;
+      __syncthreads();
+      const uint32_t total = sm.s.lb, n_hash = sm.td.n_hash, m_bits = sm.td.m_bits;
+      uint32_t* filter = my_slot + sm.td.off_filter;
+      for (uint32_t q = threadIdx.x; q < total * n_hash; q += kThreads) {
+        const uint32_t ent = q / n_hash, j = q - ent * n_hash;
+        const HashAB h = hash_ab(queue[ent], P.seed);
+        const uint32_t pos = mulhi32(h.a + j * h.b, m_bits);
+        atomicOr(filter + (pos >> 5), 1u << (pos & 31u));
+      }
+      __syncthreads();
+    }
   }
 }
 
@@ -762,16 +1009,20 @@ DR_D void phase_decode(const EngineParams& P, Smem& sm) {
 template <int kMinBlocks>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) dr_engine_kernel(const __grid_constant__ EngineParams P) {
   __shared__ Smem sm;
-  if (threadIdx.x == 0) sm.s.buf = 0;
+  if (threadIdx.x == 0) {
+    sm.s.buf = 0;
+    for (int i = 0; i < 8; ++i) mbar_init(&sm.bar[i], 1);
+    mbar_fence_init();
+  }
   __syncthreads();
   uint32_t bar_epoch = 0;
   for (int ph = P.phase_begin; ph < P.phase_end; ++ph) {
     bool ran = true;
     switch (ph) {
-      case kPhAccum: phase_accum(P, sm); break;
+      case kPhAccum: if (P.use_tma) phase_accum_tma(P, sm); else phase_accum(P, sm); break;
       case kPhFallback: if (P.use_history) hist_tiles<1>(P, sm); else ran = false; break;
-      case kPhHist2: hist_tiles<2>(P, sm); break;
-      case kPhInsert: phase_insert(P, sm); break;
+      case kPhHist2: if (P.use_tma) phase_hist2_tma(P, sm); else hist_tiles<2>(P, sm); break;
+      case kPhInsert: if (P.use_tma) phase_insert_tma(P, sm); else phase_insert(P, sm); break;
       case kPhQuery: phase_query(P, sm); break;
       case kPhEmit: phase_emit(P, sm); break;
       case kPhPush: if (P.world > 1) phase_push(P); else ran = false; break;

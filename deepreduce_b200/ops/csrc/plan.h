@@ -117,7 +117,9 @@ struct EngineParams {
   int use_history;               // pass-1 lower bound from prev_thr
   int phase_begin, phase_end;
   uint32_t spin_limit;           // watchdog for flag / look-back / barrier spins
-  uint32_t filter_smem_words;    // capacity of the dynamic-SMEM filter staging buffer
+  uint32_t filter_smem_words;    // capacity of the dynamic-SMEM buffer (filter staging / TMA tile ring)
+  int use_tma;                   // streaming phases fetch tiles with cp.async.bulk into an SMEM ring
+  uint32_t hist_shift;           // history bound = prev_thr - (1 << hist_shift): 23 -> x0.5, 22 -> ~x0.7
 };
 
 }  // namespace dr

@@ -26,7 +26,7 @@ from .plan import (ARENA_HDR_WORDS, DYN_WORDS, HIST_BINS, MODE_BLOOM, MODE_RAW, 
 
 PH_ACCUM, PH_FALLBACK, PH_HIST2, PH_INSERT, PH_QUERY, PH_EMIT, PH_PUSH, PH_SIGNAL, PH_DECODE, PH_END = range(10)
 MAGIC = 0xD33B2000
-STATUS_NAMES = {0: "ok", 1: "(unused)", 2: "peer flag watchdog", 3: "select resolve failed", 4: "grid barrier watchdog"}
+STATUS_NAMES = {0: "ok", 1: "(unused)", 2: "peer flag watchdog", 3: "select resolve failed", 4: "grid barrier watchdog", 5: "TMA mbarrier watchdog"}
 
 
 # ---------------------------------------------------------------------------
@@ -114,7 +114,8 @@ class BucketEngine:
     def __init__(self, plan: BucketPlan, device=None, group=None, *, beta: float = 1.0, gamma: float = 1.0,
                  average: bool = True, use_history: bool = True, blocks_per_sm: int = 2,
                  seed: int = spec.DEFAULT_SEED, spin_limit: int = 20_000_000, world: Optional[int] = None,
-                 rank: Optional[int] = None, filter_smem_bytes: Optional[int] = None):
+                 rank: Optional[int] = None, filter_smem_bytes: Optional[int] = None, use_tma: bool = True,
+                 hist_shift: int = 23):
         from .. import ops
         self.mod = ops.cuda_module()
         self.plan = plan
@@ -150,7 +151,7 @@ class BucketEngine:
             if filter_smem_bytes is None:      # <1>: 128 regs, 1 CTA/SM; <2>: 64 regs, 2 CTAs/SM
                 filter_smem_bytes = 160 * 1024 if blocks_per_sm < 2 else 64 * 1024
             self.ctx.configure(self.beta, self.gamma, scale, int(seed), POLICY_ID[plan.policy], int(use_history),
-                               int(spin_limit), int(blocks_per_sm), int(filter_smem_bytes))
+                               int(spin_limit), int(blocks_per_sm), int(filter_smem_bytes), int(use_tma), int(hist_shift))
         self.grad_views = plan.views(self.grad)
 
     # ---- arena -------------------------------------------------------------
