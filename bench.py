@@ -118,6 +118,7 @@ def init_dist(args):
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
+    os.environ.setdefault("NCCL_DEBUG", "WARN")       # keep stdout to the single JSON line
     need = world > 1 or args.impl == "reference"
     if need:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
