@@ -222,6 +222,32 @@ DR_D void stage_filter(const uint32_t* __restrict__ filter, uint32_t n_words) {
   __syncthreads();
 }
 
+// Occupancy hint: 128 bits per tile, bit (c*16 + warp) covers the 32 consecutive elements that warp `warp`
+// owns in slot c.  valid_from_hint() turns the 4 words into this thread's 8-bit element mask.
+DR_D uint32_t valid_from_hint(const uint32_t (&h)[4]) {
+  const uint32_t warp = threadIdx.x >> 5;
+  uint32_t v = 0;
+#pragma unroll
+  for (int c = 0; c < kPerThread; ++c) v |= ((h[c >> 1] >> (((c & 1) << 4) + warp)) & 1u) << c;
+  return v;
+}
+
+// every warp publishes which of its 8 slots contain a flagged element; 4 words land in `dst` (SMEM scratch in `s`)
+DR_D void build_hint(uint32_t mask, ScanSmem& s, uint32_t* dst) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  if (threadIdx.x < 4) s.warp_tot[threadIdx.x] = 0;
+  __syncthreads();
+  uint32_t occ = 0;
+#pragma unroll
+  for (int c = 0; c < kPerThread; ++c) if (__ballot_sync(0xFFFFFFFFu, (mask >> c) & 1u)) occ |= 1u << c;
+  if (lane == 0) {
+#pragma unroll
+    for (int c = 0; c < kPerThread; ++c) if ((occ >> c) & 1u) atomicOr(&s.warp_tot[c >> 1], 1u << (((c & 1) << 4) + warp));
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) dst[threadIdx.x] = s.warp_tot[threadIdx.x];
+}
+
 DR_D void tile_range(const EngineParams& P, uint32_t& t_begin, uint32_t& t_end) {
   t_begin = (uint32_t)(((uint64_t)P.n_tiles * blockIdx.x) / gridDim.x);
   t_end = (uint32_t)(((uint64_t)P.n_tiles * (blockIdx.x + 1)) / gridDim.x);
@@ -465,6 +491,7 @@ DR_D void phase_insert(const EngineParams& P, Smem& sm) {
       uint32_t mask = 0;
 #pragma unroll
       for (int c = 0; c < kPerThread; ++c) if ((v[c] >> 9) >= T22) mask |= 1u << c;   // padding lanes hold 0 (< T22 >= 1)
+      if (sm.td.off_hint) build_hint(mask, sm.s, my_slot + sm.td.off_hint + 4u * (tile - sm.td.tile_begin));
       // slot allocation: warp scan of the per-thread counts + one SMEM atomic per warp
       const uint32_t lane = threadIdx.x & 31u;
       const uint32_t cnt = __popc(mask);
@@ -715,6 +742,8 @@ DR_D void phase_insert_tma(const EngineParams& P, Smem& sm) {
     }
     __syncthreads();                                               // stage s consumed
     if (threadIdx.x == 0 && i + ring.n_stages < n_my) { fence_proxy_async(); issue(i + ring.n_stages); }
+    if (sm.td.mode == kModeBloom && sm.td.off_hint)
+      build_hint(mask, sm.s, my_slot + sm.td.off_hint + 4u * ((t0 + i) - sm.td.tile_begin));
     if (sm.td.mode == kModeBloom) {
       const uint32_t lane = threadIdx.x & 31u;
       const uint32_t cnt = __popc(mask);
@@ -771,6 +800,11 @@ DR_D void phase_query(const EngineParams& P, Smem& sm) {
     uint32_t flags = 0;
     if (sm.td.mode == kModeBloom) {
       const uint32_t* filter = my_slot + sm.td.off_filter;
+      if (sm.td.off_hint) {
+        const uint4 hq = __ldcg(reinterpret_cast<const uint4*>(my_slot + sm.td.off_hint + 4u * (tile - sm.td.tile_begin)));
+        const uint32_t h[4] = {hq.x, hq.y, hq.z, hq.w};
+        valid &= valid_from_hint(h);
+      }
       if (staged) flags = bloom_test8(ti.local0 + threadIdx.x, valid, P.seed, sm.td.n_hash, sm.td.m_bits,
                                       [&](uint32_t w) { return g_filter_smem[w]; });
       else flags = bloom_test8(ti.local0 + threadIdx.x, valid, P.seed, sm.td.n_hash, sm.td.m_bits,
@@ -961,6 +995,12 @@ DR_D void phase_decode(const EngineParams& P, Smem& sm) {
           for (int c = 0; c < kPerThread; ++c) {
             const uint32_t e = c * kThreads + threadIdx.x;
             if (e < ti.n && ti.local0 + e <= cutoff) valid |= 1u << c;
+          }
+          if (sm.td.off_hint) {
+            const uint4 hq = __ldcg(reinterpret_cast<const uint4*>(slot + sm.td.off_hint + 4u * (tl - sm.td.tile_begin)));
+            if ((hq.x | hq.y | hq.z | hq.w) == 0u) continue;           // tile-uniform: rank r selected nothing here
+            const uint32_t h[4] = {hq.x, hq.y, hq.z, hq.w};
+            valid &= valid_from_hint(h);
           }
           uint32_t flags;
           if (fits) flags = bloom_test8(ti.local0 + threadIdx.x, valid, P.seed, n_hash, m_bits,

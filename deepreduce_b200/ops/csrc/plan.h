@@ -34,7 +34,7 @@ struct TensorDesc {
   uint32_t val_cap;      // capacity of the value region (K, or K+slack for p0)
   uint32_t salt;         // tensor id (policy seeds)
   uint32_t n_filter_words;
-  uint32_t reserved;
+  uint32_t off_hint;     // 0 = none; else 4 words per tile: bit g set <=> 32-element group g holds a selected element
 };
 static_assert(sizeof(TensorDesc) == 64, "TensorDesc must be 16 words");
 

@@ -107,7 +107,8 @@ class DeepReduceDDP:
                                   index='bloom' if self.params.get('deepreduce') == 'index' else None,
                                   fpr=self.params.get('fpr', None),
                                   policy=canonical_policy(self.params.get('policy', 'leftmost')),
-                                  min_numel=int(self.params.get('min_numel', spec.SMALL_TENSOR_NUMEL)))
+                                  min_numel=int(self.params.get('min_numel', spec.SMALL_TENSOR_NUMEL)),
+                                  hint=bool(self.params.get('hint', True)))
                 residual = self.params.get('memory', 'none') == 'residual'
                 eng = BucketEngine(plan, device=self.device, group=self.group,
                                    beta=float(self.params.get('beta', 1.0)) if residual else 0.0,

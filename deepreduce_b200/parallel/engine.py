@@ -56,6 +56,19 @@ def encode_tensor_oracle(tp, acc: torch.Tensor, slot: np.ndarray, t_index: int, 
     if tp.mode == MODE_BLOOM:
         words = bloom_insert_oracle(sel_topk, tp.n_hash, tp.m_bits, seed)
         pos = bloom_query_oracle(words, tp.numel, tp.n_hash, tp.m_bits, seed)
+        if tp.off_hint:
+            # occupancy hint: bit g of the tile's 128-bit field <=> the 32-element group g holds a selected element;
+            # positives outside occupied groups are dropped on both sides (they can only be false positives)
+            groups = torch.unique(sel_topk // 32)
+            occ = torch.zeros((tp.numel + 31) // 32, dtype=torch.bool)
+            occ[groups] = True
+            pos = pos[occ[pos // 32]]
+            hint = np.zeros(4 * tp.n_tiles, dtype=np.uint32)
+            g = groups.numpy().astype(np.int64)
+            tile, gi = g // 128, g % 128            # group gi of a tile covers elements [32*gi, 32*gi+32) of that tile...
+            # ...in the kernel's (slot c, warp w) order: element e = c*512 + w*32 + lane  ->  gi = e // 32 = c*16 + w
+            np.bitwise_or.at(hint, tile * 4 + gi // 32, (np.uint32(1) << (gi % 32).astype(np.uint32)))
+            slot[tp.off_hint:tp.off_hint + 4 * tp.n_tiles] = hint
         limit = tp.val_cap if policy == "p0" else min(tp.k, tp.val_cap)
         sel = pos[:limit]
         n_pos = int(pos.numel())

@@ -51,11 +51,12 @@ class TensorPlan:
     val_cap: int = 0
     salt: int = 0
     n_filter_words: int = 0
+    off_hint: int = 0
 
     def words(self) -> List[int]:
         return [self.elem_off, self.numel, self.k, self.tile_begin, self.n_tiles, self.mode, self.m_bits,
                 self.n_hash, self.off_vals, self.off_filter, self.off_prefix, self.off_idx, self.val_cap,
-                self.salt, self.n_filter_words, 0]
+                self.salt, self.n_filter_words, self.off_hint]
 
 
 @dataclass
@@ -70,6 +71,7 @@ class BucketPlan:
     min_numel: int = spec.SMALL_TENSOR_NUMEL
     max_hash: int = 16
     ks: Optional[Sequence[int]] = None    # explicit per-tensor K (overrides compress_ratio)
+    hint: bool = True                     # ship the 1-bit-per-32-elements occupancy hint next to each bloom filter
     tensors: List[TensorPlan] = field(default_factory=list, init=False)
 
     def __post_init__(self):
@@ -105,6 +107,9 @@ class BucketPlan:
                 word = _align(word + n_words, 4)
                 tp.off_prefix = word
                 word = _align(word + n_tiles, 4)
+                if self.hint:
+                    tp.off_hint = word
+                    word = _align(word + 4 * n_tiles, 4)
             else:
                 tp.val_cap = k
                 tp.off_vals = word

@@ -21,13 +21,14 @@ def test_plan_layout():
         assert t.elem_off % 32 == 0 and t.k == max(1, int(t.numel * 0.01))
         rows = tt[t.tile_begin:t.tile_begin + t.n_tiles]
         assert rows[:, 0].tolist() == [i] * t.n_tiles
-        assert rows[0, 1] == t.elem_off and int(rows[:, 2].sum()) == t.numel and rows[-1, 3] == (t.n_tiles - 1) * spec.TILE
+        assert rows[0, 1] == t.elem_off and int((rows[:, 2] & 0xFFFF).sum()) == t.numel and rows[-1, 3] == (t.n_tiles - 1) * spec.TILE
+        assert bool(rows[0, 2] < 0) == (t.n_tiles == 1)                 # bit 31 flags one-tile tensors
     # regions do not overlap and fit in the payload
     regions = []
     for t in plan.tensors:
         regions.append((t.off_vals, t.val_cap))
         if t.mode == MODE_BLOOM:
-            regions += [(t.off_filter, t.n_filter_words), (t.off_prefix, t.n_tiles)]
+            regions += [(t.off_filter, t.n_filter_words), (t.off_prefix, t.n_tiles), (t.off_hint, 4 * t.n_tiles)]
         else:
             regions.append((t.off_idx, t.k))
     regions.sort()
@@ -58,7 +59,7 @@ def test_select_rule_22bit_threshold():
 
 def test_oracle_matches_grace_path_single_rank():
     torch.manual_seed(0)
-    plan = BucketPlan([36864, 500, 9408], compress_ratio=0.01)
+    plan = BucketPlan([36864, 500, 9408], compress_ratio=0.01, hint=False)      # pure bloom == the per-tensor API
     g = torch.zeros(plan.total_elems)
     for v in plan.views(g):
         v.copy_(torch.randn_like(v))
@@ -102,3 +103,22 @@ def test_p0_capacity_and_header():
     assert n_sel == n_pos and n_sel >= t.k and cutoff == 0xFFFFFFFF
     true = set(torch.topk(g[:50000].abs(), t.k).indices.tolist())
     assert true <= set(out[:50000].nonzero().flatten().tolist())        # P0 is lossless w.r.t. top-k
+
+
+def test_occupancy_hint_removes_false_positives():
+    torch.manual_seed(5)
+    g = torch.randn(200000)
+    outs = {}
+    for hint in (False, True):
+        plan = BucketPlan([200000], compress_ratio=0.01, hint=hint)
+        gg = torch.zeros(plan.total_elems); gg[:200000] = g
+        out, res, slots = engine_oracle(plan, [gg], [torch.zeros_like(gg)])
+        outs[hint] = out[:200000]
+        if hint:
+            assert plan.tensors[0].off_hint > 0 and plan.wire_bytes() < 1.09 * plan_nohint_bytes
+        else:
+            plan_nohint_bytes = plan.wire_bytes()
+    true = set(torch.topk(g.abs(), 2000).indices.tolist())
+    kept = {h: len(true & set(outs[h].nonzero().flatten().tolist())) for h in outs}
+    assert kept[True] > kept[False]                 # fewer false positives displace true top-k entries
+    assert kept[True] >= 1940

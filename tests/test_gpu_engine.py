@@ -55,6 +55,10 @@ def _compare_slot(plan, slot_gpu, slot_ref, tag):
             pa, pb = a[t.off_prefix:t.off_prefix + t.n_tiles], b[t.off_prefix:t.off_prefix + t.n_tiles]
             if not np.array_equal(pa, pb):
                 bad.append(f"{t.name} prefix gpu={pa[:8].tolist()} ref={pb[:8].tolist()}")
+            if t.off_hint:
+                ha, hb = a[t.off_hint:t.off_hint + 4 * t.n_tiles], b[t.off_hint:t.off_hint + 4 * t.n_tiles]
+                if not np.array_equal(ha, hb):
+                    bad.append(f"{t.name} hint differs in {int((ha != hb).sum())}/{4 * t.n_tiles} words")
         else:
             ia, ib = a[t.off_idx:t.off_idx + n_sel], b[t.off_idx:t.off_idx + n_sel]
             if not np.array_equal(ia, ib):
@@ -71,11 +75,12 @@ SIZES = [64, 1000, 1001, 4096, 4097, 36864, 147456, 10, 589824]
 
 
 @pytest.mark.parametrize("kind", ["randn", "sparse", "ties"])
-@pytest.mark.parametrize("index,policy", [("bloom", "leftmost"), ("bloom", "p0"), (None, "leftmost")])
-def test_engine_vs_oracle_single_rank(kind, index, policy):
+@pytest.mark.parametrize("index,policy,hint,tma", [("bloom", "leftmost", True, True), ("bloom", "leftmost", False, False),
+                                                   ("bloom", "p0", True, True), (None, "leftmost", True, True)])
+def test_engine_vs_oracle_single_rank(kind, index, policy, hint, tma):
     from deepreduce_b200.parallel import BucketEngine, BucketPlan, engine_oracle
-    plan = BucketPlan(SIZES, compress_ratio=0.01, index=index, policy=policy)
-    eng = BucketEngine(plan, device="cuda:0", world=1, rank=0, spin_limit=2_000_000)
+    plan = BucketPlan(SIZES, compress_ratio=0.01, index=index, policy=policy, hint=hint)
+    eng = BucketEngine(plan, device="cuda:0", world=1, rank=0, spin_limit=2_000_000, use_tma=tma)
     gen = torch.Generator().manual_seed(0)
     resid_ref = torch.zeros(plan.total_elems)
     for step in range(3):                       # step 0: no history; steps 1,2: history lower bound (+fallback)
@@ -88,7 +93,7 @@ def test_engine_vs_oracle_single_rank(kind, index, policy):
         torch.cuda.synchronize()
         eng.check_status()
         out_ref, new_res, slots = engine_oracle(plan, [g], [resid_ref], epoch=eng.epoch)
-        tag = f"single_{kind}_{index}_{policy}_s{step}"
+        tag = f"single_{kind}_{index}_{policy}_{hint}_s{step}"
         bad = _compare_slot(plan, eng.slot(), slots[0], tag)
         assert not bad, bad[:4]
         assert torch.equal(eng.resid.cpu(), new_res[0]), tag
