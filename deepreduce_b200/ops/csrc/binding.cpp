@@ -215,6 +215,11 @@ struct Engine {
     P.use_tma = use_tma; P.hist_shift = (uint32_t)hist_shift;
   }
 
+  void set_poly(int64_t tensors, int64_t n_poly, int64_t tasks, int64_t n_tasks) {
+    P.poly_tensors = reinterpret_cast<const uint32_t*>(tensors); P.n_poly = (uint32_t)n_poly;
+    P.poly_tasks = reinterpret_cast<const uint32_t*>(tasks); P.n_poly_tasks = (uint32_t)n_tasks;
+  }
+
   void set_buffers(int64_t grad, int64_t resid) {
     P.grad = reinterpret_cast<float*>(grad); P.resid = reinterpret_cast<float*>(resid);
   }
@@ -387,6 +392,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
                     int64_t, int64_t, int64_t, int64_t, std::vector<int64_t>, int, int>())
       .def("configure", &Engine::configure)
       .def("set_buffers", &Engine::set_buffers)
+      .def("set_poly", &Engine::set_poly)
       .def("grid", &Engine::get_grid)
       .def("run", &Engine::run);
 

@@ -155,6 +155,24 @@ DR_D void grid_barrier(uint32_t* counter, uint32_t& epoch, uint32_t* status, uin
   __syncthreads();
 }
 
+// Gram (discrete Chebyshev) polynomials on the grid x = 0..N (N = n-1), exactly orthogonal there:
+// p_0=1, p_1=1-2x/N, (k+1)(N-k)p_{k+1} = (2k+1)(N-2x)p_k - k(N+k+1)p_{k-1}   (codecs/polyfit.py)
+template <int kDegP1>
+DR_D void gram_eval(float x, float N, int deg_eff, float (&p)[kDegP1]) {
+  p[0] = 1.f;
+#pragma unroll
+  for (int k = 1; k < kDegP1; ++k) p[k] = 0.f;
+  if (deg_eff >= 1) {
+    const float u = N - 2.f * x;
+    p[1] = u / N;
+#pragma unroll
+    for (int k = 1; k < kDegP1 - 1; ++k) {
+      if (k < deg_eff)
+        p[k + 1] = ((2.f * k + 1.f) * u * p[k] - (float)k * (N + k + 1.f) * p[k - 1]) / ((k + 1.f) * (N - k));
+    }
+  }
+}
+
 // launch accounting (bench.py's "gpu_launches")
 void count_launch(int n = 1);
 long long launch_count();

@@ -60,6 +60,8 @@ struct Smem {
   ScanSmem s;
   TensorDesc td;                              // current tensor
   uint64_t bar[8];                            // mbarriers of the TMA tile ring
+  int seg_start[kMaxSeg + 2];                 // 'both': segment boundaries of the current (tensor, rank)
+  int n_seg;
 };
 
 extern __shared__ __align__(16) uint32_t g_filter_smem[];   // dynamic: staged bloom filter
@@ -78,7 +80,7 @@ DR_D Tile load_tile(const EngineParams& P, uint32_t tile) {
 
 DR_D void load_tensor(const EngineParams& P, uint32_t t, Smem& sm) {
   __syncthreads();
-  if (threadIdx.x < 16) {
+  if (threadIdx.x < kDescWords) {
     reinterpret_cast<uint32_t*>(&sm.td)[threadIdx.x] =
         __ldg(reinterpret_cast<const uint32_t*>(P.tensors + t) + threadIdx.x);
   }
@@ -817,15 +819,12 @@ DR_D void phase_query(const EngineParams& P, Smem& sm) {
       }
     }
     P.flag_buf[(size_t)tile * kThreads + threadIdx.x] = (uint8_t)flags;
-    // block-wide popcount of the flags: warp reduce + one smem atomic per warp
+    // per-tile count: one fire-and-forget RED per warp (tile_count is zeroed by the previous step's decode
+    // phase) — no CTA barrier in this loop, so warps run ahead through their tiles independently
     uint32_t pc = __popc(flags);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) pc += __shfl_xor_sync(0xFFFFFFFFu, pc, o);
-    if (threadIdx.x == 0) sm.s.lb = 0;
-    __syncthreads();
-    if ((threadIdx.x & 31u) == 0 && pc) atomicAdd(&sm.s.lb, pc);
-    __syncthreads();
-    if (threadIdx.x == 0) P.tile_count[tile] = sm.s.lb;
+    if ((threadIdx.x & 31u) == 0 && pc) atomicAdd(P.tile_count + tile, pc);
   }
 }
 
@@ -882,6 +881,7 @@ DR_D void phase_emit(const EngineParams& P, Smem& sm) {
             vals[rp] = P.resid[base + e];
             P.resid[base + e] = 0.0f;                      // residual is exactly 0 on the shipped set
             if (sm.td.mode == kModeRaw) idxs[rp] = local0 + e;
+            if (sm.td.vmode) my_slot[sm.td.off_selidx + rp] = (uint32_t)(base + e);
             if (rp == limit - 1u) dyn->cutoff = local0 + e;
           }
         }
@@ -903,7 +903,166 @@ DR_D void phase_emit(const EngineParams& P, Smem& sm) {
 }
 
 // ===========================================================================
-// phase 6/7: push + flags
+// 'both' (bloom index + polynomial value fit): phases rank / fit / fix and the decode-side evaluation.
+// Replaces the reference's PolyFit (sort + per-segment Vandermonde normal equations with a CPU 6x6
+// inverse per segment, reference pytorch/deepreduce.py:306-425) and the int64 `mapping` (:263-267).
+// ===========================================================================
+// segment table of reference get_segments (:362-377): fine segments at both steep ends of the descending curve
+DR_D void build_segments(int n, int num_pos, int* start, int& n_seg) {
+  const double ratios[10] = {1.0 / 5, 1.0 / 10, 1.0 / 30, 1.0 / 100, 1.0 / 300, 1.0 / 1000, 1.0 / 3000, 1.0 / 10000, 1.0 / 30000, 1.0 / 100000};
+  int pos[10], neg[10], np = 0, nn = 0, sp = 0, sn = 0;
+  const int num_neg = n - num_pos;
+  for (int i = 0; i < 10; ++i) {
+    const int a = (int)((double)num_pos * ratios[i]);
+    if (a > 30) { pos[np++] = a; sp += a; }
+    const int b = (int)((double)num_neg * ratios[i]);
+    if (b > 30) { neg[nn++] = b; sn += b; }
+  }
+  int s = 0, acc = 0;
+  for (int i = np - 1; i >= 0; --i) { start[s++] = acc; acc += pos[i]; }
+  start[s++] = acc; acc += num_pos - sp;
+  start[s++] = acc; acc += num_neg - sn;
+  for (int i = 0; i < nn; ++i) { start[s++] = acc; acc += neg[i]; }
+  start[s] = acc;                               // == n
+  n_seg = s;
+}
+
+DR_D float poly_value(const float* __restrict__ coef, const int* start, int n_seg, int deg, uint32_t j) {
+  int s = 0;
+  for (int i = 0; i < n_seg; ++i) if (start[i + 1] > start[i] && (int)j >= start[i]) s = i;
+  const int len = start[s + 1] - start[s];
+  float p[kMaxDeg + 1];
+  gram_eval<kMaxDeg + 1>((float)((int)j - start[s]), (float)(len - 1), min(deg, len - 1), p);
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k <= kMaxDeg; ++k) if (k <= deg) acc += __ldcg(coef + s * (deg + 1) + k) * p[k];
+  return acc;
+}
+
+DR_D uint32_t load_rank(const uint32_t* slot, const TensorDesc& td, uint32_t p) {
+  return td.rank_u32 ? __ldcg(slot + td.off_rankmap + p)
+                     : (uint32_t)__ldcg(reinterpret_cast<const uint16_t*>(slot + td.off_rankmap) + p);
+}
+
+// phase 6: rank of every shipped value in the descending order (all-pairs count, exact, stable by position)
+DR_D void phase_rank(const EngineParams& P, Smem& sm) {
+  const uint32_t parity = P.epoch & 1u;
+  uint32_t* my_slot = slot_ptr(P.arena[P.rank], P, parity, P.rank);
+  float* tile = sm.u.acc;                       // 512-value chunks of the tensor's values
+  for (uint32_t task = blockIdx.x; task < P.n_poly_tasks; task += gridDim.x) {
+    const uint32_t t = __ldg(P.poly_tasks + 2 * task), p0 = __ldg(P.poly_tasks + 2 * task + 1);
+    load_tensor(P, t, sm);
+    const DynHeader* dyn = reinterpret_cast<const DynHeader*>(my_slot + kSlotHeaderWords) + t;
+    const uint32_t n = __ldcg(&dyn->n_sel);
+    if (p0 >= n) continue;
+    const float* vals = reinterpret_cast<const float*>(my_slot + sm.td.off_vals);
+    const uint32_t p = p0 + threadIdx.x;
+    const float v = p < n ? __ldcg(vals + p) : 0.f;
+    uint32_t rank = 0;
+    for (uint32_t q0 = 0; q0 < n; q0 += kThreads) {
+      __syncthreads();
+      const uint32_t q = q0 + threadIdx.x;
+      tile[threadIdx.x] = q < n ? __ldcg(vals + q) : -INFINITY;   // -inf never outranks anything
+      __syncthreads();
+      const uint32_t lim = min((uint32_t)kThreads, n - q0);
+      if (q0 + lim <= p0) {                     // whole chunk precedes mine: ties count
+#pragma unroll 8
+        for (uint32_t i = 0; i < lim; ++i) rank += (tile[i] >= v) ? 1u : 0u;
+      } else if (q0 >= p0 + kThreads) {         // whole chunk follows mine: ties do not count
+#pragma unroll 8
+        for (uint32_t i = 0; i < lim; ++i) rank += (tile[i] > v) ? 1u : 0u;
+      } else {                                  // my own chunk
+        for (uint32_t i = 0; i < lim; ++i) {
+          const float w = tile[i];
+          rank += (w > v || (w == v && q0 + i < p)) ? 1u : 0u;
+        }
+      }
+    }
+    if (p < n) {
+      if (sm.td.rank_u32) my_slot[sm.td.off_rankmap + p] = rank;
+      else reinterpret_cast<uint16_t*>(my_slot + sm.td.off_rankmap)[p] = (uint16_t)rank;
+      reinterpret_cast<float*>(my_slot + sm.td.off_sorted)[rank] = v;
+    }
+    // positives of this chunk -> num_pos (slot word zeroed in the accumulate phase); n is written once
+    const uint32_t pc = __syncthreads_count(p < n && v > 0.f);
+    if (threadIdx.x == 0) {
+      uint32_t* tail = my_slot + sm.td.off_coef + kMaxSeg * (sm.td.poly_degree + 1);
+      if (pc) atomicAdd(tail, pc);
+      if (p0 == 0) tail[1] = n;
+    }
+  }
+}
+
+// phase 7: one warp per (tensor, segment): Gram least squares  c_k = sum p_k y / sum p_k^2
+DR_D void phase_fit(const EngineParams& P, Smem& sm) {
+  const uint32_t parity = P.epoch & 1u;
+  uint32_t* my_slot = slot_ptr(P.arena[P.rank], P, parity, P.rank);
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t gw = blockIdx.x * kWarps + (threadIdx.x >> 5), nw = gridDim.x * kWarps;
+  for (uint32_t task = gw; task < P.n_poly * kMaxSeg; task += nw) {
+    const uint32_t t = __ldg(P.poly_tensors + task / kMaxSeg), s = task % kMaxSeg;
+    const TensorDesc* td = P.tensors + t;
+    const uint32_t off_coef = __ldg(&td->off_coef), off_sorted = __ldg(&td->off_sorted);
+    const int deg = (int)__ldg(&td->poly_degree);
+    const uint32_t* tail = my_slot + off_coef + kMaxSeg * (deg + 1);
+    const int num_pos = (int)__ldcg(tail), n = (int)__ldcg(tail + 1);
+    int start[kMaxSeg + 2], n_seg;
+    build_segments(n, num_pos, start, n_seg);
+    if ((int)s >= n_seg) continue;
+    const int len = start[s + 1] - start[s];
+    if (len <= 0) continue;
+    const float* y = reinterpret_cast<const float*>(my_slot + off_sorted) + start[s];
+    const int deg_eff = min(deg, len - 1);
+    float num[kMaxDeg + 1], den[kMaxDeg + 1];
+#pragma unroll
+    for (int k = 0; k <= kMaxDeg; ++k) { num[k] = 0.f; den[k] = 0.f; }
+    for (int x = lane; x < len; x += 32) {
+      float p[kMaxDeg + 1];
+      gram_eval<kMaxDeg + 1>((float)x, (float)(len - 1), deg_eff, p);
+      const float yi = __ldcg(y + x);
+#pragma unroll
+      for (int k = 0; k <= kMaxDeg; ++k) { num[k] += p[k] * yi; den[k] += p[k] * p[k]; }
+    }
+#pragma unroll
+    for (int k = 0; k <= kMaxDeg; ++k) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        num[k] += __shfl_xor_sync(0xFFFFFFFFu, num[k], o);
+        den[k] += __shfl_xor_sync(0xFFFFFFFFu, den[k], o);
+      }
+    }
+    float* coef = reinterpret_cast<float*>(my_slot + off_coef) + s * (deg + 1);
+#pragma unroll
+    for (int k = 0; k <= kMaxDeg; ++k)
+      if ((int)lane == k && k <= deg) coef[k] = (k <= deg_eff && den[k] > 0.f) ? num[k] / den[k] : 0.f;
+  }
+}
+
+// phase 8: error feedback sees the fit error: resid[idx_p] = value_p - fitted_p
+DR_D void phase_fix(const EngineParams& P, Smem& sm) {
+  const uint32_t parity = P.epoch & 1u;
+  uint32_t* my_slot = slot_ptr(P.arena[P.rank], P, parity, P.rank);
+  for (uint32_t task = blockIdx.x; task < P.n_poly_tasks; task += gridDim.x) {
+    const uint32_t t = __ldg(P.poly_tasks + 2 * task), p0 = __ldg(P.poly_tasks + 2 * task + 1);
+    load_tensor(P, t, sm);
+    const int deg = (int)sm.td.poly_degree;
+    const uint32_t* tail = my_slot + sm.td.off_coef + kMaxSeg * (deg + 1);
+    const int num_pos = (int)__ldcg(tail), n = (int)__ldcg(tail + 1);
+    if ((int)p0 >= n) continue;
+    if (threadIdx.x == 0) build_segments(n, num_pos, sm.seg_start, sm.n_seg);
+    __syncthreads();
+    const uint32_t p = p0 + threadIdx.x;
+    if ((int)p < n) {
+      const float fitted = poly_value(reinterpret_cast<const float*>(my_slot + sm.td.off_coef), sm.seg_start, sm.n_seg,
+                                      deg, load_rank(my_slot, sm.td, p));
+      const float v = __ldcg(reinterpret_cast<const float*>(my_slot + sm.td.off_vals) + p);
+      P.resid[__ldcg(my_slot + sm.td.off_selidx + p)] = v - fitted;
+    }
+  }
+}
+
+// ===========================================================================
+// phase 9/10: push + flags
 // ===========================================================================
 DR_D void phase_push(const EngineParams& P) {
   const uint32_t parity = P.epoch & 1u;
@@ -936,7 +1095,7 @@ DR_D void phase_signal(const EngineParams& P) {
 }
 
 // ===========================================================================
-// phase 8: decode.  Contiguous tile range per CTA; rank-major so one staged
+// phase 11: decode.  Contiguous tile range per CTA; rank-major so one staged
 // filter serves all of the CTA's tiles of that tensor; sparse RMW into the
 // zero-filled dense output.
 // ===========================================================================
@@ -956,6 +1115,7 @@ DR_D void phase_decode(const EngineParams& P, Smem& sm) {
     for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n4; i += (size_t)gridDim.x * kThreads) h[i] = z;
     for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < (uint32_t)kNumHist * P.n_tensors; i += gridDim.x * kThreads)
       P.hist_total[i] = 0u;
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < P.n_tiles; i += gridDim.x * kThreads) P.tile_count[i] = 0u;
   }
   uint32_t tile, t_end;
   tile_range(P, tile, t_end);
@@ -985,6 +1145,14 @@ DR_D void phase_decode(const EngineParams& P, Smem& sm) {
         if (n_sel == 0) continue;
         const uint32_t* filter = slot + sm.td.off_filter;
         const float* vals = reinterpret_cast<const float*>(slot + sm.td.off_vals);
+        if (sm.td.vmode) {          // 'both': rank r's segment table (from its n and num_pos)
+          __syncthreads();
+          if (threadIdx.x == 0) {
+            const uint32_t* tail = slot + sm.td.off_coef + kMaxSeg * (sm.td.poly_degree + 1);
+            build_segments((int)__ldcg(tail + 1), (int)__ldcg(tail), sm.seg_start, sm.n_seg);
+          }
+          __syncthreads();
+        }
         if (fits) stage_filter(filter, sm.td.n_filter_words);
         for (uint32_t tl = tile; tl < seg_end; ++tl) {
           const Tile ti = load_tile(P, tl);
@@ -1015,7 +1183,11 @@ DR_D void phase_decode(const EngineParams& P, Smem& sm) {
               const uint32_t rp = pre + rank[c];
               if (rp < n_sel) {
                 float* o = P.grad + ti.base + c * kThreads + threadIdx.x;   // the same thread owns this element for every rank
-                *o = *o + __ldcg(vals + rp) * P.scale;
+                const float val = sm.td.vmode
+                    ? poly_value(reinterpret_cast<const float*>(slot + sm.td.off_coef), sm.seg_start, sm.n_seg,
+                                 (int)sm.td.poly_degree, load_rank(slot, sm.td, rp))
+                    : __ldcg(vals + rp);
+                *o = *o + val * P.scale;
               }
             }
           }
@@ -1065,6 +1237,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) dr_engine_kernel(const _
       case kPhInsert: if (P.use_tma) phase_insert_tma(P, sm); else phase_insert(P, sm); break;
       case kPhQuery: phase_query(P, sm); break;
       case kPhEmit: phase_emit(P, sm); break;
+      case kPhRank: if (P.n_poly) phase_rank(P, sm); else ran = false; break;
+      case kPhFit: if (P.n_poly) phase_fit(P, sm); else ran = false; break;
+      case kPhFix: if (P.n_poly) phase_fix(P, sm); else ran = false; break;
       case kPhPush: if (P.world > 1) phase_push(P); else ran = false; break;
       case kPhSignal: if (P.world > 1) phase_signal(P); else ran = false; break;
       case kPhDecode: phase_decode(P, sm); break;

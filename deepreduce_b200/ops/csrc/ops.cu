@@ -173,24 +173,6 @@ __global__ void unpack_bits_kernel(const uint32_t* __restrict__ in, int64_t n_wo
 // Gram-polynomial least squares: one CTA per segment.
 // p_0=1, p_1=1-2x/N, (k+1)(N-k)p_{k+1} = (2k+1)(N-2x)p_k - k(N+k+1)p_{k-1}
 // ---------------------------------------------------------------------------
-constexpr int kMaxDeg = 7;
-
-template <int kDegP1>
-DR_D void gram_eval(float x, float N, int deg_eff, float (&p)[kDegP1]) {
-  p[0] = 1.f;
-#pragma unroll
-  for (int k = 1; k < kDegP1; ++k) p[k] = 0.f;
-  if (deg_eff >= 1) {
-    const float u = N - 2.f * x;
-    p[1] = u / N;
-#pragma unroll
-    for (int k = 1; k < kDegP1 - 1; ++k) {
-      if (k < deg_eff)
-        p[k + 1] = ((2.f * k + 1.f) * u * p[k] - (float)k * (N + k + 1.f) * p[k - 1]) / ((k + 1.f) * (N - k));
-    }
-  }
-}
-
 __global__ void __launch_bounds__(256) polyfit_fit_kernel(const float* __restrict__ y, const int* __restrict__ seg_off,
                                                           const int* __restrict__ seg_len, int degree,
                                                           float* __restrict__ coeffs) {

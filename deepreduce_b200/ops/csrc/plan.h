@@ -35,8 +35,20 @@ struct TensorDesc {
   uint32_t salt;         // tensor id (policy seeds)
   uint32_t n_filter_words;
   uint32_t off_hint;     // 0 = none; else 4 words per tile: bit g set <=> 32-element group g holds a selected element
+  // ---- value codec ('both': bloom index + polynomial fit of the values) ----
+  uint32_t vmode;        // 0 = fp32 values on the wire, 1 = piece-wise Gram-polynomial fit + rank map
+  uint32_t off_coef;     // [kMaxSeg * (deg+1)] float coefficients, then {num_pos, n}
+  uint32_t off_rankmap;  // rank of the p-th shipped value in the descending sort (u16 if val_cap <= 65536 else u32)
+  uint32_t off_selidx;   // scratch (not shipped): element index of the p-th shipped value
+  uint32_t off_sorted;   // scratch (not shipped): values in descending order
+  uint32_t poly_degree;
+  uint32_t rank_u32;     // 1: rank map entries are 32-bit
+  uint32_t reserved;
 };
-static_assert(sizeof(TensorDesc) == 64, "TensorDesc must be 16 words");
+static_assert(sizeof(TensorDesc) == 96, "TensorDesc must be 24 words");
+constexpr int kDescWords = 24;
+constexpr int kMaxSeg = 22;            // codecs/polyfit.py MAX_SEGMENTS
+constexpr int kMaxDeg = 7;
 
 // payload slot layout (uint32 words):
 //   [0..8)                      : magic, epoch, n_tensors, payload_words, rank, 0,0,0
@@ -82,10 +94,13 @@ enum Phase : int {
   kPhInsert = 3,     // resolve T22, bloom insert of the selected set
   kPhQuery = 4,      // universe query against my filter: per-element flags + per-tile counts
   kPhEmit = 5,       // ordered compaction (local prefix of the counts) + value gather + residual zeroing
-  kPhPush = 6,       // copy the finished slot into every peer's arena (P2P stores over NVLink)
-  kPhSignal = 7,     // release flags to peers, acquire peers' flags
-  kPhDecode = 8,     // membership test on every rank's filter, rank->value, sum, scale, dense write
-  kPhEnd = 9
+  kPhRank = 6,       // 'both': exact descending rank of every shipped value (all-pairs count) + rank map
+  kPhFit = 7,        // 'both': per-segment Gram-polynomial least squares on the sorted values
+  kPhFix = 8,        // 'both': residual <- value - fitted value (error feedback sees the fit error)
+  kPhPush = 9,       // copy the finished slot into every peer's arena (P2P stores over NVLink)
+  kPhSignal = 10,    // release flags to peers, acquire peers' flags
+  kPhDecode = 11,    // membership test on every rank's filter, rank->value, sum, scale, dense write
+  kPhEnd = 12
 };
 
 // per-tile table (uint4): {tensor id, element offset of the tile in the flat buffers, valid count, offset inside tensor}
@@ -120,6 +135,10 @@ struct EngineParams {
   uint32_t filter_smem_words;    // capacity of the dynamic-SMEM buffer (filter staging / TMA tile ring)
   int use_tma;                   // streaming phases fetch tiles with cp.async.bulk into an SMEM ring
   uint32_t hist_shift;           // history bound = prev_thr - (1 << hist_shift): 23 -> x0.5, 22 -> ~x0.7
+  const uint32_t* poly_tensors;  // ids of the tensors with vmode == 1 (largest K first)
+  uint32_t n_poly;
+  const uint32_t* poly_tasks;    // rank-phase tasks: {tensor id, first value of a 512-value chunk}
+  uint32_t n_poly_tasks;
 };
 
 }  // namespace dr

@@ -45,9 +45,12 @@ def _fused_supported(params: dict) -> bool:
     dr = params.get('deepreduce', None)
     if dr is None:
         return True
+    from ..codecs.bloom import canonical_policy
+    pol_ok = canonical_policy(params.get('policy', 'leftmost')) in ('leftmost', 'p0')
     if dr == 'index' and params.get('index', 'bloom') == 'bloom':
-        from ..codecs.bloom import canonical_policy
-        return canonical_policy(params.get('policy', 'leftmost')) in ('leftmost', 'p0')
+        return pol_ok
+    if dr == 'both' and params.get('index', 'bloom') == 'bloom' and params.get('value', 'polyfit') == 'polyfit':
+        return pol_ok
     return False
 
 
@@ -104,7 +107,9 @@ class DeepReduceDDP:
             shapes = [tuple(p.shape) for _, p in items]
             if self.fused:
                 plan = BucketPlan(numels, names, shapes, compress_ratio=self.params.get('compress_ratio', 0.01),
-                                  index='bloom' if self.params.get('deepreduce') == 'index' else None,
+                                  index='bloom' if self.params.get('deepreduce') in ('index', 'both') else None,
+                                  value='polyfit' if self.params.get('deepreduce') == 'both' else None,
+                                  poly_degree=int(self.params.get('poly_degree', 5)),
                                   fpr=self.params.get('fpr', None),
                                   policy=canonical_policy(self.params.get('policy', 'leftmost')),
                                   min_numel=int(self.params.get('min_numel', spec.SMALL_TENSOR_NUMEL)),

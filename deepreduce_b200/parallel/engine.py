@@ -24,7 +24,8 @@ from ..codecs.bloom import bloom_insert_oracle, bloom_query_oracle
 from .plan import (ARENA_HDR_WORDS, DYN_WORDS, HIST_BINS, MODE_BLOOM, MODE_RAW, NUM_HIST, POLICY_ID,
                    SLOT_HEADER_WORDS, BucketPlan)
 
-PH_ACCUM, PH_FALLBACK, PH_HIST2, PH_INSERT, PH_QUERY, PH_EMIT, PH_PUSH, PH_SIGNAL, PH_DECODE, PH_END = range(10)
+(PH_ACCUM, PH_FALLBACK, PH_HIST2, PH_INSERT, PH_QUERY, PH_EMIT, PH_RANK, PH_FIT, PH_FIX, PH_PUSH, PH_SIGNAL,
+ PH_DECODE, PH_END) = range(13)
 MAGIC = 0xD33B2000
 STATUS_NAMES = {0: "ok", 1: "(unused)", 2: "peer flag watchdog", 3: "select resolve failed", 4: "grid barrier watchdog", 5: "TMA mbarrier watchdog"}
 
@@ -83,8 +84,33 @@ def encode_tensor_oracle(tp, acc: torch.Tensor, slot: np.ndarray, t_index: int, 
         slot[tp.off_idx:tp.off_idx + sel.numel()] = sel.cpu().numpy().astype(np.uint32)
         cutoff = int(sel[-1].item()) if n_pos >= limit else 0xFFFFFFFF
     vals = acc[sel].float()
-    slot[tp.off_vals:tp.off_vals + sel.numel()] = vals.cpu().numpy().view(np.uint32)
-    resid[sel] = 0
+    if tp.vmode == 1:
+        # 'both': stable descending sort -> rank map; per-segment Gram fit; fitted values are what is shipped,
+        # and the residual keeps (value - fitted)
+        from ..codecs.polyfit import MAX_SEGMENTS, get_segments, polyfit_eval_oracle, polyfit_fit_oracle
+        n = int(sel.numel())
+        order = torch.sort(vals, descending=True, stable=True).indices
+        rank = torch.empty(n, dtype=torch.int64)
+        rank[order] = torch.arange(n)
+        num_pos = int((vals > 0).sum())
+        segs = get_segments(n, num_pos)
+        coef = polyfit_fit_oracle(vals[order], segs, tp.poly_degree)
+        fitted = polyfit_eval_oracle(coef, segs, tp.poly_degree)[rank] if n else vals
+        nc = MAX_SEGMENTS * (tp.poly_degree + 1)
+        slot[tp.off_coef:tp.off_coef + nc] = coef.numpy().view(np.uint32)
+        slot[tp.off_coef + nc] = num_pos
+        slot[tp.off_coef + nc + 1] = n
+        if tp.rank_u32:
+            slot[tp.off_rankmap:tp.off_rankmap + n] = rank.numpy().astype(np.uint32)
+        else:
+            r16 = np.zeros(((n + 1) // 2) * 2, dtype=np.uint16)
+            r16[:n] = rank.numpy().astype(np.uint16)
+            slot[tp.off_rankmap:tp.off_rankmap + (n + 1) // 2] = r16.view(np.uint32)
+        resid[sel] = vals - fitted
+        vals = fitted
+    else:
+        slot[tp.off_vals:tp.off_vals + sel.numel()] = vals.cpu().numpy().view(np.uint32)
+        resid[sel] = 0
     slot[dyn + 0] = sel.numel()
     slot[dyn + 1] = cutoff
     slot[dyn + 2] = T
@@ -163,6 +189,9 @@ class BucketEngine:
             scale = (1.0 / self.world) if average else 1.0
             if filter_smem_bytes is None:      # <1>: 128 regs, 1 CTA/SM; <2>: 64 regs, 2 CTAs/SM
                 filter_smem_bytes = 160 * 1024 if blocks_per_sm < 2 else 64 * 1024
+            ids, n_poly, tasks, n_tasks = plan.poly_tables()
+            self.poly_ids, self.poly_tasks = ids.to(dev), tasks.to(dev)
+            self.ctx.set_poly(self.poly_ids.data_ptr(), n_poly, self.poly_tasks.data_ptr(), n_tasks)
             self.ctx.configure(self.beta, self.gamma, scale, int(seed), POLICY_ID[plan.policy], int(use_history),
                                int(spin_limit), int(blocks_per_sm), int(filter_smem_bytes), int(use_tma), int(hist_shift))
         self.grad_views = plan.views(self.grad)
@@ -273,6 +302,7 @@ def topk_select_cuda(flat: torch.Tensor, k: int):
     with torch.cuda.device(flat.device):
         eng.grad[:d].copy_(flat.detach().float().flatten())
         eng.hist.zero_()
+        eng.tile_count.zero_()
         eng.hist_total.zero_()
         eng.epoch += 1
         eng.ctx.run(eng.epoch, PH_ACCUM, PH_EMIT + 1)

@@ -26,6 +26,9 @@ ARENA_HDR_WORDS = 128
 HIST_BINS = 2048
 NUM_HIST = 3
 ALIGN_ELEMS = 32
+MAX_SEGMENTS = 22
+MAX_POLY_K = 1 << 17      # the all-pairs rank pass is O(K^2): larger tensors keep fp32 values
+DESC_WORDS = 24
 
 
 def _align(x: int, a: int) -> int:
@@ -52,11 +55,19 @@ class TensorPlan:
     salt: int = 0
     n_filter_words: int = 0
     off_hint: int = 0
+    vmode: int = 0
+    off_coef: int = 0
+    off_rankmap: int = 0
+    off_selidx: int = 0
+    off_sorted: int = 0
+    poly_degree: int = 5
+    rank_u32: int = 0
 
     def words(self) -> List[int]:
         return [self.elem_off, self.numel, self.k, self.tile_begin, self.n_tiles, self.mode, self.m_bits,
                 self.n_hash, self.off_vals, self.off_filter, self.off_prefix, self.off_idx, self.val_cap,
-                self.salt, self.n_filter_words, self.off_hint]
+                self.salt, self.n_filter_words, self.off_hint, self.vmode, self.off_coef, self.off_rankmap,
+                self.off_selidx, self.off_sorted, self.poly_degree, self.rank_u32, 0]
 
 
 @dataclass
@@ -72,6 +83,9 @@ class BucketPlan:
     max_hash: int = 16
     ks: Optional[Sequence[int]] = None    # explicit per-tensor K (overrides compress_ratio)
     hint: bool = True                     # ship the 1-bit-per-32-elements occupancy hint next to each bloom filter
+    value: Optional[str] = None           # None (fp32 values) or 'polyfit' ('both': bloom index + curve fit)
+    poly_degree: int = 5
+    poly_min_k: int = 512                 # tensors shipping fewer values keep them as fp32 (the fit header would be larger)
     tensors: List[TensorPlan] = field(default_factory=list, init=False)
 
     def __post_init__(self):
@@ -85,13 +99,14 @@ class BucketPlan:
         tile = 0
         word = SLOT_HEADER_WORDS + DYN_WORDS * len(self.numels)
         word = _align(word, 4)
+        scratch: List[tuple] = []           # (tensor, kind, words) placed after the shipped payload
         for i, d in enumerate(self.numels):
             d = int(d)
             assert d > 0
             k = min(d, spec.topk_k(d, self.compress_ratio)) if self.ks is None else max(1, min(d, int(self.ks[i])))
             n_tiles = (d + spec.TILE - 1) // spec.TILE
             tp = TensorPlan(name=names[i], numel=d, shape=tuple(shapes[i]), elem_off=elem, k=k, tile_begin=tile,
-                            n_tiles=n_tiles, mode=MODE_RAW, salt=i)
+                            n_tiles=n_tiles, mode=MODE_RAW, salt=i, poly_degree=int(self.poly_degree))
             if self.index == "bloom" and d > self.min_numel:
                 n_hash, m_bits, n_words = spec.bloom_layout(k, d, self.fpr, self.max_hash)
                 tp.mode = MODE_BLOOM
@@ -101,8 +116,17 @@ class BucketPlan:
                     tp.val_cap = min(d, k + int(math.ceil(2.0 * fpr * d)) + 64)
                 else:
                     tp.val_cap = k
-                tp.off_vals = word
-                word = _align(word + tp.val_cap, 4)
+                if self.value == "polyfit" and k >= self.poly_min_k and tp.val_cap <= MAX_POLY_K:
+                    tp.vmode = 1
+                    tp.rank_u32 = int(tp.val_cap > 65536)
+                    tp.off_coef = word
+                    word = _align(word + MAX_SEGMENTS * (tp.poly_degree + 1) + 2, 4)
+                    tp.off_rankmap = word
+                    word = _align(word + (tp.val_cap if tp.rank_u32 else (tp.val_cap + 1) // 2), 4)
+                    scratch += [(tp, "off_vals", tp.val_cap), (tp, "off_selidx", tp.val_cap), (tp, "off_sorted", tp.val_cap)]
+                else:
+                    tp.off_vals = word
+                    word = _align(word + tp.val_cap, 4)
                 tp.off_filter = word
                 word = _align(word + n_words, 4)
                 tp.off_prefix = word
@@ -122,7 +146,18 @@ class BucketPlan:
         self.total_elems = _align(elem, ALIGN_ELEMS)
         self.n_tiles = tile
         self.payload_words = word
+        for tp, attr, n in scratch:            # sender-local scratch lives in the slot but is never pushed
+            setattr(tp, attr, word)
+            word = _align(word + n, 4)
         self.slot_words = _align(word, 64)
+
+    def poly_tables(self):
+        """(tensor ids with vmode==1, largest K first ; rank-phase tasks {tensor, first value of a 512-chunk})."""
+        ids = sorted([i for i, t in enumerate(self.tensors) if t.vmode == 1], key=lambda i: -self.tensors[i].val_cap)
+        tasks = [(i, c) for i in ids for c in range(0, self.tensors[i].val_cap, 512)]
+        ids_t = torch.tensor(ids if ids else [0], dtype=torch.int32)
+        tasks_t = torch.tensor(tasks if tasks else [(0, 0)], dtype=torch.int32).reshape(-1)
+        return ids_t, len(ids), tasks_t, len(tasks)
 
     # ---- device tables -----------------------------------------------------
     def tensor_table(self) -> torch.Tensor:

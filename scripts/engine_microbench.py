@@ -11,7 +11,7 @@ sys.path.insert(0, ROOT)
 from deepreduce_b200.models import resnet50  # noqa: E402
 from deepreduce_b200.parallel import BucketEngine, BucketPlan  # noqa: E402
 
-PHASES = ["accum+hist1", "fallback", "hist2", "insert", "query", "emit", "push", "signal", "decode"]
+PHASES = ["accum+hist1", "fallback", "hist2", "insert", "query", "emit", "rank", "fit", "fix", "push", "signal", "decode"]
 
 
 def main():
@@ -20,9 +20,11 @@ def main():
     use_tma = bool(int(sys.argv[3])) if len(sys.argv) > 3 else True
     hist_shift = int(sys.argv[4]) if len(sys.argv) > 4 else 23
     hint = bool(int(sys.argv[5])) if len(sys.argv) > 5 else True
+    value = (sys.argv[6] if len(sys.argv) > 6 else 'none')
+    value = None if value == 'none' else value
     m = resnet50()
     named = list(reversed([(n, p) for n, p in m.named_parameters()]))
-    plan = BucketPlan([p.numel() for _, p in named], [n for n, _ in named], compress_ratio=0.01, hint=hint)
+    plan = BucketPlan([p.numel() for _, p in named], [n for n, _ in named], compress_ratio=0.01, hint=hint, value=value)
     eng = BucketEngine(plan, device="cuda:0", world=1, rank=0, blocks_per_sm=bps, use_tma=use_tma, hist_shift=hist_shift)
     gen = torch.Generator(device="cuda").manual_seed(0)
     grads = [torch.randn(plan.total_elems, device="cuda", generator=gen) * 0.01 for _ in range(4)]
@@ -70,7 +72,7 @@ def main():
     min_bytes = 4 * d
     med = fused[len(fused) // 2]
     out = {"kernel": "dr_engine_kernel (fused, W=1)", "model": "resnet50 grads", "dense_bytes": d,
-           "wire_bytes": plan.wire_bytes(), "grid": eng.grid(), "blocks_per_sm": bps, "use_tma": use_tma, "hist_shift": hist_shift, "hint": hint,
+           "wire_bytes": plan.wire_bytes(), "grid": eng.grid(), "blocks_per_sm": bps, "use_tma": use_tma, "hist_shift": hist_shift, "hint": hint, "value": value,
            "fused_ms_median": med, "fused_ms_min": fused[0],
            "phase_ms_unfused": dict(zip(PHASES, [round(x, 4) for x in per])),
            "algorithmic_min_bytes": min_bytes, "achieved_gbs_vs_min_bytes": min_bytes / med / 1e6,

@@ -16,8 +16,9 @@ def main():
     from deepreduce_b200.parallel import BucketEngine, BucketPlan, engine_oracle
     sizes = [64, 1001, 4097, 36864, 147456, 10, 589824, 2359296]
     ok = True
-    for index, policy in (("bloom", "leftmost"), ("bloom", "p0"), (None, "leftmost")):
-        plan = BucketPlan(sizes, compress_ratio=0.01, index=index, policy=policy)
+    for index, policy, value in (("bloom", "leftmost", None), ("bloom", "p0", None), (None, "leftmost", None),
+                                 ("bloom", "leftmost", "polyfit")):
+        plan = BucketPlan(sizes, compress_ratio=0.01, index=index, policy=policy, value=value)
         eng = BucketEngine(plan, device=f"cuda:{local}", spin_limit=4_000_000)
         resid_refs = [torch.zeros(plan.total_elems) for _ in range(world)]
         for step in range(3):
@@ -28,14 +29,29 @@ def main():
                 for v in plan.views(g):
                     v.copy_(torch.randn(v.shape, generator=gen))
                 grads.append(g)
+            if value is not None:
+                eng.resid.copy_(resid_refs[rank].cuda())
             eng.grad.copy_(grads[rank].cuda())
             eng.step()
             torch.cuda.synchronize()
             eng.check_status()
             out_ref, resid_refs, slots = engine_oracle(plan, grads, resid_refs, epoch=eng.epoch)
-            same_out = torch.allclose(eng.grad.cpu(), out_ref, atol=1e-6, rtol=1e-6)
-            same_res = torch.equal(eng.resid.cpu(), resid_refs[rank])
-            same_slots = all(np.array_equal(eng.slot(r).cpu().numpy().view(np.uint32), slots[r]) for r in range(world))
+            if value is None:
+                same_out = torch.allclose(eng.grad.cpu(), out_ref, atol=1e-6, rtol=1e-6)
+                same_res = torch.equal(eng.resid.cpu(), resid_refs[rank])
+                same_slots = all(np.array_equal(eng.slot(r).cpu().numpy().view(np.uint32), slots[r]) for r in range(world))
+            else:       # fitted values: fp32 sums on the GPU vs fp64 oracle; every rank must hold the same decode
+                sc = float(out_ref.abs().max())
+                same_out = torch.allclose(eng.grad.cpu(), out_ref, atol=3e-3 * sc, rtol=2e-2)
+                same_res = torch.allclose(eng.resid.cpu(), resid_refs[rank], atol=3e-3 * sc, rtol=2e-2)
+                mine = eng.grad.clone()
+                ref0 = mine.clone()
+                dist.broadcast(ref0, 0)
+                same_slots = bool(torch.equal(mine, ref0))
+                # follow the GPU residuals from here on
+                gathered = [torch.empty_like(eng.resid) for _ in range(world)]
+                dist.all_gather(gathered, eng.resid)
+                resid_refs = [g.cpu() for g in gathered]
             if not (same_out and same_res and same_slots):
                 ok = False
                 print(f"[rank {rank}] MISMATCH index={index} policy={policy} step={step} out={same_out} res={same_res} slots={same_slots}",

@@ -36,7 +36,7 @@ def test_plan_layout():
     for (a, n), (b, _) in zip(regions[:-1], regions[1:]):
         assert a + n <= b
     assert regions[-1][0] + regions[-1][1] <= plan.payload_words <= plan.slot_words
-    assert plan.tensor_table().numel() == 16 * len(SIZES)
+    assert plan.tensor_table().numel() == 24 * len(SIZES)
     # bloom wire is smaller than plain (fp32,int64) pairs: the paper's headline for index compression
     assert plan.wire_bytes() < plan.topk_pair_bytes()
 
@@ -122,3 +122,22 @@ def test_occupancy_hint_removes_false_positives():
     kept = {h: len(true & set(outs[h].nonzero().flatten().tolist())) for h in outs}
     assert kept[True] > kept[False]                 # fewer false positives displace true top-k entries
     assert kept[True] >= 1940
+
+
+def test_oracle_both_polyfit():
+    torch.manual_seed(7)
+    plan = BucketPlan([300000, 5000], compress_ratio=0.01, value="polyfit")
+    t0, t1 = plan.tensors
+    assert t0.vmode == 1 and t0.rank_u32 == 0 and t1.vmode == 0          # K=50 stays fp32 (fit header would be larger)
+    plain = BucketPlan([300000, 5000], compress_ratio=0.01)
+    assert plan.wire_bytes() < 0.75 * plain.wire_bytes()                 # values: 4 B -> 2 B (+ coefficients)
+    g = torch.zeros(plan.total_elems)
+    for v in plan.views(g):
+        v.copy_(torch.randn_like(v))
+    out, res, slots = engine_oracle(plan, [g], [torch.zeros_like(g)])
+    out_p, res_p, _ = engine_oracle(plain, [g], [torch.zeros_like(g)])
+    seg = slice(0, 300000)
+    assert torch.equal(out[seg] != 0, out_p[seg] != 0)                   # same support, fitted values
+    rel = (out[seg] - out_p[seg]).norm() / out_p[seg].norm()
+    assert rel < 0.08
+    assert torch.allclose(out[seg] + res[0][seg], g[seg], atol=1e-6)     # residual keeps the fit error

@@ -63,6 +63,18 @@ def _compare_slot(plan, slot_gpu, slot_ref, tag):
             ia, ib = a[t.off_idx:t.off_idx + n_sel], b[t.off_idx:t.off_idx + n_sel]
             if not np.array_equal(ia, ib):
                 bad.append(f"{t.name} raw idx gpu={ia[:8].tolist()} ref={ib[:8].tolist()}")
+        if t.vmode == 1:
+            nc = 22 * (t.poly_degree + 1)
+            ca, cb = a[t.off_coef:t.off_coef + nc].view(np.float32), b[t.off_coef:t.off_coef + nc].view(np.float32)
+            if not np.allclose(ca, cb, rtol=2e-3, atol=2e-4 * float(np.abs(cb).max() + 1e-30)):
+                bad.append(f"{t.name} coef max abs diff {float(np.abs(ca - cb).max())} (scale {float(np.abs(cb).max())})")
+            if not np.array_equal(a[t.off_coef + nc:t.off_coef + nc + 2], b[t.off_coef + nc:t.off_coef + nc + 2]):
+                bad.append(f"{t.name} coef tail gpu={a[t.off_coef+nc:t.off_coef+nc+2].tolist()} ref={b[t.off_coef+nc:t.off_coef+nc+2].tolist()}")
+            nw = n_sel if t.rank_u32 else n_sel // 2          # compare whole words only
+            ra, rb = a[t.off_rankmap:t.off_rankmap + nw], b[t.off_rankmap:t.off_rankmap + nw]
+            if not np.array_equal(ra, rb):
+                bad.append(f"{t.name} rank map differs in {int((ra != rb).sum())}/{nw} words")
+            continue
         va, vb = a[t.off_vals:t.off_vals + n_sel], b[t.off_vals:t.off_vals + n_sel]
         if not np.array_equal(va, vb):
             bad.append(f"{t.name} vals differ in {int((va != vb).sum())}/{n_sel}")
@@ -75,11 +87,13 @@ SIZES = [64, 1000, 1001, 4096, 4097, 36864, 147456, 10, 589824]
 
 
 @pytest.mark.parametrize("kind", ["randn", "sparse", "ties"])
-@pytest.mark.parametrize("index,policy,hint,tma", [("bloom", "leftmost", True, True), ("bloom", "leftmost", False, False),
-                                                   ("bloom", "p0", True, True), (None, "leftmost", True, True)])
-def test_engine_vs_oracle_single_rank(kind, index, policy, hint, tma):
+@pytest.mark.parametrize("index,policy,hint,tma,value", [
+    ("bloom", "leftmost", True, True, None), ("bloom", "leftmost", False, False, None), ("bloom", "p0", True, True, None),
+    (None, "leftmost", True, True, None), ("bloom", "leftmost", True, True, "polyfit")])
+def test_engine_vs_oracle_single_rank(kind, index, policy, hint, tma, value):
     from deepreduce_b200.parallel import BucketEngine, BucketPlan, engine_oracle
-    plan = BucketPlan(SIZES, compress_ratio=0.01, index=index, policy=policy, hint=hint)
+    plan = BucketPlan(SIZES + [2359296], compress_ratio=0.01, index=index, policy=policy, hint=hint, value=value,
+                      poly_min_k=300)
     eng = BucketEngine(plan, device="cuda:0", world=1, rank=0, spin_limit=2_000_000, use_tma=tma)
     gen = torch.Generator().manual_seed(0)
     resid_ref = torch.zeros(plan.total_elems)
@@ -93,12 +107,18 @@ def test_engine_vs_oracle_single_rank(kind, index, policy, hint, tma):
         torch.cuda.synchronize()
         eng.check_status()
         out_ref, new_res, slots = engine_oracle(plan, [g], [resid_ref], epoch=eng.epoch)
-        tag = f"single_{kind}_{index}_{policy}_{hint}_s{step}"
+        tag = f"single_{kind}_{index}_{policy}_{hint}_{value}_s{step}"
         bad = _compare_slot(plan, eng.slot(), slots[0], tag)
         assert not bad, bad[:4]
-        assert torch.equal(eng.resid.cpu(), new_res[0]), tag
-        assert torch.allclose(eng.grad.cpu(), out_ref, atol=0, rtol=0), tag
-        resid_ref = new_res[0]
+        if value is None:
+            assert torch.equal(eng.resid.cpu(), new_res[0]), tag
+            assert torch.allclose(eng.grad.cpu(), out_ref, atol=0, rtol=0), tag
+            resid_ref = new_res[0]
+        else:       # fp32 Gram sums on the GPU vs fp64 in the oracle
+            scale = float(out_ref.abs().max())
+            assert torch.allclose(eng.grad.cpu(), out_ref, atol=2e-3 * scale, rtol=1e-2), tag
+            assert torch.allclose(eng.resid.cpu(), new_res[0], atol=2e-3 * scale, rtol=1e-2), tag
+            resid_ref = eng.resid.cpu().clone()      # follow the GPU trajectory so later steps compare like with like
     eng.close()
 
 
@@ -178,7 +198,7 @@ def test_per_tensor_ops_vs_oracle():
 
 @pytest.mark.parametrize("cfg", [
     dict(deepreduce='index', index='bloom'), dict(deepreduce='index', index='bloom', policy='p0'),
-    dict(deepreduce='both'), dict(deepreduce='value', value='polyfit'), dict(deepreduce='value', value='qsgd'),
+    dict(deepreduce='both'), dict(deepreduce='both', min_numel=100), dict(deepreduce='value', value='polyfit'), dict(deepreduce='value', value='qsgd'),
     dict(deepreduce='index', index='rle'), dict(deepreduce='index', index='integer'), dict()])
 def test_grace_path_cuda_matches_cpu(cfg):
     import deepreduce_b200 as dr
