@@ -215,9 +215,13 @@ struct Engine {
     P.use_tma = use_tma; P.hist_shift = (uint32_t)hist_shift;
   }
 
-  void set_poly(int64_t tensors, int64_t n_poly, int64_t tasks, int64_t n_tasks) {
+  void set_poly(int64_t tensors, int64_t n_poly, int64_t tasks, int64_t n_tasks, int64_t bins, int64_t bucket_val,
+                int64_t bucket_pos, int64_t expand_buf, int64_t poly_total) {
     P.poly_tensors = reinterpret_cast<const uint32_t*>(tensors); P.n_poly = (uint32_t)n_poly;
     P.poly_tasks = reinterpret_cast<const uint32_t*>(tasks); P.n_poly_tasks = (uint32_t)n_tasks;
+    P.poly_bins = reinterpret_cast<uint32_t*>(bins); P.bucket_val = reinterpret_cast<float*>(bucket_val);
+    P.bucket_pos = reinterpret_cast<uint32_t*>(bucket_pos); P.expand_buf = reinterpret_cast<float*>(expand_buf);
+    P.poly_total = (uint32_t)poly_total;
   }
 
   void set_buffers(int64_t grad, int64_t resid) {

@@ -944,47 +944,102 @@ DR_D uint32_t load_rank(const uint32_t* slot, const TensorDesc& td, uint32_t p) 
                      : (uint32_t)__ldcg(reinterpret_cast<const uint16_t*>(slot + td.off_rankmap) + p);
 }
 
-// phase 6: rank of every shipped value in the descending order (all-pairs count, exact, stable by position)
-DR_D void phase_rank(const EngineParams& P, Smem& sm) {
+// ---- exact descending rank: counting sort on 13 bits of the order-preserving key + all-pairs inside a bin ----
+DR_D uint32_t rank_bin(float v) {               // bin 0 holds the largest values
+  const uint32_t b = __float_as_uint(v);
+  const uint32_t u = (b & 0x80000000u) ? ~b : (b | 0x80000000u);      // monotone float -> uint
+  return (uint32_t)(kRankBins - 1) - (u >> 19);
+}
+
+// phase 6: bin populations
+DR_D void phase_rank_hist(const EngineParams& P, Smem& sm) {
   const uint32_t parity = P.epoch & 1u;
   uint32_t* my_slot = slot_ptr(P.arena[P.rank], P, parity, P.rank);
-  float* tile = sm.u.acc;                       // 512-value chunks of the tensor's values
   for (uint32_t task = blockIdx.x; task < P.n_poly_tasks; task += gridDim.x) {
     const uint32_t t = __ldg(P.poly_tasks + 2 * task), p0 = __ldg(P.poly_tasks + 2 * task + 1);
     load_tensor(P, t, sm);
     const DynHeader* dyn = reinterpret_cast<const DynHeader*>(my_slot + kSlotHeaderWords) + t;
-    const uint32_t n = __ldcg(&dyn->n_sel);
-    if (p0 >= n) continue;
-    const float* vals = reinterpret_cast<const float*>(my_slot + sm.td.off_vals);
-    const uint32_t p = p0 + threadIdx.x;
-    const float v = p < n ? __ldcg(vals + p) : 0.f;
-    uint32_t rank = 0;
-    for (uint32_t q0 = 0; q0 < n; q0 += kThreads) {
-      __syncthreads();
-      const uint32_t q = q0 + threadIdx.x;
-      tile[threadIdx.x] = q < n ? __ldcg(vals + q) : -INFINITY;   // -inf never outranks anything
-      __syncthreads();
-      const uint32_t lim = min((uint32_t)kThreads, n - q0);
-      if (q0 + lim <= p0) {                     // whole chunk precedes mine: ties count
-#pragma unroll 8
-        for (uint32_t i = 0; i < lim; ++i) rank += (tile[i] >= v) ? 1u : 0u;
-      } else if (q0 >= p0 + kThreads) {         // whole chunk follows mine: ties do not count
-#pragma unroll 8
-        for (uint32_t i = 0; i < lim; ++i) rank += (tile[i] > v) ? 1u : 0u;
-      } else {                                  // my own chunk
-        for (uint32_t i = 0; i < lim; ++i) {
-          const float w = tile[i];
-          rank += (w > v || (w == v && q0 + i < p)) ? 1u : 0u;
-        }
-      }
-    }
+    const uint32_t n = __ldcg(&dyn->n_sel), p = p0 + threadIdx.x;
     if (p < n) {
+      const float v = __ldcg(reinterpret_cast<const float*>(my_slot + sm.td.off_vals) + p);
+      atomicAdd(P.poly_bins + (size_t)sm.td.poly_ord * 2 * kRankBins + rank_bin(v), 1u);
+    }
+  }
+}
+
+// phase 7: per tensor, exclusive prefix of the bin counts -> bin starts (second half of the bin table)
+DR_D void phase_rank_scan(const EngineParams& P, Smem& sm) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  for (uint32_t o = blockIdx.x; o < P.n_poly; o += gridDim.x) {
+    uint32_t* cnt = P.poly_bins + (size_t)o * 2 * kRankBins;
+    uint32_t* start = cnt + kRankBins;
+    constexpr int kPer = kRankBins / kThreads;                    // 16 consecutive bins per thread
+    uint32_t c[kPer], sum = 0;
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) { c[i] = __ldcg(cnt + threadIdx.x * kPer + i); sum += c[i]; }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t nb = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) incl += nb; }
+    __syncthreads();
+    if (lane == 31) sm.s.warp_tot[warp] = incl;
+    __syncthreads();
+    uint32_t base = 0;
+    for (uint32_t w = 0; w < warp; ++w) base += sm.s.warp_tot[w];
+    uint32_t run = base + incl - sum;
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) { start[threadIdx.x * kPer + i] = run; run += c[i]; }
+  }
+}
+
+// phase 8: group values by bin (order inside a bin is arbitrary here; phase 9 makes the rank exact)
+DR_D void phase_rank_scatter(const EngineParams& P, Smem& sm) {
+  const uint32_t parity = P.epoch & 1u;
+  uint32_t* my_slot = slot_ptr(P.arena[P.rank], P, parity, P.rank);
+  for (uint32_t task = blockIdx.x; task < P.n_poly_tasks; task += gridDim.x) {
+    const uint32_t t = __ldg(P.poly_tasks + 2 * task), p0 = __ldg(P.poly_tasks + 2 * task + 1);
+    load_tensor(P, t, sm);
+    const DynHeader* dyn = reinterpret_cast<const DynHeader*>(my_slot + kSlotHeaderWords) + t;
+    const uint32_t n = __ldcg(&dyn->n_sel), p = p0 + threadIdx.x;
+    if (p < n) {
+      const float v = __ldcg(reinterpret_cast<const float*>(my_slot + sm.td.off_vals) + p);
+      uint32_t* tab = P.poly_bins + (size_t)sm.td.poly_ord * 2 * kRankBins;
+      const uint32_t b = rank_bin(v);
+      // the count array is re-used as the running cursor: it is decremented down to 0 while filling the bin
+      const uint32_t within = atomicSub(tab + b, 1u) - 1u;
+      const uint32_t pos = __ldcg(tab + kRankBins + b) + within;
+      P.bucket_val[sm.td.poly_off + pos] = v;
+      P.bucket_pos[sm.td.poly_off + pos] = p;
+    }
+  }
+}
+
+// phase 9: exact rank = bin start + #(bin mates that sort before me); writes rank map, sorted values, num_pos
+DR_D void phase_rank_exact(const EngineParams& P, Smem& sm) {
+  const uint32_t parity = P.epoch & 1u;
+  uint32_t* my_slot = slot_ptr(P.arena[P.rank], P, parity, P.rank);
+  for (uint32_t task = blockIdx.x; task < P.n_poly_tasks; task += gridDim.x) {
+    const uint32_t t = __ldg(P.poly_tasks + 2 * task), p0 = __ldg(P.poly_tasks + 2 * task + 1);
+    load_tensor(P, t, sm);
+    const DynHeader* dyn = reinterpret_cast<const DynHeader*>(my_slot + kSlotHeaderWords) + t;
+    const uint32_t n = __ldcg(&dyn->n_sel), i = p0 + threadIdx.x;   // i = position in the grouped arrays
+    float v = 0.f;
+    if (i < n) {
+      const float* bv = P.bucket_val + sm.td.poly_off;
+      const uint32_t* bp = P.bucket_pos + sm.td.poly_off;
+      v = __ldcg(bv + i);
+      const uint32_t p = __ldcg(bp + i), b = rank_bin(v);
+      const uint32_t* start = P.poly_bins + (size_t)sm.td.poly_ord * 2 * kRankBins + kRankBins;
+      const uint32_t lo = __ldcg(start + b), hi = (b + 1 < (uint32_t)kRankBins) ? __ldcg(start + b + 1) : n;
+      uint32_t rank = lo;
+      for (uint32_t q = lo; q < hi; ++q) {
+        const float w = __ldcg(bv + q);
+        rank += (w > v || (w == v && __ldcg(bp + q) < p)) ? 1u : 0u;
+      }
       if (sm.td.rank_u32) my_slot[sm.td.off_rankmap + p] = rank;
       else reinterpret_cast<uint16_t*>(my_slot + sm.td.off_rankmap)[p] = (uint16_t)rank;
       reinterpret_cast<float*>(my_slot + sm.td.off_sorted)[rank] = v;
     }
-    // positives of this chunk -> num_pos (slot word zeroed in the accumulate phase); n is written once
-    const uint32_t pc = __syncthreads_count(p < n && v > 0.f);
+    const uint32_t pc = __syncthreads_count(i < n && v > 0.f);
     if (threadIdx.x == 0) {
       uint32_t* tail = my_slot + sm.td.off_coef + kMaxSeg * (sm.td.poly_degree + 1);
       if (pc) atomicAdd(tail, pc);
@@ -993,7 +1048,7 @@ DR_D void phase_rank(const EngineParams& P, Smem& sm) {
   }
 }
 
-// phase 7: one warp per (tensor, segment): Gram least squares  c_k = sum p_k y / sum p_k^2
+// phase 10: one warp per (tensor, segment): Gram least squares  c_k = sum p_k y / sum p_k^2
 DR_D void phase_fit(const EngineParams& P, Smem& sm) {
   const uint32_t parity = P.epoch & 1u;
   uint32_t* my_slot = slot_ptr(P.arena[P.rank], P, parity, P.rank);
@@ -1016,12 +1071,20 @@ DR_D void phase_fit(const EngineParams& P, Smem& sm) {
     float num[kMaxDeg + 1], den[kMaxDeg + 1];
 #pragma unroll
     for (int k = 0; k <= kMaxDeg; ++k) { num[k] = 0.f; den[k] = 0.f; }
-    for (int x = lane; x < len; x += 32) {
-      float p[kMaxDeg + 1];
-      gram_eval<kMaxDeg + 1>((float)x, (float)(len - 1), deg_eff, p);
-      const float yi = __ldcg(y + x);
+    for (int x0 = lane; x0 < len; x0 += 32 * 8) {                  // 8 independent loads in flight per lane
+      float yv[8];
 #pragma unroll
-      for (int k = 0; k <= kMaxDeg; ++k) { num[k] += p[k] * yi; den[k] += p[k] * p[k]; }
+      for (int u = 0; u < 8; ++u) yv[u] = (x0 + 32 * u < len) ? __ldcg(y + x0 + 32 * u) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int x = x0 + 32 * u;
+        if (x < len) {
+          float p[kMaxDeg + 1];
+          gram_eval<kMaxDeg + 1>((float)x, (float)(len - 1), deg_eff, p);
+#pragma unroll
+          for (int k = 0; k <= kMaxDeg; ++k) { num[k] += p[k] * yv[u]; den[k] += p[k] * p[k]; }
+        }
+      }
     }
 #pragma unroll
     for (int k = 0; k <= kMaxDeg; ++k) {
@@ -1038,7 +1101,7 @@ DR_D void phase_fit(const EngineParams& P, Smem& sm) {
   }
 }
 
-// phase 8: error feedback sees the fit error: resid[idx_p] = value_p - fitted_p
+// phase 11: error feedback sees the fit error: resid[idx_p] = value_p - fitted_p
 DR_D void phase_fix(const EngineParams& P, Smem& sm) {
   const uint32_t parity = P.epoch & 1u;
   uint32_t* my_slot = slot_ptr(P.arena[P.rank], P, parity, P.rank);
@@ -1094,8 +1157,30 @@ DR_D void phase_signal(const EngineParams& P) {
   __syncthreads();
 }
 
+// phase 14: evaluate every rank's fitted curve once (dense, all lanes busy); decode then gathers fitted[rank]
+DR_D void phase_expand(const EngineParams& P, Smem& sm) {
+  const uint32_t parity = P.epoch & 1u;
+  uint32_t* arena = P.arena[P.rank];
+  for (uint32_t wt = blockIdx.x; wt < P.n_poly_tasks * (uint32_t)P.world; wt += gridDim.x) {
+    const uint32_t r = wt / P.n_poly_tasks, task = wt - r * P.n_poly_tasks;
+    const uint32_t t = __ldg(P.poly_tasks + 2 * task), j0 = __ldg(P.poly_tasks + 2 * task + 1);
+    load_tensor(P, t, sm);
+    const uint32_t* slot = slot_ptr(arena, P, parity, (int)r);
+    const int deg = (int)sm.td.poly_degree;
+    const uint32_t* tail = slot + sm.td.off_coef + kMaxSeg * (deg + 1);
+    const int num_pos = (int)__ldcg(tail), n = (int)__ldcg(tail + 1);
+    if ((int)j0 >= n) continue;
+    if (threadIdx.x == 0) build_segments(n, num_pos, sm.seg_start, sm.n_seg);
+    __syncthreads();
+    const uint32_t j = j0 + threadIdx.x;
+    if ((int)j < n)
+      P.expand_buf[(size_t)r * P.poly_total + sm.td.poly_off + j] =
+          poly_value(reinterpret_cast<const float*>(slot + sm.td.off_coef), sm.seg_start, sm.n_seg, deg, j);
+  }
+}
+
 // ===========================================================================
-// phase 11: decode.  Contiguous tile range per CTA; rank-major so one staged
+// phase 15: decode.  Contiguous tile range per CTA; rank-major so one staged
 // filter serves all of the CTA's tiles of that tensor; sparse RMW into the
 // zero-filled dense output.
 // ===========================================================================
@@ -1116,6 +1201,8 @@ DR_D void phase_decode(const EngineParams& P, Smem& sm) {
     for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < (uint32_t)kNumHist * P.n_tensors; i += gridDim.x * kThreads)
       P.hist_total[i] = 0u;
     for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < P.n_tiles; i += gridDim.x * kThreads) P.tile_count[i] = 0u;
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < P.n_poly * 2u * kRankBins; i += gridDim.x * kThreads)
+      P.poly_bins[i] = 0u;
   }
   uint32_t tile, t_end;
   tile_range(P, tile, t_end);
@@ -1145,14 +1232,7 @@ DR_D void phase_decode(const EngineParams& P, Smem& sm) {
         if (n_sel == 0) continue;
         const uint32_t* filter = slot + sm.td.off_filter;
         const float* vals = reinterpret_cast<const float*>(slot + sm.td.off_vals);
-        if (sm.td.vmode) {          // 'both': rank r's segment table (from its n and num_pos)
-          __syncthreads();
-          if (threadIdx.x == 0) {
-            const uint32_t* tail = slot + sm.td.off_coef + kMaxSeg * (sm.td.poly_degree + 1);
-            build_segments((int)__ldcg(tail + 1), (int)__ldcg(tail), sm.seg_start, sm.n_seg);
-          }
-          __syncthreads();
-        }
+        const float* fitted = P.expand_buf + (size_t)r * P.poly_total + sm.td.poly_off;   // 'both': rank r's curve
         if (fits) stage_filter(filter, sm.td.n_filter_words);
         for (uint32_t tl = tile; tl < seg_end; ++tl) {
           const Tile ti = load_tile(P, tl);
@@ -1183,10 +1263,7 @@ DR_D void phase_decode(const EngineParams& P, Smem& sm) {
               const uint32_t rp = pre + rank[c];
               if (rp < n_sel) {
                 float* o = P.grad + ti.base + c * kThreads + threadIdx.x;   // the same thread owns this element for every rank
-                const float val = sm.td.vmode
-                    ? poly_value(reinterpret_cast<const float*>(slot + sm.td.off_coef), sm.seg_start, sm.n_seg,
-                                 (int)sm.td.poly_degree, load_rank(slot, sm.td, rp))
-                    : __ldcg(vals + rp);
+                const float val = sm.td.vmode ? __ldcg(fitted + load_rank(slot, sm.td, rp)) : __ldcg(vals + rp);
                 *o = *o + val * P.scale;
               }
             }
@@ -1237,16 +1314,20 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) dr_engine_kernel(const _
       case kPhInsert: if (P.use_tma) phase_insert_tma(P, sm); else phase_insert(P, sm); break;
       case kPhQuery: phase_query(P, sm); break;
       case kPhEmit: phase_emit(P, sm); break;
-      case kPhRank: if (P.n_poly) phase_rank(P, sm); else ran = false; break;
+      case kPhRankHist: if (P.n_poly) phase_rank_hist(P, sm); else ran = false; break;
+      case kPhRankScan: if (P.n_poly) phase_rank_scan(P, sm); else ran = false; break;
+      case kPhRankScatter: if (P.n_poly) phase_rank_scatter(P, sm); else ran = false; break;
+      case kPhRankExact: if (P.n_poly) phase_rank_exact(P, sm); else ran = false; break;
       case kPhFit: if (P.n_poly) phase_fit(P, sm); else ran = false; break;
       case kPhFix: if (P.n_poly) phase_fix(P, sm); else ran = false; break;
+      case kPhExpand: if (P.n_poly) phase_expand(P, sm); else ran = false; break;
       case kPhPush: if (P.world > 1) phase_push(P); else ran = false; break;
       case kPhSignal: if (P.world > 1) phase_signal(P); else ran = false; break;
       case kPhDecode: phase_decode(P, sm); break;
       default: ran = false; break;
     }
     // a barrier separates dependent phases; signal->decode needs none (every CTA waits itself)
-    if (ran && ph + 1 < P.phase_end && ph != kPhSignal) grid_barrier(P.barrier, bar_epoch, P.status, P.spin_limit);
+    if (ran && ph + 1 < P.phase_end && !(ph == kPhSignal)) grid_barrier(P.barrier, bar_epoch, P.status, P.spin_limit);
   }
 }
 

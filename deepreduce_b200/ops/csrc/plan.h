@@ -43,10 +43,13 @@ struct TensorDesc {
   uint32_t off_sorted;   // scratch (not shipped): values in descending order
   uint32_t poly_degree;
   uint32_t rank_u32;     // 1: rank map entries are 32-bit
-  uint32_t reserved;
+  uint32_t poly_off;     // offset of this tensor's values in the engine's per-value scratch arrays
+  uint32_t poly_ord;     // ordinal among the vmode==1 tensors (selects its bin table)
+  uint32_t reserved[7];
 };
-static_assert(sizeof(TensorDesc) == 96, "TensorDesc must be 24 words");
-constexpr int kDescWords = 24;
+static_assert(sizeof(TensorDesc) == 128, "TensorDesc must be 32 words");
+constexpr int kDescWords = 32;
+constexpr int kRankBins = 8192;        // 'both': counting-sort bins = sign + 8 exponent + 4 mantissa bits
 constexpr int kMaxSeg = 22;            // codecs/polyfit.py MAX_SEGMENTS
 constexpr int kMaxDeg = 7;
 
@@ -94,13 +97,19 @@ enum Phase : int {
   kPhInsert = 3,     // resolve T22, bloom insert of the selected set
   kPhQuery = 4,      // universe query against my filter: per-element flags + per-tile counts
   kPhEmit = 5,       // ordered compaction (local prefix of the counts) + value gather + residual zeroing
-  kPhRank = 6,       // 'both': exact descending rank of every shipped value (all-pairs count) + rank map
-  kPhFit = 7,        // 'both': per-segment Gram-polynomial least squares on the sorted values
-  kPhFix = 8,        // 'both': residual <- value - fitted value (error feedback sees the fit error)
-  kPhPush = 9,       // copy the finished slot into every peer's arena (P2P stores over NVLink)
-  kPhSignal = 10,    // release flags to peers, acquire peers' flags
-  kPhDecode = 11,    // membership test on every rank's filter, rank->value, sum, scale, dense write
-  kPhEnd = 12
+  // 'both' (bloom index + polynomial value fit): exact descending rank of every shipped value by a
+  // counting sort on 13 key bits + an all-pairs count inside each bin, then the fit
+  kPhRankHist = 6,   // bin populations
+  kPhRankScan = 7,   // per-tensor exclusive prefix over the bins
+  kPhRankScatter = 8,// group the values by bin
+  kPhRankExact = 9,  // exact rank inside the bin -> rank map + sorted values + num_pos
+  kPhFit = 10,       // per-segment Gram-polynomial least squares on the sorted values
+  kPhFix = 11,       // residual <- value - fitted value (error feedback sees the fit error)
+  kPhPush = 12,      // copy the finished slot into every peer's arena (P2P stores over NVLink)
+  kPhSignal = 13,    // release flags to peers, acquire peers' flags
+  kPhExpand = 14,    // 'both': evaluate every rank's fitted curve once (dense), decode then only gathers
+  kPhDecode = 15,    // membership test on every rank's filter, rank->value, sum, scale, dense write
+  kPhEnd = 16
 };
 
 // per-tile table (uint4): {tensor id, element offset of the tile in the flat buffers, valid count, offset inside tensor}
@@ -137,8 +146,13 @@ struct EngineParams {
   uint32_t hist_shift;           // history bound = prev_thr - (1 << hist_shift): 23 -> x0.5, 22 -> ~x0.7
   const uint32_t* poly_tensors;  // ids of the tensors with vmode == 1 (largest K first)
   uint32_t n_poly;
-  const uint32_t* poly_tasks;    // rank-phase tasks: {tensor id, first value of a 512-value chunk}
+  const uint32_t* poly_tasks;    // per-value tasks: {tensor id, first value of a 512-value chunk}
   uint32_t n_poly_tasks;
+  uint32_t* poly_bins;           // [n_poly][2][kRankBins]: bin counts | bin starts/cursors (zeroed in decode)
+  float* bucket_val;             // [sum K] values grouped by bin
+  uint32_t* bucket_pos;          // [sum K] original position p of the grouped values
+  float* expand_buf;             // [world][sum K] fitted curves of every rank
+  uint32_t poly_total;           // sum K over the vmode==1 tensors
 };
 
 }  // namespace dr

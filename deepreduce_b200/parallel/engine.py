@@ -24,8 +24,8 @@ from ..codecs.bloom import bloom_insert_oracle, bloom_query_oracle
 from .plan import (ARENA_HDR_WORDS, DYN_WORDS, HIST_BINS, MODE_BLOOM, MODE_RAW, NUM_HIST, POLICY_ID,
                    SLOT_HEADER_WORDS, BucketPlan)
 
-(PH_ACCUM, PH_FALLBACK, PH_HIST2, PH_INSERT, PH_QUERY, PH_EMIT, PH_RANK, PH_FIT, PH_FIX, PH_PUSH, PH_SIGNAL,
- PH_DECODE, PH_END) = range(13)
+(PH_ACCUM, PH_FALLBACK, PH_HIST2, PH_INSERT, PH_QUERY, PH_EMIT, PH_RANK_HIST, PH_RANK_SCAN, PH_RANK_SCATTER,
+ PH_RANK_EXACT, PH_FIT, PH_FIX, PH_PUSH, PH_SIGNAL, PH_EXPAND, PH_DECODE, PH_END) = range(17)
 MAGIC = 0xD33B2000
 STATUS_NAMES = {0: "ok", 1: "(unused)", 2: "peer flag watchdog", 3: "select resolve failed", 4: "grid barrier watchdog", 5: "TMA mbarrier watchdog"}
 
@@ -191,7 +191,15 @@ class BucketEngine:
                 filter_smem_bytes = 160 * 1024 if blocks_per_sm < 2 else 64 * 1024
             ids, n_poly, tasks, n_tasks = plan.poly_tables()
             self.poly_ids, self.poly_tasks = ids.to(dev), tasks.to(dev)
-            self.ctx.set_poly(self.poly_ids.data_ptr(), n_poly, self.poly_tasks.data_ptr(), n_tasks)
+            from .plan import RANK_BINS
+            tot = max(int(plan.poly_total), 1)
+            self.poly_bins = torch.zeros(max(n_poly, 1) * 2 * RANK_BINS, dtype=torch.int32, device=dev)
+            self.bucket_val = torch.zeros(tot, dtype=torch.float32, device=dev)
+            self.bucket_pos = torch.zeros(tot, dtype=torch.int32, device=dev)
+            self.expand_buf = torch.zeros(self.world * tot, dtype=torch.float32, device=dev)
+            self.ctx.set_poly(self.poly_ids.data_ptr(), n_poly, self.poly_tasks.data_ptr(), n_tasks,
+                              self.poly_bins.data_ptr(), self.bucket_val.data_ptr(), self.bucket_pos.data_ptr(),
+                              self.expand_buf.data_ptr(), int(plan.poly_total))
             self.ctx.configure(self.beta, self.gamma, scale, int(seed), POLICY_ID[plan.policy], int(use_history),
                                int(spin_limit), int(blocks_per_sm), int(filter_smem_bytes), int(use_tma), int(hist_shift))
         self.grad_views = plan.views(self.grad)

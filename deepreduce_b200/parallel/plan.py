@@ -28,7 +28,8 @@ NUM_HIST = 3
 ALIGN_ELEMS = 32
 MAX_SEGMENTS = 22
 MAX_POLY_K = 1 << 17      # the all-pairs rank pass is O(K^2): larger tensors keep fp32 values
-DESC_WORDS = 24
+DESC_WORDS = 32
+RANK_BINS = 8192
 
 
 def _align(x: int, a: int) -> int:
@@ -62,12 +63,15 @@ class TensorPlan:
     off_sorted: int = 0
     poly_degree: int = 5
     rank_u32: int = 0
+    poly_off: int = 0
+    poly_ord: int = 0
 
     def words(self) -> List[int]:
         return [self.elem_off, self.numel, self.k, self.tile_begin, self.n_tiles, self.mode, self.m_bits,
                 self.n_hash, self.off_vals, self.off_filter, self.off_prefix, self.off_idx, self.val_cap,
                 self.salt, self.n_filter_words, self.off_hint, self.vmode, self.off_coef, self.off_rankmap,
-                self.off_selidx, self.off_sorted, self.poly_degree, self.rank_u32, 0]
+                self.off_selidx, self.off_sorted, self.poly_degree, self.rank_u32, self.poly_off, self.poly_ord,
+                0, 0, 0, 0, 0, 0, 0]
 
 
 @dataclass
@@ -150,10 +154,16 @@ class BucketPlan:
             setattr(tp, attr, word)
             word = _align(word + n, 4)
         self.slot_words = _align(word, 64)
+        self.poly_tables()                     # assigns poly_off / poly_ord
 
     def poly_tables(self):
         """(tensor ids with vmode==1, largest K first ; rank-phase tasks {tensor, first value of a 512-chunk})."""
         ids = sorted([i for i, t in enumerate(self.tensors) if t.vmode == 1], key=lambda i: -self.tensors[i].val_cap)
+        off = 0
+        for o, i in enumerate(ids):
+            self.tensors[i].poly_off, self.tensors[i].poly_ord = off, o
+            off += self.tensors[i].val_cap
+        self.poly_total = off
         tasks = [(i, c) for i in ids for c in range(0, self.tensors[i].val_cap, 512)]
         ids_t = torch.tensor(ids if ids else [0], dtype=torch.int32)
         tasks_t = torch.tensor(tasks if tasks else [(0, 0)], dtype=torch.int32).reshape(-1)

@@ -36,7 +36,7 @@ def test_plan_layout():
     for (a, n), (b, _) in zip(regions[:-1], regions[1:]):
         assert a + n <= b
     assert regions[-1][0] + regions[-1][1] <= plan.payload_words <= plan.slot_words
-    assert plan.tensor_table().numel() == 24 * len(SIZES)
+    assert plan.tensor_table().numel() == 32 * len(SIZES)
     # bloom wire is smaller than plain (fp32,int64) pairs: the paper's headline for index compression
     assert plan.wire_bytes() < plan.topk_pair_bytes()
 
