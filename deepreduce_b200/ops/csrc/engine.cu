@@ -945,10 +945,21 @@ DR_D uint32_t load_rank(const uint32_t* slot, const TensorDesc& td, uint32_t p) 
 }
 
 // ---- exact descending rank: counting sort on 13 bits of the order-preserving key + all-pairs inside a bin ----
-DR_D uint32_t rank_bin(float v) {               // bin 0 holds the largest values
-  const uint32_t b = __float_as_uint(v);
-  const uint32_t u = (b & 0x80000000u) ? ~b : (b | 0x80000000u);      // monotone float -> uint
-  return (uint32_t)(kRankBins - 1) - (u >> 19);
+// Bins are monotone non-increasing in the value and centred on the tensor's selection threshold T (31-bit
+// key): per sign 1024 coarse bins above 4T (16 per octave), 2048 fine bins on [T, 4T) (relative width 2^-10)
+// and 1024 coarse bins below T (false positives carry arbitrary small values).  Exactness never depends on
+// the binning — phase 9 counts inside the bin — only the amount of in-bin work does.
+DR_D uint32_t rank_bin(float v, uint32_t T) {
+  const uint32_t bits = __float_as_uint(v), key = bits & 0x7FFFFFFFu;
+  uint32_t pb;                                   // 0 = largest magnitude ... 4095 = smallest
+  if (key >= T) {
+    const uint32_t d = key - T;
+    if (d < (2u << 23)) pb = 1024u + (2047u - (d >> 13));
+    else pb = 1023u - min(1023u, (key >> 19) - ((T + (2u << 23)) >> 19));
+  } else {
+    pb = 3072u + min(1023u, (T >> 19) - (key >> 19));
+  }
+  return (bits & 0x80000000u) ? (4096u + (4095u - pb)) : pb;
 }
 
 // phase 6: bin populations
@@ -962,7 +973,7 @@ DR_D void phase_rank_hist(const EngineParams& P, Smem& sm) {
     const uint32_t n = __ldcg(&dyn->n_sel), p = p0 + threadIdx.x;
     if (p < n) {
       const float v = __ldcg(reinterpret_cast<const float*>(my_slot + sm.td.off_vals) + p);
-      atomicAdd(P.poly_bins + (size_t)sm.td.poly_ord * 2 * kRankBins + rank_bin(v), 1u);
+      atomicAdd(P.poly_bins + (size_t)sm.td.poly_ord * 2 * kRankBins + rank_bin(v, __ldcg(&P.sel[t].thr)), 1u);
     }
   }
 }
@@ -1003,7 +1014,7 @@ DR_D void phase_rank_scatter(const EngineParams& P, Smem& sm) {
     if (p < n) {
       const float v = __ldcg(reinterpret_cast<const float*>(my_slot + sm.td.off_vals) + p);
       uint32_t* tab = P.poly_bins + (size_t)sm.td.poly_ord * 2 * kRankBins;
-      const uint32_t b = rank_bin(v);
+      const uint32_t b = rank_bin(v, __ldcg(&P.sel[t].thr));
       // the count array is re-used as the running cursor: it is decremented down to 0 while filling the bin
       const uint32_t within = atomicSub(tab + b, 1u) - 1u;
       const uint32_t pos = __ldcg(tab + kRankBins + b) + within;
@@ -1027,7 +1038,7 @@ DR_D void phase_rank_exact(const EngineParams& P, Smem& sm) {
       const float* bv = P.bucket_val + sm.td.poly_off;
       const uint32_t* bp = P.bucket_pos + sm.td.poly_off;
       v = __ldcg(bv + i);
-      const uint32_t p = __ldcg(bp + i), b = rank_bin(v);
+      const uint32_t p = __ldcg(bp + i), b = rank_bin(v, __ldcg(&P.sel[t].thr));
       const uint32_t* start = P.poly_bins + (size_t)sm.td.poly_ord * 2 * kRankBins + kRankBins;
       const uint32_t lo = __ldcg(start + b), hi = (b + 1 < (uint32_t)kRankBins) ? __ldcg(start + b + 1) : n;
       uint32_t rank = lo;
@@ -1068,6 +1079,16 @@ DR_D void phase_fit(const EngineParams& P, Smem& sm) {
     if (len <= 0) continue;
     const float* y = reinterpret_cast<const float*>(my_slot + off_sorted) + start[s];
     const int deg_eff = min(deg, len - 1);
+    // recurrence constants of this segment (no divisions in the inner loop):
+    //   p_{k+1} = ra[k] * (N - 2x) * p_k - rb[k] * p_{k-1}
+    const float N = (float)(len - 1), invN = len > 1 ? 1.f / N : 0.f;
+    float ra[kMaxDeg], rb[kMaxDeg];
+#pragma unroll
+    for (int k = 1; k < kMaxDeg; ++k) {
+      const float dnm = (k + 1.f) * (N - k);
+      ra[k] = (k < deg_eff) ? (2.f * k + 1.f) / dnm : 0.f;
+      rb[k] = (k < deg_eff) ? (float)k * (N + k + 1.f) / dnm : 0.f;
+    }
     float num[kMaxDeg + 1], den[kMaxDeg + 1];
 #pragma unroll
     for (int k = 0; k <= kMaxDeg; ++k) { num[k] = 0.f; den[k] = 0.f; }
@@ -1080,7 +1101,11 @@ DR_D void phase_fit(const EngineParams& P, Smem& sm) {
         const int x = x0 + 32 * u;
         if (x < len) {
           float p[kMaxDeg + 1];
-          gram_eval<kMaxDeg + 1>((float)x, (float)(len - 1), deg_eff, p);
+          const float uu = N - 2.f * (float)x;
+          p[0] = 1.f;
+          p[1] = deg_eff >= 1 ? uu * invN : 0.f;
+#pragma unroll
+          for (int k = 1; k < kMaxDeg; ++k) p[k + 1] = ra[k] * uu * p[k] - rb[k] * p[k - 1];
 #pragma unroll
           for (int k = 0; k <= kMaxDeg; ++k) { num[k] += p[k] * yv[u]; den[k] += p[k] * p[k]; }
         }
