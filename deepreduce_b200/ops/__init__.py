@@ -178,13 +178,11 @@ def delta_bp128_decode(payload, n):
 
 
 def rle_runs(idxs, d):
-    from ..codecs.rle import runs_from_sorted_oracle
-    return runs_from_sorted_oracle(idxs, d)      # vectorised torch on the GPU (O(K))
+    return cuda_module().rle_runs(idxs.long().contiguous(), int(d))
 
 
 def rle_indices(runs, n):
-    from ..codecs.rle import indices_from_runs_oracle
-    return indices_from_runs_oracle(runs)
+    return cuda_module().rle_indices(runs.long().contiguous())
 
 
 def u8_to_nhwc_norm(x_u8, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)):

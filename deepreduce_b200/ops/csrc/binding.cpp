@@ -160,6 +160,48 @@ static torch::Tensor delta_bp128_decode(torch::Tensor payload, int64_t n) {
   return deltas.cumsum(0);
 }
 
+// sorted unique indices -> runs [z0, o0, z1, o1, ..., (tail zeros)]
+static torch::Tensor rle_runs(torch::Tensor idx, int64_t d) {
+  CHECK_CUDA_T(idx);
+  c10::cuda::CUDAGuard g(idx.device());
+  const int64_t n = idx.numel();
+  auto o64 = idx.options().dtype(torch::kInt64);
+  if (n == 0) return torch::full({1}, d, o64);
+  const int64_t nb = (n + 1023) / 1024;
+  auto counts = torch::empty({nb}, idx.options().dtype(torch::kInt32));
+  auto excl = torch::empty({nb + 1}, idx.options().dtype(torch::kInt32));
+  dr::launch_rle_count(idx.data_ptr<int64_t>(), n, (uint32_t*)counts.data_ptr<int32_t>(), (uint32_t*)excl.data_ptr<int32_t>(),
+                       cur_stream());
+  const int64_t n_runs = excl[nb].item<int32_t>();
+  auto start_pos = torch::empty({n_runs}, o64), end_pos = torch::empty({n_runs}, o64);
+  auto runs = torch::zeros({2 * n_runs + 1}, o64);
+  dr::launch_rle_runs(idx.data_ptr<int64_t>(), n, (const uint32_t*)excl.data_ptr<int32_t>(), start_pos.data_ptr<int64_t>(),
+                      end_pos.data_ptr<int64_t>(), n_runs, d, runs.data_ptr<int64_t>(), cur_stream());
+  check_last("rle_runs");
+  const int64_t last = idx[n - 1].item<int64_t>();
+  return (d - 1 - last > 0) ? runs : runs.slice(0, 0, 2 * n_runs);
+}
+
+static torch::Tensor rle_indices(torch::Tensor runs) {
+  CHECK_CUDA_T(runs);
+  c10::cuda::CUDAGuard g(runs.device());
+  const int64_t n_pairs = runs.numel() / 2;
+  auto o64 = runs.options().dtype(torch::kInt64);
+  if (n_pairs == 0) return torch::empty({0}, o64);
+  auto pairs = runs.slice(0, 0, 2 * n_pairs).to(torch::kInt64).view({n_pairs, 2});
+  auto z = pairs.select(1, 0), o = pairs.select(1, 1);
+  auto csum = (z + o).cumsum(0);
+  auto run_start = (csum - o).contiguous();
+  auto ones_incl = o.cumsum(0);
+  auto ones_excl = (ones_incl - o).contiguous();
+  const int64_t total = ones_incl[n_pairs - 1].item<int64_t>();
+  auto out = torch::empty({total}, o64);
+  dr::launch_rle_expand(ones_excl.data_ptr<int64_t>(), run_start.data_ptr<int64_t>(), n_pairs, total, out.data_ptr<int64_t>(),
+                        cur_stream());
+  check_last("rle_indices");
+  return out;
+}
+
 static torch::Tensor u8_to_nhwc_norm(torch::Tensor in, std::vector<double> mean, std::vector<double> stdv) {
   CHECK_CUDA_T(in);
   TORCH_CHECK(in.scalar_type() == torch::kUInt8 && in.size(-1) == 3, "expect uint8 [...,3] NHWC");
@@ -377,6 +419,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("delta_bp128_encode", &delta_bp128_encode);
   m.def("delta_bp128_decode", &delta_bp128_decode);
   m.def("u8_to_nhwc_norm", &u8_to_nhwc_norm);
+  m.def("rle_runs", &rle_runs);
+  m.def("rle_indices", &rle_indices);
   m.def("arena_alloc", &arena_alloc);
   m.def("arena_free", [](int64_t p) { dr::arena_free((void*)p); });
   m.def("arena_export", &arena_export);

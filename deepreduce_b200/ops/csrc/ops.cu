@@ -316,6 +316,61 @@ __global__ void bp128_header_scan_kernel(const uint32_t* __restrict__ in, int64_
   }
 }
 
+// ---------------------------------------------------------------------------
+// bit-level run-length index coding (reference RunLength, pytorch/deepreduce.py:805-846, which loops over all d
+// bits in Python).  Runs are derived from the sorted indices: a run of ones starts where idx[i] != idx[i-1]+1.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) rle_count_kernel(const int64_t* __restrict__ idx, int64_t n, uint32_t* __restrict__ counts) {
+  const int64_t i = blockIdx.x * 1024ll + threadIdx.x;
+  const bool start = i < n && (i == 0 || idx[i] != idx[i - 1] + 1);
+  const int c = __syncthreads_count(start);
+  if (threadIdx.x == 0) counts[blockIdx.x] = c;
+}
+
+__global__ void __launch_bounds__(1024) rle_mark_kernel(const int64_t* __restrict__ idx, int64_t n, const uint32_t* __restrict__ excl,
+                                                        int64_t* __restrict__ start_pos, int64_t* __restrict__ end_pos) {
+  __shared__ uint32_t wsum[32];
+  const int64_t i = blockIdx.x * 1024ll + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const bool start = i < n && (i == 0 || idx[i] != idx[i - 1] + 1);
+  const bool end = i < n && (i == n - 1 || idx[i + 1] != idx[i] + 1);
+  const uint32_t ball = __ballot_sync(0xFFFFFFFFu, start);
+  if (lane == 0) wsum[warp] = __popc(ball);
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = wsum[lane], wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t nb = __shfl_up_sync(0xFFFFFFFFu, wi, o); if (lane >= (uint32_t)o) wi += nb; }
+    wsum[lane] = wi - w;
+  }
+  __syncthreads();
+  // inclusive count of starts up to and including element i
+  const uint32_t incl = excl[blockIdx.x] + wsum[warp] + __popc(ball & ((2u << lane) - 1u));
+  if (start) start_pos[incl - 1] = i;
+  if (end) end_pos[incl - 1] = i;               // an end closes the run opened by the latest start
+}
+
+__global__ void rle_runs_kernel(const int64_t* __restrict__ idx, const int64_t* __restrict__ start_pos,
+                                const int64_t* __restrict__ end_pos, int64_t n_runs, int64_t d, int64_t* __restrict__ runs) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_runs; r += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = start_pos[r], e = end_pos[r];
+    const int64_t prev_end = r ? idx[end_pos[r - 1]] : -1;
+    runs[2 * r] = idx[s] - prev_end - 1;
+    runs[2 * r + 1] = e - s + 1;
+    if (r == n_runs - 1) { const int64_t tail = d - 1 - idx[e]; if (tail > 0) runs[2 * n_runs] = tail; }
+  }
+}
+
+// decode: thread j finds the run holding the j-th index (binary search over the cumulative ones counts)
+__global__ void rle_expand_kernel(const int64_t* __restrict__ ones_excl, const int64_t* __restrict__ run_start, int64_t n_runs,
+                                  int64_t total, int64_t* __restrict__ out) {
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < total; j += (int64_t)gridDim.x * blockDim.x) {
+    int64_t lo = 0, hi = n_runs;                 // largest r with ones_excl[r] <= j
+    while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (ones_excl[mid] <= j) lo = mid; else hi = mid; }
+    out[j] = run_start[lo] + (j - ones_excl[lo]);
+  }
+}
+
 inline int grid_for(int64_t n, int threads, int cap = 148 * 8) {
   int64_t g = (n + threads - 1) / threads;
   if (g < 1) g = 1;
@@ -407,6 +462,28 @@ void launch_bp128_pack(const int64_t* idx, int64_t n, const uint32_t* widths, co
   const int64_t n_blocks = (n + 127) / 128;
   count_launch();
   bp128_pack_kernel<<<(int)((n_blocks * 32 + 255) / 256), 256, 0, st>>>(idx, n, widths, word_off, out);
+}
+
+void launch_rle_count(const int64_t* idx, int64_t n, uint32_t* counts, uint32_t* excl, cudaStream_t st) {
+  const uint32_t nb = (uint32_t)((n + 1023) / 1024);
+  count_launch(2);
+  rle_count_kernel<<<nb, 1024, 0, st>>>(idx, n, counts);
+  scan_counts_kernel<<<1, 1024, 0, st>>>(counts, excl, nb);
+}
+
+void launch_rle_runs(const int64_t* idx, int64_t n, const uint32_t* excl, int64_t* start_pos, int64_t* end_pos,
+                     int64_t n_runs, int64_t d, int64_t* runs, cudaStream_t st) {
+  const uint32_t nb = (uint32_t)((n + 1023) / 1024);
+  count_launch(2);
+  rle_mark_kernel<<<nb, 1024, 0, st>>>(idx, n, excl, start_pos, end_pos);
+  rle_runs_kernel<<<grid_for(n_runs, 256), 256, 0, st>>>(idx, start_pos, end_pos, n_runs, d, runs);
+}
+
+void launch_rle_expand(const int64_t* ones_excl, const int64_t* run_start, int64_t n_runs, int64_t total, int64_t* out,
+                       cudaStream_t st) {
+  if (total == 0) return;
+  count_launch();
+  rle_expand_kernel<<<grid_for(total, 256), 256, 0, st>>>(ones_excl, run_start, n_runs, total, out);
 }
 
 void launch_bp128_unpack(const uint32_t* in, int64_t n, int64_t* word_off, int64_t* deltas, cudaStream_t st) {

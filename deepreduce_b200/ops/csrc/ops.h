@@ -34,6 +34,11 @@ void launch_bp128_widths(const int64_t* idx, int64_t n, uint32_t* widths, cudaSt
 void launch_bp128_pack(const int64_t* idx, int64_t n, const uint32_t* widths, const int64_t* word_off, uint32_t* out,
                        cudaStream_t st);
 void launch_bp128_unpack(const uint32_t* in, int64_t n, int64_t* word_off, int64_t* deltas, cudaStream_t st);
+void launch_rle_count(const int64_t* idx, int64_t n, uint32_t* counts, uint32_t* excl, cudaStream_t st);
+void launch_rle_runs(const int64_t* idx, int64_t n, const uint32_t* excl, int64_t* start_pos, int64_t* end_pos,
+                     int64_t n_runs, int64_t d, int64_t* runs, cudaStream_t st);
+void launch_rle_expand(const int64_t* ones_excl, const int64_t* run_start, int64_t n_runs, int64_t total, int64_t* out,
+                       cudaStream_t st);
 
 // p2p.cu — symmetric arena over CUDA IPC
 struct ArenaHandle { unsigned char bytes[64]; };

@@ -76,6 +76,7 @@ class DeepReduceDDP:
         self.sched = None
         self.grc = None
         self._handles = []
+        self._exchange = True
         if self.fused or (self.dense and self.is_cuda):
             self._build_buckets(bucket_cap_mb, blocks_per_sm, use_history)
             if self.fused and self.overlap and background_thread:
@@ -140,7 +141,13 @@ class DeepReduceDDP:
         for n, p in self.named:
             self._handles.append(p.register_post_accumulate_grad_hook(self._hook))
 
+    def set_exchange_enabled(self, on: bool):
+        """Gradient accumulation: hooks only launch the exchange on the last micro-step."""
+        self._exchange = bool(on)
+
     def _hook(self, p):
+        if not self._exchange:
+            return
         b = self.bucket_of[id(p)]
         self._ready_count[b] += 1
         if self._ready_count[b] == self._bucket_size[b]:

@@ -24,7 +24,7 @@ class Trainer:
                  weight_decay: float = 1e-4, amp_dtype: Optional[torch.dtype] = torch.bfloat16,
                  channels_last: bool = False, loss_fn: Optional[Callable] = None, optimizer=None,
                  overlap: bool = True, bucket_cap_mb: float = 1e9, background_thread: bool = True,
-                 blocks_per_sm: int = 2, u8_input: bool = False):
+                 blocks_per_sm: int = 2, u8_input: bool = False, accum_steps: int = 1, nvtx: bool = False):
         self.model = model
         self.device = next(model.parameters()).device
         self.is_cuda = self.device.type == "cuda"
@@ -42,6 +42,9 @@ class Trainer:
             optimizer = torch.optim.SGD(self.model.parameters(), **kw)
         self.opt = optimizer
         self.u8_input = u8_input
+        self.accum_steps = max(1, int(accum_steps))     # reference trainers' --grads_accumulated
+        self._micro = 0
+        self.nvtx = nvtx and self.is_cuda
         self._copy_stream = torch.cuda.Stream(device=self.device) if self.is_cuda else None
         self._staged = None
         self._loss_host = torch.zeros(1, dtype=torch.float32).pin_memory() if self.is_cuda else torch.zeros(1)
@@ -57,19 +60,33 @@ class Trainer:
             x = x.contiguous(memory_format=torch.channels_last)
         return x
 
+    def _range(self, name):
+        import contextlib
+        return torch.cuda.nvtx.range(name) if self.nvtx else contextlib.nullcontext()
+
     def step(self, *inputs, target) -> torch.Tensor:
-        """One optimisation step on device tensors; returns the loss (device scalar)."""
-        self.ddp.zero_grad()
+        """One optimisation step on device tensors; returns the loss (device scalar).  With
+        ``accum_steps > 1`` gradients accumulate locally and are exchanged every ``accum_steps`` calls."""
+        first = self._micro == 0
+        last = self._micro == self.accum_steps - 1
+        if first:
+            self.ddp.zero_grad()
+        self.ddp.set_exchange_enabled(last)
         inputs = tuple(self._prep(x) for x in inputs)
-        if self.amp_dtype is not None:
-            with torch.autocast(device_type="cuda", dtype=self.amp_dtype):
+        with self._range("forward"):
+            if self.amp_dtype is not None:
+                with torch.autocast(device_type="cuda", dtype=self.amp_dtype):
+                    out = self.model(*inputs)
+            else:
                 out = self.model(*inputs)
-        else:
-            out = self.model(*inputs)
-        loss = self.loss_fn(out.float() if out.is_floating_point() else out, target)
-        loss.backward()
-        self.ddp.finish()
-        self.opt.step()
+            loss = self.loss_fn(out.float() if torch.is_tensor(out) and out.is_floating_point() else out, target)
+        with self._range("backward+exchange"):
+            (loss / self.accum_steps if self.accum_steps > 1 else loss).backward()
+        self._micro = (self._micro + 1) % self.accum_steps
+        if last:
+            with self._range("finish+optimizer"):
+                self.ddp.finish()
+                self.opt.step()
         return loss.detach()
 
     # ---- end-to-end step (host in, host out) -----------------------------------

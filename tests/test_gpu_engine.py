@@ -188,6 +188,13 @@ def test_per_tensor_ops_vs_oracle():
     from deepreduce_b200.codecs.integer import int_encode
     ref = int_encode(np.diff(idx.numpy().astype(np.uint32), prepend=np.uint32(0)).astype(np.uint32), "bp128")
     assert np.array_equal(enc.cpu().numpy().view(np.uint32), ref)
+    # run-length kernels
+    from deepreduce_b200.codecs import rle as R
+    blocks = torch.cat([torch.arange(100, 160), torch.arange(5000, 5003), idx[idx > 6000]]).unique()
+    for ix, dd in ((idx, d), (blocks, d), (torch.arange(0, 50), 50), (torch.tensor([d - 1]), d)):
+        runs = ops.rle_runs(ix.cuda(), dd)
+        assert torch.equal(runs.cpu(), R.runs_from_sorted_oracle(ix, dd)), (ix[:5], dd)
+        assert torch.equal(ops.rle_indices(runs, ix.numel()).cpu(), ix)
     # input normalisation kernel
     img = torch.randint(0, 256, (4, 32, 32, 3), dtype=torch.uint8)
     o = ops.u8_to_nhwc_norm(img.cuda()).float().cpu()
