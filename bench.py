@@ -34,6 +34,9 @@ CONFIGS = {
     "both": {'compressor': 'topk', 'memory': 'residual', 'communicator': 'allgather', 'compress_ratio': 0.01,
              'deepreduce': 'both', 'index': 'bloom', 'value': 'polyfit'},
     "topk": {'compressor': 'topk', 'memory': 'residual', 'communicator': 'allgather', 'compress_ratio': 0.01},
+    # BASELINE.json config 4: NCF top-k 0.1 % + run-length index
+    "rle": {'compressor': 'topk', 'memory': 'residual', 'communicator': 'allgather', 'compress_ratio': 0.001,
+            'deepreduce': 'index', 'index': 'rle'},
     "dense": {'compressor': 'none', 'memory': 'none', 'communicator': 'allreduce'},
 }
 
@@ -46,11 +49,13 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="bloom", choices=sorted(CONFIGS))
     ap.add_argument("--model", default="resnet50")
-    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (weak scaling)")
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (weak scaling); default 256 (resnet50), 8 (bert_large), 65536 (ncf)")
+    ap.add_argument("--seq", type=int, default=128, help="sequence length for bert_large")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--no-thread", action="store_true")
-    ap.add_argument("--bucket-mb", type=float, default=32.0)
+    ap.add_argument("--bucket-mb", type=float, default=128.0,
+                    help="flat bucket size; on a compute-saturated GPU one bucket launched at the end of backward is fastest (profiles/)")
     ap.add_argument("--blocks-per-sm", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="also time the exchange kernel alone (extra keys)")
@@ -172,30 +177,55 @@ def timed(fn, steps, world):
     return max_over_ranks(e0.elapsed_time(e1), world), max_over_ranks(wall, world)
 
 
+def model_spec(args):
+    """(model, kind, default per-GPU batch, metric unit)"""
+    from deepreduce_b200 import models as M
+    if args.model == "resnet50":
+        return M.resnet50(), "image224", 256, "images/s"
+    if args.model == "resnet20":
+        return M.resnet20(), "image32", 256, "images/s"
+    if args.model == "bert_large":
+        return M.bert_large(seq_len=max(args.seq, 128)), "bert", 8, "sequences/s"
+    if args.model == "ncf":
+        return M.NeuMF(), "ncf", 65536, "samples/s"
+    raise ValueError(args.model)
+
+
 def run_ours(args, rank, world, local):
     import torch
     from deepreduce_b200 import ops
     from deepreduce_b200.trainer import Trainer
     torch.manual_seed(1234)
     torch.backends.cudnn.benchmark = True
-    hw = 224 if args.model == "resnet50" else 32
-    ncls = 1000 if args.model == "resnet50" else 10
-    model = build_model(args.model).cuda()
+    model, kind, default_b, unit = model_spec(args)
+    model = model.cuda()
+    B = args.batch or default_b
     cfg = dict(CONFIGS[args.config])
     amp = torch.bfloat16 if args.dtype == "bf16" else None
-    tr = Trainer(model, cfg, lr=0.05, amp_dtype=amp, channels_last=True, overlap=not args.no_overlap,
-                 bucket_cap_mb=args.bucket_mb, background_thread=not args.no_thread,
-                 blocks_per_sm=args.blocks_per_sm, u8_input=True)
-    B = args.batch
     gen = torch.Generator().manual_seed(77 + rank)
-    # device-resident synthetic batches (uint8 NHWC, normalised on device by our kernel)
-    pool = [torch.randint(0, 256, (B, hw, hw, 3), dtype=torch.uint8, generator=gen) for _ in range(2)]
-    tgt = [torch.randint(0, ncls, (B,), generator=gen) for _ in range(2)]
-    dev_x = [p.cuda() for p in pool]
+    loss_fn = None
+    if kind.startswith("image"):
+        hw = 224 if kind == "image224" else 32
+        ncls = 1000 if kind == "image224" else 10
+        pool = [(torch.randint(0, 256, (B, hw, hw, 3), dtype=torch.uint8, generator=gen),) for _ in range(2)]
+        tgt = [torch.randint(0, ncls, (B,), generator=gen) for _ in range(2)]
+    elif kind == "bert":
+        V = 30522
+        pool = [(torch.randint(0, V, (B, args.seq), generator=gen),) for _ in range(2)]
+        tgt = [p[0].clone() for p in pool]
+        loss_fn = lambda out, y: torch.nn.functional.cross_entropy(out.logits.reshape(-1, V).float(), y.reshape(-1))  # noqa: E731
+    else:   # ncf
+        pool = [(torch.randint(0, 138493, (B,), generator=gen), torch.randint(0, 26744, (B,), generator=gen)) for _ in range(2)]
+        tgt = [torch.randint(0, 2, (B,), generator=gen).float() for _ in range(2)]
+        loss_fn = torch.nn.functional.binary_cross_entropy_with_logits
+    tr = Trainer(model, cfg, lr=0.05 if kind != "bert" else 1e-4, amp_dtype=amp, channels_last=kind.startswith("image"),
+                 overlap=not args.no_overlap, bucket_cap_mb=args.bucket_mb, background_thread=not args.no_thread,
+                 blocks_per_sm=args.blocks_per_sm, u8_input=kind.startswith("image"), loss_fn=loss_fn)
+    dev_x = [tuple(t.cuda() for t in p) for p in pool]
     dev_y = [t.cuda() for t in tgt]
 
     def step(i):
-        tr.step(dev_x[i & 1], target=dev_y[i & 1])
+        tr.step(*dev_x[i & 1], target=dev_y[i & 1])
 
     for i in range(args.warmup):
         step(i)
@@ -212,23 +242,22 @@ def run_ours(args, rank, world, local):
 
     e2e = None
     if not args.no_e2e:
-        host_x = [p.pin_memory() for p in pool]
+        host_x = [tuple(t.pin_memory() for t in p) for p in pool]
         host_y = [t.pin_memory() for t in tgt]
 
         def step_e2e(i):
-            nxt = ((host_x[(i + 1) & 1],), host_y[(i + 1) & 1])
-            tr.step_host((host_x[i & 1],), host_y[i & 1], next_batch=nxt)
+            nxt = (host_x[(i + 1) & 1], host_y[(i + 1) & 1])
+            tr.step_host(host_x[i & 1], host_y[i & 1], next_batch=nxt)
 
         for i in range(2):
             step_e2e(i)
         _, wall_e = timed(step_e2e, args.steps, world)
-        e2e = {"value": world * B * args.steps / (wall_e / 1e3), "unit": "images/s",
+        e2e = {"value": world * B * args.steps / (wall_e / 1e3), "unit": unit,
                "h2d_bytes_per_step": int(tr.h2d_bytes), "d2h_bytes_per_step": int(tr.d2h_bytes)}
 
     extra = {}
     if args.breakdown and tr.ddp.engines:
-        # exchange kernel alone on the last gradients (all buckets back to back)
-        def ex(i):
+        def ex(i):       # exchange kernel alone on the last gradients (all buckets back to back)
             for e in tr.ddp.engines:
                 e.step()
         for i in range(3):
@@ -238,15 +267,18 @@ def run_ours(args, rank, world, local):
         extra["engine_grid"] = tr.ddp.engines[0].grid()
     wire = tr.ddp.wire_bytes_per_step()
     dense = tr.ddp.dense_bytes()
+    names = {"resnet50": "ResNet-50 images/sec (whole job, device-timed, max over ranks)",
+             "bert_large": "BERT-large sequences/sec (whole job, device-timed, max over ranks)",
+             "ncf": "NCF (MovieLens-20M shapes) samples/sec (whole job, device-timed, max over ranks)"}
     out = {
-        "metric": "ResNet-50 images/sec (whole job, device-timed, max over ranks)" if args.model == "resnet50"
-        else f"{args.model} images/sec",
-        "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": names.get(args.model, f"{args.model} {unit}"),
+        "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": args.dtype, "data": "synthetic (uint8 224x224x3, random-init weights)", "impl": "ours",
-        "config": {"model": args.model, "global_batch": B * world, "per_gpu_batch": B, "image": hw,
+        "dtype": args.dtype, "data": "synthetic (shapes of the named benchmark, random-init weights)", "impl": "ours",
+        "config": {"model": args.model, "global_batch": B * world, "per_gpu_batch": B,
+                   "seq_len": args.seq if kind == "bert" else None,
                    "parallelism": f"dp{world}", "gradient_exchange": args.config, "params": cfg,
-                   "l2": "working set (activations, 102 MB fp32 grads + residual) exceeds the 126 MB L2 every step",
+                   "l2": "working set (activations + fp32 gradients + residual) exceeds the 126 MB L2 every step",
                    "overlap": not args.no_overlap, "buckets": len(tr.ddp.flat), "bucket_mb": args.bucket_mb},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "wire_bytes_per_step_per_rank": int(wire), "dense_bytes": int(dense),
@@ -294,7 +326,7 @@ def run_reference(args, rank, world, local):
         wrapper = {'value': R.ValueCompressor, 'index': R.IndexCompressor, 'both': R.DeepReduce}[cfg["deepreduce"]]
         grc.compressor = wrapper(grc.compressor, cfg)
     opt = torch.optim.SGD(model.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
-    B = args.batch
+    B = args.batch or 256
     gen = torch.Generator().manual_seed(77 + rank)
     host_x = [torch.randn(B, 3, 224, 224, generator=gen).pin_memory() for _ in range(2)]
     host_y = [torch.randint(0, 1000, (B,), generator=gen).pin_memory() for _ in range(2)]

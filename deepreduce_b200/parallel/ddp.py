@@ -135,6 +135,7 @@ class DeepReduceDDP:
                 p.grad = seg.as_strided(p.size(), p.stride()) if _is_dense(p) else seg.view(p.shape)
                 self.bucket_of[id(p)] = b
         self._ready_count = [0] * len(self.buckets)
+        self._launched = [False] * len(self.buckets)
         self._bucket_size = [len(it) for it in self.buckets]
 
     def _install_hooks(self):
@@ -155,6 +156,7 @@ class DeepReduceDDP:
 
     def _launch_bucket(self, b):
         self._ready_count[b] = 0
+        self._launched[b] = True
         if self.fused:
             eng = self.engines[b]
             eng.epoch = self.step_count + 1
@@ -183,15 +185,17 @@ class DeepReduceDDP:
                 if p.grad is not None:
                     p.grad = self.grc.step(p.grad, n).view_as(p)
         elif self.fused:
-            if not self.overlap:
-                for b in range(len(self.buckets)):
+            for b in range(len(self.buckets)):        # not overlapped, or a parameter received no gradient this step
+                if not self._launched[b]:
                     self._launch_bucket(b)
             if self.sched is not None:
                 self.sched.wait_all()
+            self._launched = [False] * len(self.buckets)
         else:
-            if not self.overlap:
-                for b in range(len(self.buckets)):
+            for b in range(len(self.buckets)):
+                if not self._launched[b]:
                     self._launch_bucket(b)
+            self._launched = [False] * len(self.buckets)
             for w in self.pending:
                 w.wait()
             self.pending = []
