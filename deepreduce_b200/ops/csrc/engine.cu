@@ -45,11 +45,10 @@ constexpr uint32_t kErrLookback = 1u, kErrPeerWait = 2u, kErrResolve = 3u;
 constexpr uint32_t kNoTensor = 0xFFFFFFFFu;
 
 struct ScanSmem {
-  uint32_t cnt[2][kPerThread * kWarps + 4];   // double-buffered tile_rank scratch (+ total)
+  alignas(16) uint32_t cnt[2][kPerThread * kWarps];   // double-buffered tile_rank scratch
   uint32_t warp_tot[kWarps];
   uint32_t res[4];                            // resolve results: bin, krem, bincount, spare
-  uint32_t lb;                                // look-back result
-  uint32_t buf;                               // which cnt buffer is next
+  uint32_t lb;                                // small CTA-wide scratch word
 };
 
 struct Smem {
@@ -90,11 +89,14 @@ DR_D void load_tensor(const EngineParams& P, uint32_t t, Smem& sm) {
 // ---------------------------------------------------------------------------
 // ordered in-tile ranks.  Thread `tid` owns elements tid + c*kThreads (c < 8);
 // bit c of `flags` marks element c.  Returns the exclusive rank of every
-// flagged element in element order and the tile total.  Two __syncthreads.
+// flagged element in element order and the tile total.  ONE __syncthreads:
+// every warp publishes its 8 slot counts, then scans all 128 counts itself.
+// `buf` is a per-thread toggle (double buffering makes a trailing barrier
+// unnecessary: a buffer is rewritten two calls later, after the barrier of the
+// call in between).
 // ---------------------------------------------------------------------------
-DR_D void tile_rank(uint32_t flags, ScanSmem& s, uint32_t (&rank)[kPerThread], uint32_t& total) {
+DR_D void tile_rank(uint32_t flags, ScanSmem& s, uint32_t& buf, uint32_t (&rank)[kPerThread], uint32_t& total) {
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const uint32_t buf = s.buf & 1u;            // uniform: read before the first sync of this call
   uint32_t ball[kPerThread];
 #pragma unroll
   for (int c = 0; c < kPerThread; ++c) ball[c] = __ballot_sync(0xFFFFFFFFu, (flags >> c) & 1u);
@@ -103,27 +105,31 @@ DR_D void tile_rank(uint32_t flags, ScanSmem& s, uint32_t (&rank)[kPerThread], u
     for (int c = 0; c < kPerThread; ++c) s.cnt[buf][c * kWarps + warp] = __popc(ball[c]);
   }
   __syncthreads();
-  if (warp == 0) {
-    uint32_t v[4], sum = 0;                   // 128 counters, 4 per lane
+  // lane l holds counts 4l .. 4l+3 (element order = slot-major, warp-minor)
+  const uint4 v = reinterpret_cast<const uint4*>(s.cnt[buf])[lane];
+  const uint32_t sum = v.x + v.y + v.z + v.w;
+  uint32_t incl = sum;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { v[i] = s.cnt[buf][lane * 4 + i]; sum += v[i]; }
-    uint32_t incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-      if (lane >= (uint32_t)o) incl += n;
-    }
-    uint32_t run = incl - sum;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { s.cnt[buf][lane * 4 + i] = run; run += v[i]; }
-    if (lane == 31) s.cnt[buf][kPerThread * kWarps] = incl;
-    if (lane == 0) s.buf = buf ^ 1u;
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= (uint32_t)o) incl += n;
   }
-  __syncthreads();
+  const uint32_t base = incl - sum;
+  const uint32_t sub = warp & 3u;
+  const uint32_t part = (sub > 0 ? v.x : 0u) + (sub > 1 ? v.y : 0u) + (sub > 2 ? v.z : 0u);   // my lane's partials, reused below
   const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
-  for (int c = 0; c < kPerThread; ++c) rank[c] = s.cnt[buf][c * kWarps + warp] + __popc(ball[c] & lt);
-  total = s.cnt[buf][kPerThread * kWarps];
+  for (int c = 0; c < kPerThread; ++c) {
+    // prefix of index i = c*16 + warp lives in lane i>>2 = 4c + (warp>>2), at sub-position warp&3
+    const int src = 4 * c + (int)(warp >> 2);
+    const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, base, src);
+    const uint32_t vx = __shfl_sync(0xFFFFFFFFu, v.x, src), vy = __shfl_sync(0xFFFFFFFFu, v.y, src),
+                   vz = __shfl_sync(0xFFFFFFFFu, v.z, src);
+    rank[c] = b0 + (sub > 0 ? vx : 0u) + (sub > 1 ? vy : 0u) + (sub > 2 ? vz : 0u) + __popc(ball[c] & lt);
+  }
+  (void)part;
+  total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+  buf ^= 1u;
 }
 
 // ---------------------------------------------------------------------------
@@ -838,7 +844,7 @@ DR_D void phase_emit(const EngineParams& P, Smem& sm) {
     my_slot[0] = kMagic; my_slot[1] = P.epoch; my_slot[2] = P.n_tensors; my_slot[3] = P.payload_words;
     my_slot[4] = (uint32_t)P.rank;
   }
-  uint32_t cur = kNoTensor, T22 = 1, excl = 0;
+  uint32_t cur = kNoTensor, T22 = 1, excl = 0, rank_buf = 0;
   uint32_t tile, t_end;
   tile_range(P, tile, t_end);
   for (; tile < t_end; ++tile) {
@@ -866,7 +872,7 @@ DR_D void phase_emit(const EngineParams& P, Smem& sm) {
     const bool last_tile = (tile_local + 1 == sm.td.n_tiles);
     const uint32_t flags = P.flag_buf[(size_t)tile * kThreads + threadIdx.x];
     uint32_t rank[kPerThread], total;
-    tile_rank(flags, sm.s, rank, total);
+    tile_rank(flags, sm.s, rank_buf, rank, total);
     const uint32_t limit = (sm.td.mode == kModeBloom && P.policy != kPolicyP0) ? min(sm.td.k, sm.td.val_cap)
                                                                                : sm.td.val_cap;
     float* vals = reinterpret_cast<float*>(my_slot + sm.td.off_vals);
@@ -1229,7 +1235,7 @@ DR_D void phase_decode(const EngineParams& P, Smem& sm) {
     for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < P.n_poly * 2u * kRankBins; i += gridDim.x * kThreads)
       P.poly_bins[i] = 0u;
   }
-  uint32_t tile, t_end;
+  uint32_t tile, t_end, rank_buf = 0;
   tile_range(P, tile, t_end);
   while (tile < t_end) {
     const Tile t0 = load_tile(P, tile);
@@ -1281,7 +1287,7 @@ DR_D void phase_decode(const EngineParams& P, Smem& sm) {
           else flags = bloom_test8(ti.local0 + threadIdx.x, valid, P.seed, n_hash, m_bits,
                                    [&](uint32_t w) { return filter[w]; });
           uint32_t rank[kPerThread], total;
-          tile_rank(flags, sm.s, rank, total);
+          tile_rank(flags, sm.s, rank_buf, rank, total);
 #pragma unroll
           for (int c = 0; c < kPerThread; ++c) {
             if ((flags >> c) & 1u) {
@@ -1324,7 +1330,6 @@ template <int kMinBlocks>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) dr_engine_kernel(const __grid_constant__ EngineParams P) {
   __shared__ Smem sm;
   if (threadIdx.x == 0) {
-    sm.s.buf = 0;
     for (int i = 0; i < 8; ++i) mbar_init(&sm.bar[i], 1);
     mbar_fence_init();
   }
