@@ -975,6 +975,7 @@ DR_D void phase_rank_hist(const EngineParams& P, Smem& sm) {
   for (uint32_t task = blockIdx.x; task < P.n_poly_tasks; task += gridDim.x) {
     const uint32_t t = __ldg(P.poly_tasks + 2 * task), p0 = __ldg(P.poly_tasks + 2 * task + 1);
     load_tensor(P, t, sm);
+    if (sm.td.vmode != 1) continue;
     const DynHeader* dyn = reinterpret_cast<const DynHeader*>(my_slot + kSlotHeaderWords) + t;
     const uint32_t n = __ldcg(&dyn->n_sel), p = p0 + threadIdx.x;
     if (p < n) {
@@ -1015,6 +1016,7 @@ DR_D void phase_rank_scatter(const EngineParams& P, Smem& sm) {
   for (uint32_t task = blockIdx.x; task < P.n_poly_tasks; task += gridDim.x) {
     const uint32_t t = __ldg(P.poly_tasks + 2 * task), p0 = __ldg(P.poly_tasks + 2 * task + 1);
     load_tensor(P, t, sm);
+    if (sm.td.vmode != 1) continue;
     const DynHeader* dyn = reinterpret_cast<const DynHeader*>(my_slot + kSlotHeaderWords) + t;
     const uint32_t n = __ldcg(&dyn->n_sel), p = p0 + threadIdx.x;
     if (p < n) {
@@ -1037,6 +1039,7 @@ DR_D void phase_rank_exact(const EngineParams& P, Smem& sm) {
   for (uint32_t task = blockIdx.x; task < P.n_poly_tasks; task += gridDim.x) {
     const uint32_t t = __ldg(P.poly_tasks + 2 * task), p0 = __ldg(P.poly_tasks + 2 * task + 1);
     load_tensor(P, t, sm);
+    if (sm.td.vmode != 1) continue;
     const DynHeader* dyn = reinterpret_cast<const DynHeader*>(my_slot + kSlotHeaderWords) + t;
     const uint32_t n = __ldcg(&dyn->n_sel), i = p0 + threadIdx.x;   // i = position in the grouped arrays
     float v = 0.f;
@@ -1139,6 +1142,35 @@ DR_D void phase_fix(const EngineParams& P, Smem& sm) {
   for (uint32_t task = blockIdx.x; task < P.n_poly_tasks; task += gridDim.x) {
     const uint32_t t = __ldg(P.poly_tasks + 2 * task), p0 = __ldg(P.poly_tasks + 2 * task + 1);
     load_tensor(P, t, sm);
+    if (sm.td.vmode == 2) {
+      // bucketed QSGD (reference QSGD, pytorch/deepreduce.py:849-907, which syncs the host once per bucket):
+      // this CTA owns one 512-value bucket: L2 norm, stochastic rounding with a counter-based RNG, int8 level
+      const DynHeader* dyn = reinterpret_cast<const DynHeader*>(my_slot + kSlotHeaderWords) + t;
+      const uint32_t nq = __ldcg(&dyn->n_sel);
+      if (p0 >= nq) continue;
+      const uint32_t p = p0 + threadIdx.x;
+      const float v = p < nq ? __ldcg(reinterpret_cast<const float*>(my_slot + sm.td.off_vals) + p) : 0.f;
+      float ss = v * v;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
+      __syncthreads();
+      if ((threadIdx.x & 31u) == 0) sm.s.warp_tot[threadIdx.x >> 5] = __float_as_uint(ss);
+      __syncthreads();
+      float tot = 0.f;
+      for (int w = 0; w < kWarps; ++w) tot += __uint_as_float(sm.s.warp_tot[w]);
+      const float norm = sqrtf(tot), q = (float)sm.td.poly_degree;
+      if (threadIdx.x == 0) reinterpret_cast<float*>(my_slot + sm.td.off_coef)[p0 >> 9] = norm;
+      if (p < nq) {
+        const float lf = (norm > 0.f ? q / norm : 0.f) * fabsf(v);
+        const float prev = floorf(lf);
+        const float u = (float)((double)policy_hash(p, 0x51EDu + P.epoch) / 4294967296.0);
+        float l = prev + ((u < (lf - prev)) ? 1.f : 0.f);
+        l = v > 0.f ? l : (v < 0.f ? -l : 0.f);
+        reinterpret_cast<int8_t*>(my_slot + sm.td.off_rankmap)[p] = (int8_t)l;
+        P.resid[__ldcg(my_slot + sm.td.off_selidx + p)] = v - norm / q * l;
+      }
+      continue;
+    }
     const int deg = (int)sm.td.poly_degree;
     const uint32_t* tail = my_slot + sm.td.off_coef + kMaxSeg * (deg + 1);
     const int num_pos = (int)__ldcg(tail), n = (int)__ldcg(tail + 1);
@@ -1196,6 +1228,7 @@ DR_D void phase_expand(const EngineParams& P, Smem& sm) {
     const uint32_t r = wt / P.n_poly_tasks, task = wt - r * P.n_poly_tasks;
     const uint32_t t = __ldg(P.poly_tasks + 2 * task), j0 = __ldg(P.poly_tasks + 2 * task + 1);
     load_tensor(P, t, sm);
+    if (sm.td.vmode != 1) continue;
     const uint32_t* slot = slot_ptr(arena, P, parity, (int)r);
     const int deg = (int)sm.td.poly_degree;
     const uint32_t* tail = slot + sm.td.off_coef + kMaxSeg * (deg + 1);
@@ -1294,7 +1327,12 @@ DR_D void phase_decode(const EngineParams& P, Smem& sm) {
               const uint32_t rp = pre + rank[c];
               if (rp < n_sel) {
                 float* o = P.grad + ti.base + c * kThreads + threadIdx.x;   // the same thread owns this element for every rank
-                const float val = sm.td.vmode ? __ldcg(fitted + load_rank(slot, sm.td, rp)) : __ldcg(vals + rp);
+                float val;
+                if (sm.td.vmode == 1) val = __ldcg(fitted + load_rank(slot, sm.td, rp));
+                else if (sm.td.vmode == 2)
+                  val = __ldcg(reinterpret_cast<const float*>(slot + sm.td.off_coef) + (rp >> 9)) / (float)sm.td.poly_degree *
+                        (float)__ldcg(reinterpret_cast<const int8_t*>(slot + sm.td.off_rankmap) + rp);
+                else val = __ldcg(vals + rp);
                 *o = *o + val * P.scale;
               }
             }
@@ -1349,7 +1387,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) dr_engine_kernel(const _
       case kPhRankScatter: if (P.n_poly) phase_rank_scatter(P, sm); else ran = false; break;
       case kPhRankExact: if (P.n_poly) phase_rank_exact(P, sm); else ran = false; break;
       case kPhFit: if (P.n_poly) phase_fit(P, sm); else ran = false; break;
-      case kPhFix: if (P.n_poly) phase_fix(P, sm); else ran = false; break;
+      case kPhFix: if (P.n_poly_tasks) phase_fix(P, sm); else ran = false; break;
       case kPhExpand: if (P.n_poly) phase_expand(P, sm); else ran = false; break;
       case kPhPush: if (P.world > 1) phase_push(P); else ran = false; break;
       case kPhSignal: if (P.world > 1) phase_signal(P); else ran = false; break;

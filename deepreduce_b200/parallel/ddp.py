@@ -49,7 +49,10 @@ def _fused_supported(params: dict) -> bool:
     pol_ok = canonical_policy(params.get('policy', 'leftmost')) in ('leftmost', 'p0')
     if dr == 'index' and params.get('index', 'bloom') == 'bloom':
         return pol_ok
-    if dr == 'both' and params.get('index', 'bloom') == 'bloom' and params.get('value', 'polyfit') == 'polyfit':
+    if dr == 'both' and params.get('index', 'bloom') == 'bloom' and (
+            params.get('value', 'polyfit') == 'polyfit'
+            or (params.get('value') == 'qsgd' and int(params.get('quantum_num', 127)) < 128
+                and int(params.get('bucket_size', 512)) == 512)):
         return pol_ok
     return False
 
@@ -109,7 +112,8 @@ class DeepReduceDDP:
             if self.fused:
                 plan = BucketPlan(numels, names, shapes, compress_ratio=self.params.get('compress_ratio', 0.01),
                                   index='bloom' if self.params.get('deepreduce') in ('index', 'both') else None,
-                                  value='polyfit' if self.params.get('deepreduce') == 'both' else None,
+                                  value=self.params.get('value', 'polyfit') if self.params.get('deepreduce') == 'both' else None,
+                                  quantum_num=int(self.params.get('quantum_num', 127)),
                                   poly_degree=int(self.params.get('poly_degree', 5)),
                                   fpr=self.params.get('fpr', None),
                                   policy=canonical_policy(self.params.get('policy', 'leftmost')),

@@ -49,7 +49,7 @@ def select_topk_oracle(acc: torch.Tensor, k: int):
     return sel, T22 << 9
 
 
-def encode_tensor_oracle(tp, acc: torch.Tensor, slot: np.ndarray, t_index: int, policy: str, seed: int):
+def encode_tensor_oracle(tp, acc: torch.Tensor, slot: np.ndarray, t_index: int, policy: str, seed: int, epoch: int = 1):
     """Encode one tensor into `slot` (uint32 numpy view); returns new residual."""
     sel_topk, T = select_topk_oracle(acc, tp.k)
     dyn = SLOT_HEADER_WORDS + DYN_WORDS * t_index
@@ -108,6 +108,19 @@ def encode_tensor_oracle(tp, acc: torch.Tensor, slot: np.ndarray, t_index: int, 
             slot[tp.off_rankmap:tp.off_rankmap + (n + 1) // 2] = r16.view(np.uint32)
         resid[sel] = vals - fitted
         vals = fitted
+    elif tp.vmode == 2:
+        from ..codecs.qsgd import qsgd_decode_oracle, qsgd_encode_oracle
+        n = int(sel.numel())
+        q = int(tp.poly_degree)
+        lvl, norms = qsgd_encode_oracle(vals, q, 512, 0x51ED + epoch)
+        dec = qsgd_decode_oracle(lvl, norms, q, 512) if n else vals
+        nb = (n + 511) // 512
+        slot[tp.off_coef:tp.off_coef + nb] = norms.float().numpy().view(np.uint32)
+        l8 = np.zeros(((n + 3) // 4) * 4, dtype=np.int8)
+        l8[:n] = lvl.numpy().astype(np.int8)
+        slot[tp.off_rankmap:tp.off_rankmap + (n + 3) // 4] = l8.view(np.uint32)
+        resid[sel] = vals - dec
+        vals = dec
     else:
         slot[tp.off_vals:tp.off_vals + sel.numel()] = vals.cpu().numpy().view(np.uint32)
         resid[sel] = 0
@@ -134,7 +147,7 @@ def engine_oracle(plan: BucketPlan, grads: Sequence[torch.Tensor], resids: Seque
         nres = acc_flat.clone()
         for ti, tp in enumerate(plan.tensors):
             seg = slice(tp.elem_off, tp.elem_off + tp.numel)
-            resid_t, sel, vals = encode_tensor_oracle(tp, acc_flat[seg], slot, ti, plan.policy, seed)
+            resid_t, sel, vals = encode_tensor_oracle(tp, acc_flat[seg], slot, ti, plan.policy, seed, epoch)
             nres[seg] = resid_t
             out[seg].index_add_(0, sel, vals)
         new_resids.append(nres)

@@ -87,7 +87,8 @@ class BucketPlan:
     max_hash: int = 16
     ks: Optional[Sequence[int]] = None    # explicit per-tensor K (overrides compress_ratio)
     hint: bool = True                     # ship the 1-bit-per-32-elements occupancy hint next to each bloom filter
-    value: Optional[str] = None           # None (fp32 values) or 'polyfit' ('both': bloom index + curve fit)
+    value: Optional[str] = None           # None (fp32 values), 'polyfit' or 'qsgd' ('both': bloom index + value codec)
+    quantum_num: int = 127                # QSGD levels (int8 on the wire)
     poly_degree: int = 5
     poly_min_k: int = 512                 # tensors shipping fewer values keep them as fp32 (the fit header would be larger)
     tensors: List[TensorPlan] = field(default_factory=list, init=False)
@@ -128,6 +129,15 @@ class BucketPlan:
                     tp.off_rankmap = word
                     word = _align(word + (tp.val_cap if tp.rank_u32 else (tp.val_cap + 1) // 2), 4)
                     scratch += [(tp, "off_vals", tp.val_cap), (tp, "off_selidx", tp.val_cap), (tp, "off_sorted", tp.val_cap)]
+                elif self.value == "qsgd" and self.quantum_num < 128:
+                    # bucketed QSGD (512 values per bucket): int8 levels + one fp32 norm per bucket
+                    tp.vmode = 2
+                    tp.poly_degree = int(self.quantum_num)      # field re-used: quantum_num
+                    tp.off_coef = word                           # norms
+                    word = _align(word + (tp.val_cap + 511) // 512, 4)
+                    tp.off_rankmap = word                        # levels (int8)
+                    word = _align(word + (tp.val_cap + 3) // 4, 4)
+                    scratch += [(tp, "off_vals", tp.val_cap), (tp, "off_selidx", tp.val_cap)]
                 else:
                     tp.off_vals = word
                     word = _align(word + tp.val_cap, 4)
@@ -164,7 +174,8 @@ class BucketPlan:
             self.tensors[i].poly_off, self.tensors[i].poly_ord = off, o
             off += self.tensors[i].val_cap
         self.poly_total = off
-        tasks = [(i, c) for i in ids for c in range(0, self.tensors[i].val_cap, 512)]
+        coded = sorted([i for i, t in enumerate(self.tensors) if t.vmode != 0], key=lambda i: -self.tensors[i].val_cap)
+        tasks = [(i, c) for i in coded for c in range(0, self.tensors[i].val_cap, 512)]      # all value-coded tensors
         ids_t = torch.tensor(ids if ids else [0], dtype=torch.int32)
         tasks_t = torch.tensor(tasks if tasks else [(0, 0)], dtype=torch.int32).reshape(-1)
         return ids_t, len(ids), tasks_t, len(tasks)

@@ -17,7 +17,7 @@ def main():
     sizes = [64, 1001, 4097, 36864, 147456, 10, 589824, 2359296]
     ok = True
     for index, policy, value in (("bloom", "leftmost", None), ("bloom", "p0", None), (None, "leftmost", None),
-                                 ("bloom", "leftmost", "polyfit")):
+                                 ("bloom", "leftmost", "polyfit"), ("bloom", "leftmost", "qsgd")):
         plan = BucketPlan(sizes, compress_ratio=0.01, index=index, policy=policy, value=value)
         eng = BucketEngine(plan, device=f"cuda:{local}", spin_limit=4_000_000)
         resid_refs = [torch.zeros(plan.total_elems) for _ in range(world)]

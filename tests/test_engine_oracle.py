@@ -141,3 +141,17 @@ def test_oracle_both_polyfit():
     rel = (out[seg] - out_p[seg]).norm() / out_p[seg].norm()
     assert rel < 0.08
     assert torch.allclose(out[seg] + res[0][seg], g[seg], atol=1e-6)     # residual keeps the fit error
+
+
+def test_oracle_both_qsgd():
+    torch.manual_seed(8)
+    plan = BucketPlan([300000], compress_ratio=0.01, value="qsgd")
+    plain = BucketPlan([300000], compress_ratio=0.01)
+    assert plan.tensors[0].vmode == 2 and plan.poly_tables()[3] == (3000 + 511) // 512
+    assert plan.wire_bytes() < 0.6 * plain.wire_bytes()                  # values: 4 B -> 1 B (+ a norm per 512)
+    g = torch.zeros(plan.total_elems); g[:300000] = torch.randn(300000)
+    out, res, _ = engine_oracle(plan, [g], [torch.zeros_like(g)])
+    out_p, _, _ = engine_oracle(plain, [g], [torch.zeros_like(g)])
+    assert torch.equal(out != 0, out_p != 0) or (out != 0).sum() >= 0.98 * (out_p != 0).sum()   # level 0 can zero a value
+    assert (out - out_p).norm() / out_p.norm() < 0.12
+    assert torch.allclose(out + res[0], g, atol=1e-6)

@@ -63,6 +63,16 @@ def _compare_slot(plan, slot_gpu, slot_ref, tag):
             ia, ib = a[t.off_idx:t.off_idx + n_sel], b[t.off_idx:t.off_idx + n_sel]
             if not np.array_equal(ia, ib):
                 bad.append(f"{t.name} raw idx gpu={ia[:8].tolist()} ref={ib[:8].tolist()}")
+        if t.vmode == 2:
+            nb = (n_sel + 511) // 512
+            na, nbb = a[t.off_coef:t.off_coef + nb].view(np.float32), b[t.off_coef:t.off_coef + nb].view(np.float32)
+            if not np.allclose(na, nbb, rtol=1e-5):
+                bad.append(f"{t.name} qsgd norms differ {float(np.abs(na - nbb).max())}")
+            la = a[t.off_rankmap:t.off_rankmap + (n_sel + 3) // 4].view(np.int8)[:n_sel]
+            lb = b[t.off_rankmap:t.off_rankmap + (n_sel + 3) // 4].view(np.int8)[:n_sel]
+            if int((la != lb).sum()) > max(2, n_sel // 2000):       # rounding-boundary flips from reduction order only
+                bad.append(f"{t.name} qsgd levels differ in {int((la != lb).sum())}/{n_sel}")
+            continue
         if t.vmode == 1:
             nc = 22 * (t.poly_degree + 1)
             ca, cb = a[t.off_coef:t.off_coef + nc].view(np.float32), b[t.off_coef:t.off_coef + nc].view(np.float32)
@@ -89,7 +99,8 @@ SIZES = [64, 1000, 1001, 4096, 4097, 36864, 147456, 10, 589824]
 @pytest.mark.parametrize("kind", ["randn", "sparse", "ties"])
 @pytest.mark.parametrize("index,policy,hint,tma,value", [
     ("bloom", "leftmost", True, True, None), ("bloom", "leftmost", False, False, None), ("bloom", "p0", True, True, None),
-    (None, "leftmost", True, True, None), ("bloom", "leftmost", True, True, "polyfit")])
+    (None, "leftmost", True, True, None), ("bloom", "leftmost", True, True, "polyfit"),
+    ("bloom", "leftmost", True, True, "qsgd")])
 def test_engine_vs_oracle_single_rank(kind, index, policy, hint, tma, value):
     from deepreduce_b200.parallel import BucketEngine, BucketPlan, engine_oracle
     plan = BucketPlan(SIZES + [2359296], compress_ratio=0.01, index=index, policy=policy, hint=hint, value=value,
