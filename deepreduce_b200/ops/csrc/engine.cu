@@ -69,6 +69,21 @@ DR_D uint32_t* slot_ptr(uint32_t* arena, const EngineParams& P, uint32_t parity,
   return arena + kArenaHdrWords + (size_t)(parity * (uint32_t)P.world + (uint32_t)src) * P.slot_words;
 }
 
+DR_D uint32_t* s2_ptr(uint32_t* arena, const EngineParams& P, uint32_t parity, int src) {
+  return arena + kArenaHdrWords + (size_t)2 * (uint32_t)P.world * P.slot_words +
+         (size_t)(parity * (uint32_t)P.world + (uint32_t)src) * P.s2_words;
+}
+
+DR_D bool sharded(const EngineParams& P) { return P.shard && P.world > 1; }
+
+// tiles this rank decodes: everything (W == 1 / unsharded) or its 1/W slice
+DR_D void decode_span(const EngineParams& P, int owner, uint32_t& s_begin, uint32_t& s_end) {
+  if (sharded(P)) {
+    s_begin = (uint32_t)(((uint64_t)P.n_tiles * (uint32_t)owner) / (uint32_t)P.world);
+    s_end = (uint32_t)(((uint64_t)P.n_tiles * ((uint32_t)owner + 1u)) / (uint32_t)P.world);
+  } else { s_begin = 0; s_end = P.n_tiles; }
+}
+
 struct Tile { uint32_t tensor, base, n, local0, single; };   // `single`: the tensor has exactly one tile
 
 DR_D Tile load_tile(const EngineParams& P, uint32_t tile) {
@@ -298,6 +313,7 @@ DR_D void phase_accum(const EngineParams& P, Smem& sm) {
     const uint4 z = make_uint4(0, 0, 0, 0);
     for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n4; i += gridDim.x * kThreads) p[i] = z;
   }
+  if (sharded(P) && blockIdx.x == 0 && threadIdx.x == 0) *s2_ptr(P.arena[P.rank], P, parity, P.rank) = 0u;
   clear_hist(sm);
   const bool has_resid = (P.beta != 0.0f);
   uint32_t cur = kNoTensor, lower = 0, n_mine = 0;
@@ -570,6 +586,7 @@ DR_D void phase_accum_tma(const EngineParams& P, Smem& sm) {
     const uint4 z = make_uint4(0, 0, 0, 0);
     for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n4; i += gridDim.x * kThreads) p[i] = z;
   }
+  if (sharded(P) && blockIdx.x == 0 && threadIdx.x == 0) *s2_ptr(P.arena[P.rank], P, parity_slot, P.rank) = 0u;
   clear_hist(sm);
   const bool has_resid = (P.beta != 0.0f);
   const Ring ring = ring_setup(P, sm, 2u * kTile * 4u, 8u);      // stage = g tile | r tile
@@ -1269,7 +1286,13 @@ DR_D void phase_decode(const EngineParams& P, Smem& sm) {
       P.poly_bins[i] = 0u;
   }
   uint32_t tile, t_end, rank_buf = 0;
-  tile_range(P, tile, t_end);
+  {
+    uint32_t s_begin, s_end;
+    decode_span(P, P.rank, s_begin, s_end);
+    const uint32_t span = s_end - s_begin;
+    tile = s_begin + (uint32_t)(((uint64_t)span * blockIdx.x) / gridDim.x);
+    t_end = s_begin + (uint32_t)(((uint64_t)span * (blockIdx.x + 1)) / gridDim.x);
+  }
   while (tile < t_end) {
     const Tile t0 = load_tile(P, tile);
     const uint32_t t = t0.tensor;
@@ -1364,6 +1387,106 @@ DR_D void phase_decode(const EngineParams& P, Smem& sm) {
   }
 }
 
+// ===========================================================================
+// sharded decode, stage 2 (W > 1): my decoded slice -> exact (index, value) list -> peers
+// ===========================================================================
+DR_D void phase_compact(const EngineParams& P, Smem& sm) {
+  const uint32_t parity = P.epoch & 1u;
+  uint32_t my_b, my_e;
+  decode_span(P, P.rank, my_b, my_e);
+  // (a) zero every tile outside my slice (peers' lists are scattered into them later)
+  for (uint32_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+    if (tile >= my_b && tile < my_e) continue;
+    const Tile ti = load_tile(P, tile);
+    float4* dst = reinterpret_cast<float4*>(P.grad + ti.base);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (uint32_t i = threadIdx.x; i < ((ti.n + 3u) >> 2); i += kThreads) dst[i] = z;   // tensors are padded to 32 floats
+  }
+  // (b) non-zeros of my slice -> my stage-2 slot (unordered: slices are disjoint, receivers only write)
+  uint32_t* s2 = s2_ptr(P.arena[P.rank], P, parity, P.rank);
+  uint32_t* idx_out = s2 + 4;
+  float* val_out = reinterpret_cast<float*>(s2 + 4 + P.s2_cap);
+  const uint32_t lane = threadIdx.x & 31u;
+  for (uint32_t tile = my_b + blockIdx.x; tile < my_e; tile += gridDim.x) {
+    const Tile ti = load_tile(P, tile);
+    float v[kPerThread];
+    uint32_t nz = 0;
+#pragma unroll
+    for (int c = 0; c < kPerThread; ++c) {
+      const uint32_t e = c * kThreads + threadIdx.x;
+      v[c] = e < ti.n ? __ldcg(P.grad + ti.base + e) : 0.f;
+      if (v[c] != 0.f) nz |= 1u << c;
+    }
+    const uint32_t cnt = __popc(nz);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t nb = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += nb; }
+    uint32_t wbase = 0;
+    if (lane == 31 && incl) wbase = atomicAdd(s2, incl);          // s2[0] = entry count (zeroed in the accumulate phase)
+    wbase = __shfl_sync(0xFFFFFFFFu, wbase, 31);
+    uint32_t pos = wbase + incl - cnt;
+#pragma unroll
+    for (int c = 0; c < kPerThread; ++c) {
+      if ((nz >> c) & 1u) {
+        if (pos < P.s2_cap) { idx_out[pos] = ti.base + c * kThreads + threadIdx.x; val_out[pos] = v[c]; }
+        else atomicExch(P.status, 6u);                            // stage-2 capacity exceeded
+        ++pos;
+      }
+    }
+  }
+}
+
+DR_D void phase_push2(const EngineParams& P) {
+  const uint32_t parity = P.epoch & 1u;
+  const uint32_t* src = s2_ptr(P.arena[P.rank], P, parity, P.rank);
+  const uint32_t n = min(__ldcg(src), P.s2_cap);
+  for (int h = 1; h < P.world; ++h) {
+    const int peer = (P.rank + h) % P.world;
+    uint32_t* dst = s2_ptr(P.arena[peer], P, parity, P.rank);
+    const uint32_t gtid = blockIdx.x * kThreads + threadIdx.x, gsz = gridDim.x * kThreads;
+    if (gtid < 4) dst[gtid] = gtid == 0 ? n : (gtid == 1 ? P.epoch : 0u);
+    // idx block and val block, 16 bytes at a time
+    const uint4* si = reinterpret_cast<const uint4*>(src + 4);
+    const uint4* sv = reinterpret_cast<const uint4*>(src + 4 + P.s2_cap);
+    uint4* di = reinterpret_cast<uint4*>(dst + 4);
+    uint4* dv = reinterpret_cast<uint4*>(dst + 4 + P.s2_cap);
+    const uint32_t n4 = (n + 3u) >> 2;
+    for (uint32_t i = gtid; i < n4; i += gsz) {
+      const uint4 a = __ldcg(si + i), b = __ldcg(sv + i);
+      asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(di + i), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w) : "memory");
+      asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dv + i), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+    }
+  }
+  __threadfence_system();
+}
+
+DR_D void phase_signal2(const EngineParams& P) {
+  const int p = threadIdx.x;
+  if (blockIdx.x == 0 && p < P.world && p != P.rank) st_release_sys(P.arena[p] + kArenaFlagWords + P.rank, P.epoch);
+  if (p < P.world && p != P.rank) {
+    const uint32_t* flag = P.arena[P.rank] + kArenaFlagWords + p;
+    uint32_t spins = 0;
+    while ((int32_t)(ld_acquire_sys(flag) - P.epoch) < 0) {
+      if (++spins > P.spin_limit) { atomicExch(P.status, kErrPeerWait); atomicExch(P.status + 1, 100u + (uint32_t)p); break; }
+      __nanosleep(100);
+    }
+  }
+  __syncthreads();
+}
+
+DR_D void phase_scatter(const EngineParams& P) {
+  const uint32_t parity = P.epoch & 1u;
+  const uint32_t gtid = blockIdx.x * kThreads + threadIdx.x, gsz = gridDim.x * kThreads;
+  for (int h = 1; h < P.world; ++h) {
+    const int r = (P.rank + h) % P.world;
+    const uint32_t* s2 = s2_ptr(P.arena[P.rank], P, parity, r);
+    const uint32_t n = min(__ldcg(s2), P.s2_cap);
+    const uint32_t* idx = s2 + 4;
+    const float* val = reinterpret_cast<const float*>(s2 + 4 + P.s2_cap);
+    for (uint32_t i = gtid; i < n; i += gsz) P.grad[__ldcg(idx + i)] = __ldcg(val + i);
+  }
+}
+
 template <int kMinBlocks>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) dr_engine_kernel(const __grid_constant__ EngineParams P) {
   __shared__ Smem sm;
@@ -1392,10 +1515,14 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) dr_engine_kernel(const _
       case kPhPush: if (P.world > 1) phase_push(P); else ran = false; break;
       case kPhSignal: if (P.world > 1) phase_signal(P); else ran = false; break;
       case kPhDecode: phase_decode(P, sm); break;
+      case kPhCompact: if (sharded(P)) phase_compact(P, sm); else ran = false; break;
+      case kPhPush2: if (sharded(P)) phase_push2(P); else ran = false; break;
+      case kPhSignal2: if (sharded(P)) phase_signal2(P); else ran = false; break;
+      case kPhScatter: if (sharded(P)) phase_scatter(P); else ran = false; break;
       default: ran = false; break;
     }
     // a barrier separates dependent phases; signal->decode needs none (every CTA waits itself)
-    if (ran && ph + 1 < P.phase_end && !(ph == kPhSignal)) grid_barrier(P.barrier, bar_epoch, P.status, P.spin_limit);
+    if (ran && ph + 1 < P.phase_end && !(ph == kPhSignal) && !(ph == kPhSignal2)) grid_barrier(P.barrier, bar_epoch, P.status, P.spin_limit);
   }
 }
 

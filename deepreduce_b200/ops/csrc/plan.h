@@ -81,7 +81,8 @@ constexpr int kHistBins = 2048;
 constexpr int kNumHist = 3;
 // hist arrays: [3][n_tensors][kHistBins]  (pass1, pass1-fallback, pass2);  hist_total: [3][n_tensors] merge tickets
 
-// arena layout per rank (uint32 words): [flags: 64][status: 64][slots: 2 * world * slot_words]
+// arena layout per rank (uint32 words): [flags: 64][stage-2 flags: 64][slots: 2 * world * slot_words]
+//                                       [stage-2 slots: 2 * world * s2_words]
 constexpr uint32_t kArenaFlagWords = 64;
 constexpr uint32_t kArenaHdrWords = 128;
 
@@ -109,7 +110,14 @@ enum Phase : int {
   kPhSignal = 13,    // release flags to peers, acquire peers' flags
   kPhExpand = 14,    // 'both': evaluate every rank's fitted curve once (dense), decode then only gathers
   kPhDecode = 15,    // membership test on every rank's filter, rank->value, sum, scale, dense write
-  kPhEnd = 16
+                     // (sharded mode, W>1: only this rank's 1/W slice of the tiles, for all W senders)
+  // sharded decode (W > 1): the decoded slice is exchanged as an exact (index, value) list — decode work per rank
+  // no longer grows with W; NVLink carries the extra ~2 MB/rank
+  kPhCompact = 16,   // zero the tiles outside my slice; compact the non-zeros of my decoded slice into my stage-2 slot
+  kPhPush2 = 17,     // P2P stores of the stage-2 slot into every peer's arena
+  kPhSignal2 = 18,   // second flag set (release/acquire)
+  kPhScatter = 19,   // write every peer's slice list into the dense gradient
+  kPhEnd = 20
 };
 
 // per-tile table (uint4): {tensor id, element offset of the tile in the flat buffers, valid count, offset inside tensor}
@@ -153,6 +161,9 @@ struct EngineParams {
   uint32_t* bucket_pos;          // [sum K] original position p of the grouped values
   float* expand_buf;             // [world][sum K] fitted curves of every rank
   uint32_t poly_total;           // sum K over the vmode==1 tensors
+  int shard;                     // 1: sharded decode + stage-2 exchange (when world > 1)
+  uint32_t s2_words;             // words per stage-2 slot: [count, epoch, 0, 0][idx x cap][val x cap]
+  uint32_t s2_cap;               // entries per stage-2 slot
 };
 
 }  // namespace dr

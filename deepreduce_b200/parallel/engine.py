@@ -12,6 +12,8 @@ the bucketed API.
 """
 from __future__ import annotations
 
+import os
+
 from collections import OrderedDict
 from typing import List, Optional, Sequence
 
@@ -25,9 +27,11 @@ from .plan import (ARENA_HDR_WORDS, DYN_WORDS, HIST_BINS, MODE_BLOOM, MODE_RAW, 
                    SLOT_HEADER_WORDS, BucketPlan)
 
 (PH_ACCUM, PH_FALLBACK, PH_HIST2, PH_INSERT, PH_QUERY, PH_EMIT, PH_RANK_HIST, PH_RANK_SCAN, PH_RANK_SCATTER,
- PH_RANK_EXACT, PH_FIT, PH_FIX, PH_PUSH, PH_SIGNAL, PH_EXPAND, PH_DECODE, PH_END) = range(17)
+ PH_RANK_EXACT, PH_FIT, PH_FIX, PH_PUSH, PH_SIGNAL, PH_EXPAND, PH_DECODE, PH_COMPACT, PH_PUSH2, PH_SIGNAL2,
+ PH_SCATTER, PH_END) = range(21)
 MAGIC = 0xD33B2000
-STATUS_NAMES = {0: "ok", 1: "(unused)", 2: "peer flag watchdog", 3: "select resolve failed", 4: "grid barrier watchdog", 5: "TMA mbarrier watchdog"}
+STATUS_NAMES = {0: "ok", 1: "(unused)", 2: "peer flag watchdog", 3: "select resolve failed", 4: "grid barrier watchdog", 5: "TMA mbarrier watchdog",
+                6: "stage-2 slot overflow (sharded decode)"}
 
 
 # ---------------------------------------------------------------------------
@@ -167,7 +171,7 @@ class BucketEngine:
                  average: bool = True, use_history: bool = True, blocks_per_sm: int = 2,
                  seed: int = spec.DEFAULT_SEED, spin_limit: int = 20_000_000, world: Optional[int] = None,
                  rank: Optional[int] = None, filter_smem_bytes: Optional[int] = None, use_tma: bool = True,
-                 hist_shift: int = 23):
+                 hist_shift: int = 23, shard: Optional[bool] = None):
         from .. import ops
         self.mod = ops.cuda_module()
         self.plan = plan
@@ -179,6 +183,9 @@ class BucketEngine:
         self.world, self.rank = int(world), int(rank or 0)
         self.beta, self.gamma, self.average = float(beta), float(gamma), bool(average)
         self.epoch = 0
+        # sharded decode (W > 1): each rank decodes 1/W of the tiles for all senders, then the exact slices are
+        # exchanged by a second in-kernel push.  DR_SHARD=0 restores the every-rank-decodes-everything path.
+        self.shard = (os.environ.get("DR_SHARD", "1") != "0") if shard is None else bool(shard)
         dev = self.device
         nT, nt = len(plan.tensors), plan.n_tiles
         with torch.cuda.device(dev):
@@ -202,6 +209,9 @@ class BucketEngine:
             scale = (1.0 / self.world) if average else 1.0
             if filter_smem_bytes is None:      # <1>: 128 regs, 1 CTA/SM; <2>: 64 regs, 2 CTAs/SM
                 filter_smem_bytes = 160 * 1024 if blocks_per_sm < 2 else 64 * 1024
+            if self.shard and self.world > 1:
+                cap, s2w = plan.stage2_layout(self.world)
+                self.ctx.set_shard(1, s2w, cap)
             ids, n_poly, tasks, n_tasks = plan.poly_tables()
             self.poly_ids, self.poly_tasks = ids.to(dev), tasks.to(dev)
             from .plan import RANK_BINS
@@ -219,7 +229,7 @@ class BucketEngine:
 
     # ---- arena -------------------------------------------------------------
     def _setup_arena(self):
-        words = self.plan.arena_words(self.world)
+        words = self.plan.arena_words(self.world, self.shard)
         self._ipc = self.world > 1
         if not self._ipc:
             self.arena = torch.zeros(words, dtype=torch.int32, device=self.device)

@@ -197,8 +197,18 @@ class BucketPlan:
             rows[:, 3] = loc
         return torch.from_numpy(out.astype(np.uint32).view(np.int32).copy())
 
-    def arena_words(self, world: int) -> int:
-        return ARENA_HDR_WORDS + 2 * world * self.slot_words
+    def stage2_layout(self, world: int):
+        """(entries, words) of a stage-2 slot for the sharded decode: a rank's slice holds about
+        sum(K) distinct non-zeros (W senders x K/W each); 2x slack + a floor."""
+        k_total = sum(t.val_cap for t in self.tensors)
+        cap = _align(2 * k_total + 8192, 4)
+        return cap, _align(4 + 2 * cap, 64)
+
+    def arena_words(self, world: int, shard: bool = True) -> int:
+        words = ARENA_HDR_WORDS + 2 * world * self.slot_words
+        if shard and world > 1:
+            words += 2 * world * self.stage2_layout(world)[1]
+        return words
 
     # ---- accounting --------------------------------------------------------
     def wire_bytes(self) -> int:

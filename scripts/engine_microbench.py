@@ -12,7 +12,7 @@ from deepreduce_b200.models import resnet50  # noqa: E402
 from deepreduce_b200.parallel import BucketEngine, BucketPlan  # noqa: E402
 
 PHASES = ["accum+hist1", "fallback", "hist2", "insert", "query", "emit", "rank_hist", "rank_scan", "rank_scatter", "rank_exact",
-          "fit", "fix", "push", "signal", "expand", "decode"]
+          "fit", "fix", "push", "signal", "expand", "decode", "compact", "push2", "signal2", "scatter"]
 
 
 def main():

@@ -16,10 +16,12 @@ def main():
     from deepreduce_b200.parallel import BucketEngine, BucketPlan, engine_oracle
     sizes = [64, 1001, 4097, 36864, 147456, 10, 589824, 2359296]
     ok = True
-    for index, policy, value in (("bloom", "leftmost", None), ("bloom", "p0", None), (None, "leftmost", None),
-                                 ("bloom", "leftmost", "polyfit"), ("bloom", "leftmost", "qsgd")):
+    for index, policy, value, shard in (("bloom", "leftmost", None, True), ("bloom", "leftmost", None, False),
+                                        ("bloom", "p0", None, True), (None, "leftmost", None, True),
+                                        ("bloom", "leftmost", "polyfit", True), ("bloom", "leftmost", "polyfit", False),
+                                        ("bloom", "leftmost", "qsgd", True)):
         plan = BucketPlan(sizes, compress_ratio=0.01, index=index, policy=policy, value=value)
-        eng = BucketEngine(plan, device=f"cuda:{local}", spin_limit=4_000_000)
+        eng = BucketEngine(plan, device=f"cuda:{local}", spin_limit=4_000_000, shard=shard)
         resid_refs = [torch.zeros(plan.total_elems) for _ in range(world)]
         for step in range(3):
             grads = []
@@ -54,7 +56,7 @@ def main():
                 resid_refs = [g.cpu() for g in gathered]
             if not (same_out and same_res and same_slots):
                 ok = False
-                print(f"[rank {rank}] MISMATCH index={index} policy={policy} step={step} out={same_out} res={same_res} slots={same_slots}",
+                print(f"[rank {rank}] MISMATCH index={index} policy={policy} value={value} shard={shard} step={step} out={same_out} res={same_res} slots={same_slots}",
                       flush=True)
         eng.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
