@@ -49,6 +49,7 @@ struct ScanSmem {
   uint32_t warp_tot[kWarps];
   uint32_t res[4];                            // resolve results: bin, krem, bincount, spare
   uint32_t lb;                                // small CTA-wide scratch word
+  uint32_t rle_pre[16];                       // kModeRle decode: running entry prefix per sender
 };
 
 struct Smem {
@@ -798,6 +799,36 @@ DR_D void phase_insert_tma(const EngineParams& P, Smem& sm) {
 }
 
 // ===========================================================================
+// kModeRle helpers: 12-bit fields, LSB-first, entry j at bit 12*j of the stream
+// ===========================================================================
+DR_D uint32_t rle_stream_words(uint32_t val_cap) { return (val_cap * 12u + 31u) / 32u + 1u; }
+
+DR_D void rle_put(uint32_t* stream, uint32_t j, uint32_t pos) {
+  const uint32_t bit = 12u * j, w = bit >> 5, sh = bit & 31u;
+  atomicOr(stream + w, pos << sh);
+  if (sh > 20u) atomicOr(stream + w + 1, pos >> (32u - sh));
+}
+
+DR_D uint32_t rle_get(const uint32_t* stream, uint32_t j) {
+  const uint32_t bit = 12u * j, w = bit >> 5, sh = bit & 31u;
+  uint32_t v = __ldcg(stream + w) >> sh;
+  if (sh > 20u) v |= __ldcg(stream + w + 1) << (32u - sh);
+  return v & 0xFFFu;
+}
+
+// the emit phase ORs fields into the stream: clear it first (any phase before emit; runs with the digit-2 pass)
+DR_D void rle_zero_streams(const EngineParams& P) {
+  uint32_t* my_slot = slot_ptr(P.arena[P.rank], P, P.epoch & 1u, P.rank);
+  for (uint32_t t = 0; t < P.n_tensors; ++t) {
+    const TensorDesc* td = P.tensors + t;
+    if (__ldg(&td->mode) != (uint32_t)kModeRle) continue;
+    const uint32_t n = rle_stream_words(__ldg(&td->val_cap));
+    uint32_t* dst = my_slot + __ldg(&td->off_idx);
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) dst[i] = 0u;
+  }
+}
+
+// ===========================================================================
 // phase 4: universe query — per-element flags + per-tile counts
 // ===========================================================================
 DR_D void phase_query(const EngineParams& P, Smem& sm) {
@@ -904,6 +935,7 @@ DR_D void phase_emit(const EngineParams& P, Smem& sm) {
             vals[rp] = P.resid[base + e];
             P.resid[base + e] = 0.0f;                      // residual is exactly 0 on the shipped set
             if (sm.td.mode == kModeRaw) idxs[rp] = local0 + e;
+            else if (sm.td.mode == kModeRle) rle_put(idxs, rp, e);
             if (sm.td.vmode) my_slot[sm.td.off_selidx + rp] = (uint32_t)(base + e);
             if (rp == limit - 1u) dyn->cutoff = local0 + e;
           }
@@ -912,6 +944,9 @@ DR_D void phase_emit(const EngineParams& P, Smem& sm) {
     }
     if (threadIdx.x == 0) {
       if (sm.td.mode == kModeBloom) my_slot[sm.td.off_prefix + tile_local] = min(excl, limit);
+      else if (sm.td.mode == kModeRle)
+        reinterpret_cast<uint16_t*>(my_slot + sm.td.off_prefix)[tile_local] =
+            (uint16_t)(excl >= limit ? 0u : min(total, limit - excl));
       if (last_tile) {
         const uint32_t incl = excl + total;
         dyn->n_sel = min(incl, limit);
@@ -1363,6 +1398,39 @@ DR_D void phase_decode(const EngineParams& P, Smem& sm) {
         }
       }
       tile = seg_end;
+    } else if (sm.td.mode == kModeRle) {
+      // running entry prefix of every sender at my first tile of this tensor = sum of the earlier tiles' counts
+      __syncthreads();
+      if (threadIdx.x < 16) sm.s.rle_pre[threadIdx.x] = 0u;
+      __syncthreads();
+      const uint32_t first_local = tile - sm.td.tile_begin;
+      for (int r = 0; r < P.world; ++r) {
+        const uint16_t* cnt = reinterpret_cast<const uint16_t*>(slot_ptr(arena, P, parity, r) + sm.td.off_prefix);
+        uint32_t part = 0;
+        for (uint32_t j = threadIdx.x; j < first_local; j += kThreads) part += __ldcg(cnt + j);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
+        if ((threadIdx.x & 31u) == 0 && part) atomicAdd(&sm.s.rle_pre[r], part);
+      }
+      for (; tile < seg_end; ++tile) {
+        const Tile ti = load_tile(P, tile);
+        __syncthreads();
+        for (int j = threadIdx.x; j < kTile; j += kThreads) sm.u.acc[j] = 0.0f;
+        __syncthreads();
+        for (int r = 0; r < P.world; ++r) {
+          const uint32_t* slot = slot_ptr(arena, P, parity, r);
+          const uint32_t c = __ldcg(reinterpret_cast<const uint16_t*>(slot + sm.td.off_prefix) + (tile - sm.td.tile_begin));
+          const uint32_t pre = sm.s.rle_pre[r];
+          const float* vals = reinterpret_cast<const float*>(slot + sm.td.off_vals);
+          for (uint32_t j = threadIdx.x; j < c; j += kThreads) {
+            const uint32_t rp = pre + j;
+            if (rp < sm.td.val_cap) sm.u.acc[rle_get(slot + sm.td.off_idx, rp)] += __ldcg(vals + rp) * P.scale;   // distinct positions per sender
+          }
+          __syncthreads();                                  // senders are added in rank order: deterministic sums
+          if (threadIdx.x == 0) sm.s.rle_pre[r] = pre + c;
+        }
+        for (uint32_t e = threadIdx.x; e < ti.n; e += kThreads) P.grad[ti.base + e] = sm.u.acc[e];
+      }
     } else {
       for (; tile < seg_end; ++tile) {
         const Tile ti = load_tile(P, tile);
@@ -1501,7 +1569,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) dr_engine_kernel(const _
     switch (ph) {
       case kPhAccum: if (P.use_tma) phase_accum_tma(P, sm); else phase_accum(P, sm); break;
       case kPhFallback: if (P.use_history) hist_tiles<1>(P, sm); else ran = false; break;
-      case kPhHist2: if (P.use_tma) phase_hist2_tma(P, sm); else hist_tiles<2>(P, sm); break;
+      case kPhHist2:
+        if (P.has_rle) rle_zero_streams(P);
+        if (P.use_tma) phase_hist2_tma(P, sm); else hist_tiles<2>(P, sm);
+        break;
       case kPhInsert: if (P.use_tma) phase_insert_tma(P, sm); else phase_insert(P, sm); break;
       case kPhQuery: phase_query(P, sm); break;
       case kPhEmit: phase_emit(P, sm); break;

@@ -13,6 +13,8 @@ constexpr uint32_t kDefaultSeed = 0x9747B28Cu;
 enum TensorMode : uint32_t {
   kModeRaw = 0,     // plain (value, index) pairs — small-tensor bypass / plain top-k
   kModeBloom = 1,   // bloom-filter index codec, fp32 values
+  kModeRle = 2,     // lossless tile-local run coding: u16 count per 4096-element tile (off_prefix) + the cumulative
+                    // zero-run offset of every selected element inside its tile, 12 bits each, LSB-first (off_idx)
 };
 
 enum Policy : int { kPolicyLeftmost = 0, kPolicyRandom = 1, kPolicyP0 = 2 };
@@ -161,6 +163,7 @@ struct EngineParams {
   uint32_t* bucket_pos;          // [sum K] original position p of the grouped values
   float* expand_buf;             // [world][sum K] fitted curves of every rank
   uint32_t poly_total;           // sum K over the vmode==1 tensors
+  int has_rle;                   // some tensor uses kModeRle (its bit stream is OR-ed, so it is zeroed every step)
   int shard;                     // 1: sharded decode + stage-2 exchange (when world > 1)
   uint32_t s2_words;             // words per stage-2 slot: [count, epoch, 0, 0][idx x cap][val x cap]
   uint32_t s2_cap;               // entries per stage-2 slot

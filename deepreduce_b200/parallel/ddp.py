@@ -49,6 +49,8 @@ def _fused_supported(params: dict) -> bool:
     pol_ok = canonical_policy(params.get('policy', 'leftmost')) in ('leftmost', 'p0')
     if dr == 'index' and params.get('index', 'bloom') == 'bloom':
         return pol_ok
+    if dr == 'index' and params.get('index') == 'rle':
+        return True                      # lossless tile-local run coding inside the fused kernel
     if dr == 'both' and params.get('index', 'bloom') == 'bloom' and (
             params.get('value', 'polyfit') == 'polyfit'
             or (params.get('value') == 'qsgd' and int(params.get('quantum_num', 127)) < 128
@@ -111,7 +113,8 @@ class DeepReduceDDP:
             shapes = [tuple(p.shape) for _, p in items]
             if self.fused:
                 plan = BucketPlan(numels, names, shapes, compress_ratio=self.params.get('compress_ratio', 0.01),
-                                  index='bloom' if self.params.get('deepreduce') in ('index', 'both') else None,
+                                  index=(self.params.get('index', 'bloom') if self.params.get('deepreduce') in ('index', 'both')
+                                         else None),
                                   value=self.params.get('value', 'polyfit') if self.params.get('deepreduce') == 'both' else None,
                                   quantum_num=int(self.params.get('quantum_num', 127)),
                                   poly_degree=int(self.params.get('poly_degree', 5)),

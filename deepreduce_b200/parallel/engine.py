@@ -23,8 +23,8 @@ import torch.distributed as dist
 
 from .. import spec
 from ..codecs.bloom import bloom_insert_oracle, bloom_query_oracle
-from .plan import (ARENA_HDR_WORDS, DYN_WORDS, HIST_BINS, MODE_BLOOM, MODE_RAW, NUM_HIST, POLICY_ID,
-                   SLOT_HEADER_WORDS, BucketPlan)
+from .plan import (ARENA_HDR_WORDS, DYN_WORDS, HIST_BINS, MODE_BLOOM, MODE_RAW, MODE_RLE, NUM_HIST, POLICY_ID,
+                   SLOT_HEADER_WORDS, BucketPlan, rle_stream_words)
 
 (PH_ACCUM, PH_FALLBACK, PH_HIST2, PH_INSERT, PH_QUERY, PH_EMIT, PH_RANK_HIST, PH_RANK_SCAN, PH_RANK_SCATTER,
  PH_RANK_EXACT, PH_FIT, PH_FIX, PH_PUSH, PH_SIGNAL, PH_EXPAND, PH_DECODE, PH_COMPACT, PH_PUSH2, PH_SIGNAL2,
@@ -37,6 +37,27 @@ STATUS_NAMES = {0: "ok", 1: "(unused)", 2: "peer flag watchdog", 3: "select reso
 # ---------------------------------------------------------------------------
 # oracle
 # ---------------------------------------------------------------------------
+def rle_pack12(pos: np.ndarray, cap: int) -> np.ndarray:
+    """12-bit fields, LSB-first, entry j at bit 12*j (the kModeRle index stream)."""
+    out = np.zeros(rle_stream_words(cap), dtype=np.uint64)
+    j = np.arange(pos.size, dtype=np.int64)
+    bit = 12 * j
+    w, sh = bit >> 5, (bit & 31).astype(np.uint64)
+    v = pos.astype(np.uint64) << sh                       # up to 43 bits
+    np.bitwise_or.at(out, w, v & np.uint64(0xFFFFFFFF))
+    np.bitwise_or.at(out, w + 1, v >> np.uint64(32))
+    return out.astype(np.uint32)
+
+
+def rle_unpack12(stream: np.ndarray, n: int) -> np.ndarray:
+    j = np.arange(n, dtype=np.int64)
+    bit = 12 * j
+    w, sh = bit >> 5, (bit & 31).astype(np.uint64)
+    s64 = stream.astype(np.uint64)
+    both = s64[w] | (s64[np.minimum(w + 1, s64.size - 1)] << np.uint64(32))
+    return ((both >> sh) & np.uint64(0xFFF)).astype(np.int64)
+
+
 def _abs_keys(x: torch.Tensor) -> torch.Tensor:
     return x.contiguous().view(torch.int32).to(torch.int64) & 0x7FFFFFFF
 
@@ -81,6 +102,16 @@ def encode_tensor_oracle(tp, acc: torch.Tensor, slot: np.ndarray, t_index: int, 
         starts = torch.arange(tp.n_tiles, dtype=torch.int64) * spec.TILE
         slot[tp.off_prefix:tp.off_prefix + tp.n_tiles] = torch.searchsorted(sel.cpu(), starts).numpy().astype(np.uint32)
         cutoff = int(sel[-1].item()) if n_pos >= limit and limit > 0 else 0xFFFFFFFF
+    elif tp.mode == MODE_RLE:
+        n_pos = int(sel_topk.numel())
+        limit = tp.val_cap
+        sel = sel_topk[:limit]
+        s_np = sel.cpu().numpy().astype(np.int64)
+        cnt = np.zeros(((tp.n_tiles + 1) // 2) * 2, dtype=np.uint16)
+        cnt[:tp.n_tiles] = np.bincount(s_np // spec.TILE, minlength=tp.n_tiles).astype(np.uint16)
+        slot[tp.off_prefix:tp.off_prefix + (tp.n_tiles + 1) // 2] = cnt.view(np.uint32)
+        slot[tp.off_idx:tp.off_idx + rle_stream_words(tp.val_cap)] = rle_pack12(s_np % spec.TILE, tp.val_cap)
+        cutoff = int(sel[-1].item()) if n_pos >= limit else 0xFFFFFFFF
     else:
         n_pos = int(sel_topk.numel())
         limit = tp.val_cap
@@ -212,6 +243,7 @@ class BucketEngine:
             if self.shard and self.world > 1:
                 cap, s2w = plan.stage2_layout(self.world)
                 self.ctx.set_shard(1, s2w, cap)
+            self.ctx.set_has_rle(int(any(t.mode == MODE_RLE for t in plan.tensors)))
             ids, n_poly, tasks, n_tasks = plan.poly_tables()
             self.poly_ids, self.poly_tasks = ids.to(dev), tasks.to(dev)
             from .plan import RANK_BINS

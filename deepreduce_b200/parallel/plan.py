@@ -18,7 +18,7 @@ import torch
 
 from .. import spec
 
-MODE_RAW, MODE_BLOOM = 0, 1
+MODE_RAW, MODE_BLOOM, MODE_RLE = 0, 1, 2
 POLICY_ID = {"leftmost": 0, "random": 1, "p0": 2}
 SLOT_HEADER_WORDS = 8
 DYN_WORDS = 4
@@ -30,6 +30,10 @@ MAX_SEGMENTS = 22
 MAX_POLY_K = 1 << 17      # the all-pairs rank pass is O(K^2): larger tensors keep fp32 values
 DESC_WORDS = 32
 RANK_BINS = 8192
+
+
+def rle_stream_words(k: int) -> int:
+    return (k * 12 + 31) // 32 + 1
 
 
 def _align(x: int, a: int) -> int:
@@ -80,7 +84,7 @@ class BucketPlan:
     names: Optional[Sequence[str]] = None
     shapes: Optional[Sequence[tuple]] = None
     compress_ratio: float = 0.01
-    index: Optional[str] = "bloom"        # 'bloom' or None (plain top-k pairs)
+    index: Optional[str] = "bloom"        # 'bloom', 'rle' (lossless tile-local run coding) or None (plain top-k pairs)
     fpr: Optional[float] = None
     policy: str = "leftmost"
     min_numel: int = spec.SMALL_TENSOR_NUMEL
@@ -94,6 +98,10 @@ class BucketPlan:
     tensors: List[TensorPlan] = field(default_factory=list, init=False)
 
     def __post_init__(self):
+        if self.index not in (None, "bloom", "rle"):
+            raise ValueError(f"fused engine index codecs: None, 'bloom', 'rle'; got {self.index!r}")
+        if self.index == "rle" and self.value is not None:
+            raise NotImplementedError("value codecs are fused with the bloom index only")
         if self.policy not in POLICY_ID:
             raise ValueError(f"fused engine supports policies {list(POLICY_ID)}; got {self.policy!r}")
         if self.policy == "random":
@@ -148,6 +156,17 @@ class BucketPlan:
                 if self.hint:
                     tp.off_hint = word
                     word = _align(word + 4 * n_tiles, 4)
+            elif self.index == "rle" and d > self.min_numel:
+                # lossless run coding of the selection bitmap, tile-local: a u16 count per tile and, per selected
+                # element, the zeros+ones run offset from the tile start (< 4096 -> 12 bits), bit-packed
+                tp.mode = MODE_RLE
+                tp.val_cap = k
+                tp.off_vals = word
+                word = _align(word + k, 4)
+                tp.off_prefix = word
+                word = _align(word + (n_tiles + 1) // 2, 4)
+                tp.off_idx = word
+                word = _align(word + rle_stream_words(k), 4)
             else:
                 tp.val_cap = k
                 tp.off_vals = word

@@ -18,6 +18,7 @@ def main():
     ok = True
     for index, policy, value, shard in (("bloom", "leftmost", None, True), ("bloom", "leftmost", None, False),
                                         ("bloom", "p0", None, True), (None, "leftmost", None, True),
+                                        ("rle", "leftmost", None, True), ("rle", "leftmost", None, False),
                                         ("bloom", "leftmost", "polyfit", True), ("bloom", "leftmost", "polyfit", False),
                                         ("bloom", "leftmost", "qsgd", True)):
         plan = BucketPlan(sizes, compress_ratio=0.01, index=index, policy=policy, value=value)

@@ -155,3 +155,31 @@ def test_oracle_both_qsgd():
     assert torch.equal(out != 0, out_p != 0) or (out != 0).sum() >= 0.98 * (out_p != 0).sum()   # level 0 can zero a value
     assert (out - out_p).norm() / out_p.norm() < 0.12
     assert torch.allclose(out + res[0], g, atol=1e-6)
+
+
+def test_oracle_rle_index_is_lossless_and_smaller_than_pairs():
+    """Fused 'rle' index mode (kModeRle): same selection / output / residual as plain top-k pairs, smaller wire,
+    and the bit stream decodes back to the selected indices (tile count + 12-bit in-tile offsets)."""
+    from deepreduce_b200.parallel import BucketPlan, engine_oracle
+    from deepreduce_b200.parallel.engine import rle_unpack12
+    from deepreduce_b200.parallel.plan import DYN_WORDS, MODE_RLE, SLOT_HEADER_WORDS
+    sizes = [64, 5000, 20000, 100000]
+    rle = BucketPlan(sizes, compress_ratio=0.01, index="rle")
+    raw = BucketPlan(sizes, compress_ratio=0.01, index=None)
+    assert rle.tensors[0].mode != MODE_RLE and all(t.mode == MODE_RLE for t in rle.tensors[1:])
+    assert rle.wire_bytes() < 0.75 * raw.wire_bytes()
+    gen = torch.Generator().manual_seed(5)
+    g = [torch.randn(rle.total_elems, generator=gen) for _ in range(3)]
+    r = [torch.zeros(rle.total_elems) for _ in range(3)]
+    o1, r1, s1 = engine_oracle(rle, g, r)
+    o2, r2, s2 = engine_oracle(raw, g, r)
+    assert torch.equal(o1, o2) and all(torch.equal(a, b) for a, b in zip(r1, r2))
+    for ti, (ta, tb) in enumerate(zip(rle.tensors, raw.tensors)):
+        if ta.mode != MODE_RLE:
+            continue
+        n = int(s1[0][SLOT_HEADER_WORDS + DYN_WORDS * ti])
+        cnt = s1[0][ta.off_prefix:ta.off_prefix + (ta.n_tiles + 1) // 2].view(np.uint16)[:ta.n_tiles].astype(np.int64)
+        assert cnt.sum() == n
+        tile_of = np.repeat(np.arange(ta.n_tiles), cnt)
+        idx = tile_of * 4096 + rle_unpack12(s1[0][ta.off_idx:], n)
+        assert np.array_equal(idx, s2[0][tb.off_idx:tb.off_idx + n].astype(np.int64))

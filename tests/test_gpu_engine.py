@@ -40,7 +40,7 @@ def _compare_slot(plan, slot_gpu, slot_ref, tag):
     bad = []
     a = slot_gpu.cpu().numpy().view(np.uint32)
     b = slot_ref
-    from deepreduce_b200.parallel.plan import SLOT_HEADER_WORDS, DYN_WORDS, MODE_BLOOM
+    from deepreduce_b200.parallel.plan import SLOT_HEADER_WORDS, DYN_WORDS, MODE_BLOOM, MODE_RLE, rle_stream_words
     if not np.array_equal(a[:5], b[:5]):
         bad.append(f"header {a[:5]} vs {b[:5]}")
     for ti, t in enumerate(plan.tensors):
@@ -59,6 +59,14 @@ def _compare_slot(plan, slot_gpu, slot_ref, tag):
                 ha, hb = a[t.off_hint:t.off_hint + 4 * t.n_tiles], b[t.off_hint:t.off_hint + 4 * t.n_tiles]
                 if not np.array_equal(ha, hb):
                     bad.append(f"{t.name} hint differs in {int((ha != hb).sum())}/{4 * t.n_tiles} words")
+        elif t.mode == MODE_RLE:
+            nc = (t.n_tiles + 1) // 2
+            if not np.array_equal(a[t.off_prefix:t.off_prefix + nc], b[t.off_prefix:t.off_prefix + nc]):
+                bad.append(f"{t.name} rle tile counts differ gpu={a[t.off_prefix:t.off_prefix+4].tolist()} ref={b[t.off_prefix:t.off_prefix+4].tolist()}")
+            nw = rle_stream_words(t.val_cap)
+            sa, sb = a[t.off_idx:t.off_idx + nw], b[t.off_idx:t.off_idx + nw]
+            if not np.array_equal(sa, sb):
+                bad.append(f"{t.name} rle stream differs in {int((sa != sb).sum())}/{nw} words")
         else:
             ia, ib = a[t.off_idx:t.off_idx + n_sel], b[t.off_idx:t.off_idx + n_sel]
             if not np.array_equal(ia, ib):
@@ -99,7 +107,8 @@ SIZES = [64, 1000, 1001, 4096, 4097, 36864, 147456, 10, 589824]
 @pytest.mark.parametrize("kind", ["randn", "sparse", "ties"])
 @pytest.mark.parametrize("index,policy,hint,tma,value", [
     ("bloom", "leftmost", True, True, None), ("bloom", "leftmost", False, False, None), ("bloom", "p0", True, True, None),
-    (None, "leftmost", True, True, None), ("bloom", "leftmost", True, True, "polyfit"),
+    (None, "leftmost", True, True, None), ("rle", "leftmost", True, True, None),
+    ("bloom", "leftmost", True, True, "polyfit"),
     ("bloom", "leftmost", True, True, "qsgd")])
 def test_engine_vs_oracle_single_rank(kind, index, policy, hint, tma, value):
     from deepreduce_b200.parallel import BucketEngine, BucketPlan, engine_oracle
