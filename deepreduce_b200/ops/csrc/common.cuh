@@ -134,6 +134,13 @@ DR_D void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t* status = nullptr) 
   } while (!ok);
 }
 
+// NVLS: a store to a multicast address is replicated by the NVSwitch into every bound GPU's memory
+DR_D void multimem_st_v4(uint4* mc_addr, uint4 v) {
+  asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(mc_addr), "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)),
+                  "f"(__uint_as_float(v.w)) : "memory");
+}
+
 // Grid-wide barrier for a co-resident (cooperative-launch) grid.  `counter`
 // is zeroed by the host before launch; `*epoch` is a per-thread-0 register
 // copy counting barriers passed.

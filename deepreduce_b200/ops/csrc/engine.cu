@@ -1246,6 +1246,12 @@ DR_D void phase_push(const EngineParams& P) {
   const uint32_t parity = P.epoch & 1u;
   const uint4* src = reinterpret_cast<const uint4*>(slot_ptr(P.arena[P.rank], P, parity, P.rank));
   const uint32_t n4 = (P.payload_words + 3u) >> 2;
+  if (P.mc_arena) {                                      // NVLS: one multimem store lands in every GPU's arena (the switch replicates)
+    uint4* dst = reinterpret_cast<uint4*>(slot_ptr(P.mc_arena, P, parity, P.rank));
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n4; i += gridDim.x * kThreads) multimem_st_v4(dst + i, __ldcg(src + i));
+    __threadfence_system();
+    return;
+  }
   for (int h = 1; h < P.world; ++h) {
     const int peer = (P.rank + h) % P.world;             // stagger so peers are not hit in lock-step
     uint4* dst = reinterpret_cast<uint4*>(slot_ptr(P.arena[peer], P, parity, P.rank));
@@ -1508,6 +1514,19 @@ DR_D void phase_push2(const EngineParams& P) {
   const uint32_t parity = P.epoch & 1u;
   const uint32_t* src = s2_ptr(P.arena[P.rank], P, parity, P.rank);
   const uint32_t n = min(__ldcg(src), P.s2_cap);
+  if (P.mc_arena) {
+    uint32_t* dst = s2_ptr(P.mc_arena, P, parity, P.rank);
+    const uint32_t gtid = blockIdx.x * kThreads + threadIdx.x, gsz = gridDim.x * kThreads;
+    if (gtid == 0) multimem_st_v4(reinterpret_cast<uint4*>(dst), make_uint4(n, P.epoch, 0u, 0u));
+    const uint4* si = reinterpret_cast<const uint4*>(src + 4);
+    const uint4* sv = reinterpret_cast<const uint4*>(src + 4 + P.s2_cap);
+    uint4* di = reinterpret_cast<uint4*>(dst + 4);
+    uint4* dv = reinterpret_cast<uint4*>(dst + 4 + P.s2_cap);
+    const uint32_t n4 = (n + 3u) >> 2;
+    for (uint32_t i = gtid; i < n4; i += gsz) { multimem_st_v4(di + i, __ldcg(si + i)); multimem_st_v4(dv + i, __ldcg(sv + i)); }
+    __threadfence_system();
+    return;
+  }
   for (int h = 1; h < P.world; ++h) {
     const int peer = (P.rank + h) % P.world;
     uint32_t* dst = s2_ptr(P.arena[peer], P, parity, P.rank);

@@ -163,6 +163,7 @@ struct EngineParams {
   uint32_t* bucket_pos;          // [sum K] original position p of the grouped values
   float* expand_buf;             // [world][sum K] fitted curves of every rank
   uint32_t poly_total;           // sum K over the vmode==1 tensors
+  uint32_t* mc_arena;            // NVLS multicast mapping of the symmetric arena (nullptr: per-peer P2P stores)
   int has_rle;                   // some tensor uses kModeRle (its bit stream is OR-ed, so it is zeroed every step)
   int shard;                     // 1: sharded decode + stage-2 exchange (when world > 1)
   uint32_t s2_words;             // words per stage-2 slot: [count, epoch, 0, 0][idx x cap][val x cap]

@@ -243,6 +243,8 @@ class BucketEngine:
             if self.shard and self.world > 1:
                 cap, s2w = plan.stage2_layout(self.world)
                 self.ctx.set_shard(1, s2w, cap)
+            if getattr(self, "multicast_ptr", 0):
+                self.ctx.set_multicast(self.multicast_ptr)
             self.ctx.set_has_rle(int(any(t.mode == MODE_RLE for t in plan.tensors)))
             ids, n_poly, tasks, n_tasks = plan.poly_tables()
             self.poly_ids, self.poly_tasks = ids.to(dev), tasks.to(dev)
@@ -267,6 +269,9 @@ class BucketEngine:
             self.arena = torch.zeros(words, dtype=torch.int32, device=self.device)
             self.arena_ptrs = [self.arena.data_ptr()]
             return
+        self.multicast_ptr = 0
+        if os.environ.get("DR_NVLS", "0") == "1" and self._setup_arena_nvls(words):
+            return
         self.mod.enable_peer_access(torch.cuda.device_count())
         self._arena_ptr = self.mod.arena_alloc(words * 4)
         self.arena = self.mod.arena_as_tensor(self._arena_ptr, words, self.device.index or 0)
@@ -283,6 +288,36 @@ class BucketEngine:
                 self._imported.append(p)
                 self.arena_ptrs.append(p)
         dist.barrier(group=self.group)
+
+    def _setup_arena_nvls(self, words: int) -> bool:
+        """Arena in NVLS-capable symmetric memory (cuMem + multicast object, torch's symmetric-memory rendezvous does the
+        handle exchange): peers' arenas are mapped like the IPC path and a multicast VA lets ONE store reach all of
+        them through the NVSwitch.  Every rank must agree, so the outcome is all-reduced; False -> IPC path."""
+        ok, hdl, t = 1, None, None
+        try:
+            import torch.distributed._symmetric_memory as symm
+            t = symm.empty(words, dtype=torch.int32, device=self.device)
+            grp = self.group if self.group is not None else dist.group.WORLD
+            hdl = symm.rendezvous(t, group=grp)
+            if int(hdl.multicast_ptr) == 0 or hdl.world_size != self.world:
+                ok = 0
+        except Exception as e:  # noqa: BLE001
+            self._nvls_error = repr(e)
+            ok = 0
+        flag = torch.tensor([ok], device=self.device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            return False
+        t.zero_()
+        torch.cuda.synchronize(self.device)
+        self._symm_tensor, self._symm_handle = t, hdl
+        self.arena = t
+        self.arena_ptrs = [int(p) for p in hdl.buffer_ptrs]
+        self.multicast_ptr = int(hdl.multicast_ptr)
+        self._ipc = False
+        self._imported = []
+        dist.barrier(group=self.group)
+        return True
 
     def close(self):
         if getattr(self, "_ipc", False):

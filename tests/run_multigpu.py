@@ -23,6 +23,9 @@ def main():
                                         ("bloom", "leftmost", "qsgd", True)):
         plan = BucketPlan(sizes, compress_ratio=0.01, index=index, policy=policy, value=value)
         eng = BucketEngine(plan, device=f"cuda:{local}", spin_limit=4_000_000, shard=shard)
+        if rank == 0:
+            print(f"engine index={index} value={value} shard={shard} nvls={bool(getattr(eng, 'multicast_ptr', 0))} "
+                  f"{getattr(eng, '_nvls_error', '')}", flush=True)
         resid_refs = [torch.zeros(plan.total_elems) for _ in range(world)]
         for step in range(3):
             grads = []
