@@ -123,7 +123,6 @@ def init_dist(args):
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
-    os.environ.setdefault("NCCL_DEBUG", "WARN")       # keep stdout to the single JSON line
     need = world > 1 or args.impl == "reference"
     if need:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -382,9 +381,14 @@ def run_reference(args, rank, world, local):
 
 def main():
     args = parse()
+    # stdout carries exactly ONE line (the JSON): keep a private handle to it and point fd 1 at stderr so that
+    # library banners (e.g. "NCCL version ...") and stray prints cannot end up next to the result
+    sys.stdout.flush()
+    result_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     if not torch.cuda.is_available():
-        print(json.dumps({"impl": args.impl, "unavailable": "no CUDA device on this box"}))
+        print(json.dumps({"impl": args.impl, "unavailable": "no CUDA device on this box"}), file=result_out, flush=True)
         return 0
     rank, world, local = init_dist(args)
     if world != args.gpus and rank == 0:
@@ -394,7 +398,7 @@ def main():
     finally:
         pass
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        print(json.dumps(out), file=result_out, flush=True)
     import torch.distributed as dist
     if dist.is_initialized():
         dist.destroy_process_group()

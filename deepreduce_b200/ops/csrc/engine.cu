@@ -885,6 +885,9 @@ DR_D void phase_query(const EngineParams& P, Smem& sm) {
 // ===========================================================================
 // phase 5: ordered compaction + value gather + residual update
 // ===========================================================================
+// kFull = false compiles the value-codec / run-length branches out of the two hot loops (emit, decode): the
+// index-only kernel (plain pairs, bloom) keeps its registers for the probe loop instead of spilling
+template <bool kFull>
 DR_D void phase_emit(const EngineParams& P, Smem& sm) {
   const uint32_t parity = P.epoch & 1u;
   uint32_t* my_slot = slot_ptr(P.arena[P.rank], P, parity, P.rank);
@@ -935,8 +938,8 @@ DR_D void phase_emit(const EngineParams& P, Smem& sm) {
             vals[rp] = P.resid[base + e];
             P.resid[base + e] = 0.0f;                      // residual is exactly 0 on the shipped set
             if (sm.td.mode == kModeRaw) idxs[rp] = local0 + e;
-            else if (sm.td.mode == kModeRle) rle_put(idxs, rp, e);
-            if (sm.td.vmode) my_slot[sm.td.off_selidx + rp] = (uint32_t)(base + e);
+            else if (kFull && sm.td.mode == kModeRle) rle_put(idxs, rp, e);
+            if (kFull && sm.td.vmode) my_slot[sm.td.off_selidx + rp] = (uint32_t)(base + e);
             if (rp == limit - 1u) dyn->cutoff = local0 + e;
           }
         }
@@ -944,7 +947,7 @@ DR_D void phase_emit(const EngineParams& P, Smem& sm) {
     }
     if (threadIdx.x == 0) {
       if (sm.td.mode == kModeBloom) my_slot[sm.td.off_prefix + tile_local] = min(excl, limit);
-      else if (sm.td.mode == kModeRle)
+      else if (kFull && sm.td.mode == kModeRle)
         reinterpret_cast<uint16_t*>(my_slot + sm.td.off_prefix)[tile_local] =
             (uint16_t)(excl >= limit ? 0u : min(total, limit - excl));
       if (last_tile) {
@@ -1312,6 +1315,7 @@ DR_D uint32_t lower_bound_u32(const uint32_t* a, uint32_t n, uint32_t x) {
   return lo;
 }
 
+template <bool kFull>
 DR_D void phase_decode(const EngineParams& P, Smem& sm) {
   const uint32_t parity = P.epoch & 1u;
   uint32_t* arena = P.arena[P.rank];
@@ -1392,8 +1396,8 @@ DR_D void phase_decode(const EngineParams& P, Smem& sm) {
               if (rp < n_sel) {
                 float* o = P.grad + ti.base + c * kThreads + threadIdx.x;   // the same thread owns this element for every rank
                 float val;
-                if (sm.td.vmode == 1) val = __ldcg(fitted + load_rank(slot, sm.td, rp));
-                else if (sm.td.vmode == 2)
+                if (kFull && sm.td.vmode == 1) val = __ldcg(fitted + load_rank(slot, sm.td, rp));
+                else if (kFull && sm.td.vmode == 2)
                   val = __ldcg(reinterpret_cast<const float*>(slot + sm.td.off_coef) + (rp >> 9)) / (float)sm.td.poly_degree *
                         (float)__ldcg(reinterpret_cast<const int8_t*>(slot + sm.td.off_rankmap) + rp);
                 else val = __ldcg(vals + rp);
@@ -1404,7 +1408,7 @@ DR_D void phase_decode(const EngineParams& P, Smem& sm) {
         }
       }
       tile = seg_end;
-    } else if (sm.td.mode == kModeRle) {
+    } else if (kFull && sm.td.mode == kModeRle) {
       // running entry prefix of every sender at my first tile of this tensor = sum of the earlier tiles' counts
       __syncthreads();
       if (threadIdx.x < 16) sm.s.rle_pre[threadIdx.x] = 0u;
@@ -1574,7 +1578,7 @@ DR_D void phase_scatter(const EngineParams& P) {
   }
 }
 
-template <int kMinBlocks>
+template <int kMinBlocks, bool kFull>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) dr_engine_kernel(const __grid_constant__ EngineParams P) {
   __shared__ Smem sm;
   if (threadIdx.x == 0) {
@@ -1589,22 +1593,22 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) dr_engine_kernel(const _
       case kPhAccum: if (P.use_tma) phase_accum_tma(P, sm); else phase_accum(P, sm); break;
       case kPhFallback: if (P.use_history) hist_tiles<1>(P, sm); else ran = false; break;
       case kPhHist2:
-        if (P.has_rle) rle_zero_streams(P);
+        if (kFull && P.has_rle) rle_zero_streams(P);
         if (P.use_tma) phase_hist2_tma(P, sm); else hist_tiles<2>(P, sm);
         break;
       case kPhInsert: if (P.use_tma) phase_insert_tma(P, sm); else phase_insert(P, sm); break;
       case kPhQuery: phase_query(P, sm); break;
-      case kPhEmit: phase_emit(P, sm); break;
-      case kPhRankHist: if (P.n_poly) phase_rank_hist(P, sm); else ran = false; break;
-      case kPhRankScan: if (P.n_poly) phase_rank_scan(P, sm); else ran = false; break;
-      case kPhRankScatter: if (P.n_poly) phase_rank_scatter(P, sm); else ran = false; break;
-      case kPhRankExact: if (P.n_poly) phase_rank_exact(P, sm); else ran = false; break;
-      case kPhFit: if (P.n_poly) phase_fit(P, sm); else ran = false; break;
-      case kPhFix: if (P.n_poly_tasks) phase_fix(P, sm); else ran = false; break;
-      case kPhExpand: if (P.n_poly) phase_expand(P, sm); else ran = false; break;
+      case kPhEmit: phase_emit<kFull>(P, sm); break;
+      case kPhRankHist: if constexpr (kFull) { if (P.n_poly) phase_rank_hist(P, sm); else ran = false; } else ran = false; break;
+      case kPhRankScan: if constexpr (kFull) { if (P.n_poly) phase_rank_scan(P, sm); else ran = false; } else ran = false; break;
+      case kPhRankScatter: if constexpr (kFull) { if (P.n_poly) phase_rank_scatter(P, sm); else ran = false; } else ran = false; break;
+      case kPhRankExact: if constexpr (kFull) { if (P.n_poly) phase_rank_exact(P, sm); else ran = false; } else ran = false; break;
+      case kPhFit: if constexpr (kFull) { if (P.n_poly) phase_fit(P, sm); else ran = false; } else ran = false; break;
+      case kPhFix: if constexpr (kFull) { if (P.n_poly_tasks) phase_fix(P, sm); else ran = false; } else ran = false; break;
+      case kPhExpand: if constexpr (kFull) { if (P.n_poly) phase_expand(P, sm); else ran = false; } else ran = false; break;
       case kPhPush: if (P.world > 1) phase_push(P); else ran = false; break;
       case kPhSignal: if (P.world > 1) phase_signal(P); else ran = false; break;
-      case kPhDecode: phase_decode(P, sm); break;
+      case kPhDecode: phase_decode<kFull>(P, sm); break;
       case kPhCompact: if (sharded(P)) phase_compact(P, sm); else ran = false; break;
       case kPhPush2: if (sharded(P)) phase_push2(P); else ran = false; break;
       case kPhSignal2: if (sharded(P)) phase_signal2(P); else ran = false; break;
@@ -1625,14 +1629,18 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) dr_engine_kernel(const _
 // filter staging; <2> = 64 regs, two CTAs per SM, up to 88 KB each.
 static bool g_attr_set = false;
 
-static const void* kernel_for(int blocks_per_sm) {
-  return blocks_per_sm >= 2 ? (const void*)dr_engine_kernel<2> : (const void*)dr_engine_kernel<1>;
+// ... x two feature sets: <.., false> index-only (plain pairs / bloom), <.., true> + value codecs and run-length index
+static const void* kernel_for(int blocks_per_sm, bool full) {
+  if (blocks_per_sm >= 2) return full ? (const void*)dr_engine_kernel<2, true> : (const void*)dr_engine_kernel<2, false>;
+  return full ? (const void*)dr_engine_kernel<1, true> : (const void*)dr_engine_kernel<1, false>;
 }
 
 static void ensure_attr() {
   if (!g_attr_set) {
-    cudaFuncSetAttribute(dr_engine_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(dr_engine_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 88 * 1024);
+    cudaFuncSetAttribute(dr_engine_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(dr_engine_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(dr_engine_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 88 * 1024);
+    cudaFuncSetAttribute(dr_engine_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 88 * 1024);
     g_attr_set = true;
   }
 }
@@ -1642,7 +1650,10 @@ int engine_max_grid(int blocks_per_sm, int dyn_smem_bytes) {
   ensure_attr();
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel_for(blocks_per_sm), kThreads, (size_t)dyn_smem_bytes);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel_for(blocks_per_sm, true), kThreads, (size_t)dyn_smem_bytes);
+  int occ_plain = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_plain, kernel_for(blocks_per_sm, false), kThreads, (size_t)dyn_smem_bytes);
+  if (occ_plain < occ) occ = occ_plain;
   if (occ < 1) occ = 1;
   if (blocks_per_sm > 0 && blocks_per_sm < occ) occ = blocks_per_sm;
   return occ * sms;
@@ -1654,7 +1665,8 @@ cudaError_t engine_launch(const EngineParams& P, int grid, int blocks_per_sm, in
   if (e != cudaSuccess) return e;
   void* args[] = {const_cast<EngineParams*>(&P)};
   count_launch(1);
-  return cudaLaunchCooperativeKernel(kernel_for(blocks_per_sm), dim3(grid), dim3(kThreads), args,
+  const bool full = P.n_poly != 0 || P.n_poly_tasks != 0 || P.has_rle != 0;
+  return cudaLaunchCooperativeKernel(kernel_for(blocks_per_sm, full), dim3(grid), dim3(kThreads), args,
                                      (size_t)dyn_smem_bytes, stream);
 }
 

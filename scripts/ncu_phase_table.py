@@ -4,7 +4,10 @@ import subprocess
 import sys
 
 rep = sys.argv[1]
-names = ['accum', 'fallback', 'hist2', 'insert', 'query', 'emit', 'push', 'signal', 'decode']
+names = ['accum', 'fallback', 'hist2', 'insert', 'query', 'emit', 'rank_hist', 'rank_scan', 'rank_scatter', 'rank_exact', 'fit', 'fix',
+         'push', 'signal', 'expand', 'decode', 'compact', 'push2', 'signal2', 'scatter']
+if len(sys.argv) > 2:          # older captures: explicit comma-separated launch names
+    names = sys.argv[2].split(',')
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr = rows[0]
