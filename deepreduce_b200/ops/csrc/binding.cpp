@@ -245,7 +245,7 @@ struct Engine {
     P.spin_limit = 20u * 1000u * 1000u;
     P.filter_smem_words = (uint32_t)(dyn_smem / 4);
     P.use_tma = 1; P.hist_shift = 23;
-    P.shard = 0; P.s2_words = 0; P.s2_cap = 0; P.has_rle = 0; P.mc_arena = nullptr;
+    P.shard = 0; P.s2_words = 0; P.s2_cap = 0; P.has_rle = 0; P.mc_arena = nullptr; P.own_flags = 0; P.warp_count = nullptr;
     cudaGetDevice(&device);
   }
 
@@ -268,6 +268,9 @@ struct Engine {
   }
 
   void set_has_rle(int v) { P.has_rle = v; }
+  void set_opts(int own_flags, int64_t warp_count) {
+    P.own_flags = own_flags; P.warp_count = reinterpret_cast<uint8_t*>(warp_count);
+  }
   void set_multicast(int64_t p) { P.mc_arena = reinterpret_cast<uint32_t*>(p); }
 
   void set_shard(int shard, int64_t s2_words, int64_t s2_cap) {
@@ -451,6 +454,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("set_poly", &Engine::set_poly)
       .def("set_shard", &Engine::set_shard)
       .def("set_has_rle", &Engine::set_has_rle)
+      .def("set_opts", &Engine::set_opts)
       .def("set_multicast", &Engine::set_multicast)
       .def("grid", &Engine::get_grid)
       .def("run", &Engine::run);

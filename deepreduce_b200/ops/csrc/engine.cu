@@ -148,6 +148,34 @@ DR_D void tile_rank(uint32_t flags, ScanSmem& s, uint32_t& buf, uint32_t (&rank)
   buf ^= 1u;
 }
 
+// Same ranks from per-(slot, warp) counts that the query phase left in global memory (128 bytes per tile, index
+// c*16 + warp): no shared memory, no CTA barrier — warps drift through their tiles independently.
+DR_D void tile_rank_counts(uint32_t flags, const uint8_t* cnt, uint32_t (&rank)[kPerThread], uint32_t& total) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t w = __ldcg(reinterpret_cast<const uint32_t*>(cnt) + lane);       // counts 4l .. 4l+3
+  const uint32_t vx = w & 0xFFu, vy = (w >> 8) & 0xFFu, vz = (w >> 16) & 0xFFu, vw = w >> 24;
+  const uint32_t sum = vx + vy + vz + vw;
+  uint32_t incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= (uint32_t)o) incl += n;
+  }
+  const uint32_t base = incl - sum;
+  const uint32_t sub = warp & 3u;
+  const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int c = 0; c < kPerThread; ++c) {
+    const int src = 4 * c + (int)(warp >> 2);
+    const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, base, src);
+    const uint32_t sx = __shfl_sync(0xFFFFFFFFu, vx, src), sy = __shfl_sync(0xFFFFFFFFu, vy, src),
+                   sz = __shfl_sync(0xFFFFFFFFu, vz, src);
+    const uint32_t ball = __ballot_sync(0xFFFFFFFFu, (flags >> c) & 1u);
+    rank[c] = b0 + (sub > 0 ? sx : 0u) + (sub > 1 ? sy : 0u) + (sub > 2 ? sz : 0u) + __popc(ball & lt);
+  }
+  total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+}
+
 // ---------------------------------------------------------------------------
 // radix-select digit resolve: find the bin holding the k-th largest key.
 // Result in s.res: [0] bin (0xFFFFFFFF if total < k), [1] k remaining inside
@@ -875,6 +903,19 @@ DR_D void phase_query(const EngineParams& P, Smem& sm) {
     P.flag_buf[(size_t)tile * kThreads + threadIdx.x] = (uint8_t)flags;
     // per-tile count: one fire-and-forget RED per warp (tile_count is zeroed by the previous step's decode
     // phase) — no CTA barrier in this loop, so warps run ahead through their tiles independently
+    if (P.warp_count) {
+      const uint32_t lane = threadIdx.x & 31u;
+      uint32_t pc = 0, mine = 0;
+#pragma unroll
+      for (int c = 0; c < kPerThread; ++c) {
+        const uint32_t n = __popc(__ballot_sync(0xFFFFFFFFu, (flags >> c) & 1u));
+        pc += n;
+        if (lane == (uint32_t)c) mine = n;
+      }
+      if (lane < (uint32_t)kPerThread) P.warp_count[(size_t)tile * 128u + lane * kWarps + (threadIdx.x >> 5)] = (uint8_t)mine;
+      if (lane == 0 && pc) atomicAdd(P.tile_count + tile, pc);
+      continue;
+    }
     uint32_t pc = __popc(flags);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) pc += __shfl_xor_sync(0xFFFFFFFFu, pc, o);
@@ -923,7 +964,8 @@ DR_D void phase_emit(const EngineParams& P, Smem& sm) {
     const bool last_tile = (tile_local + 1 == sm.td.n_tiles);
     const uint32_t flags = P.flag_buf[(size_t)tile * kThreads + threadIdx.x];
     uint32_t rank[kPerThread], total;
-    tile_rank(flags, sm.s, rank_buf, rank, total);
+    if (P.warp_count) tile_rank_counts(flags, P.warp_count + (size_t)tile * 128u, rank, total);
+    else tile_rank(flags, sm.s, rank_buf, rank, total);
     const uint32_t limit = (sm.td.mode == kModeBloom && P.policy != kPolicyP0) ? min(sm.td.k, sm.td.val_cap)
                                                                                : sm.td.val_cap;
     float* vals = reinterpret_cast<float*>(my_slot + sm.td.off_vals);
@@ -1365,7 +1407,8 @@ DR_D void phase_decode(const EngineParams& P, Smem& sm) {
         const uint32_t* filter = slot + sm.td.off_filter;
         const float* vals = reinterpret_cast<const float*>(slot + sm.td.off_vals);
         const float* fitted = P.expand_buf + (size_t)r * P.poly_total + sm.td.poly_off;   // 'both': rank r's curve
-        if (fits) stage_filter(filter, sm.td.n_filter_words);
+        const bool own = P.own_flags && r == P.rank;               // my own positives are already in flag_buf (query phase)
+        if (fits && !own) stage_filter(filter, sm.td.n_filter_words);
         for (uint32_t tl = tile; tl < seg_end; ++tl) {
           const Tile ti = load_tile(P, tl);
           const uint32_t pre = __ldcg(slot + sm.td.off_prefix + (tl - sm.td.tile_begin));
@@ -1383,8 +1426,9 @@ DR_D void phase_decode(const EngineParams& P, Smem& sm) {
             valid &= valid_from_hint(h);
           }
           uint32_t flags;
-          if (fits) flags = bloom_test8(ti.local0 + threadIdx.x, valid, P.seed, n_hash, m_bits,
-                                        [&](uint32_t w) { return g_filter_smem[w]; });
+          if (own) flags = (uint32_t)P.flag_buf[(size_t)tl * kThreads + threadIdx.x] & valid;
+          else if (fits) flags = bloom_test8(ti.local0 + threadIdx.x, valid, P.seed, n_hash, m_bits,
+                                             [&](uint32_t w) { return g_filter_smem[w]; });
           else flags = bloom_test8(ti.local0 + threadIdx.x, valid, P.seed, n_hash, m_bits,
                                    [&](uint32_t w) { return filter[w]; });
           uint32_t rank[kPerThread], total;

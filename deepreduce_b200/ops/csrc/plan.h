@@ -163,6 +163,8 @@ struct EngineParams {
   uint32_t* bucket_pos;          // [sum K] original position p of the grouped values
   float* expand_buf;             // [world][sum K] fitted curves of every rank
   uint32_t poly_total;           // sum K over the vmode==1 tensors
+  int own_flags;                 // decode takes this rank's own positives from flag_buf instead of re-testing its filter
+  uint8_t* warp_count;           // [n_tiles * 128] per-(slot, warp) positive counts written by query: emit ranks without a CTA barrier (nullptr: off)
   uint32_t* mc_arena;            // NVLS multicast mapping of the symmetric arena (nullptr: per-peer P2P stores)
   int has_rle;                   // some tensor uses kModeRle (its bit stream is OR-ed, so it is zeroed every step)
   int shard;                     // 1: sharded decode + stage-2 exchange (when world > 1)

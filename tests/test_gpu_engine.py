@@ -111,6 +111,22 @@ SIZES = [64, 1000, 1001, 4096, 4097, 36864, 147456, 10, 589824]
     ("bloom", "leftmost", True, True, "polyfit"),
     ("bloom", "leftmost", True, True, "qsgd")])
 def test_engine_vs_oracle_single_rank(kind, index, policy, hint, tma, value):
+    _run_vs_oracle(kind, index, policy, hint, tma, value)
+
+
+@pytest.mark.parametrize("own,counts", [(0, 0), (1, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("index,policy,value", [("bloom", "leftmost", None), ("bloom", "p0", None), (None, "leftmost", None),
+                                                ("rle", "leftmost", None), ("bloom", "leftmost", "polyfit")])
+def test_engine_option_flags_vs_oracle(monkeypatch, own, counts, index, policy, value):
+    """DR_OWN_FLAGS (decode reuses the sender's own query flags) and DR_EMIT_COUNTS (barrier-free emit from the
+    query phase's per-warp counts) must not change a single bit of the slot / output / residual."""
+    monkeypatch.setenv("DR_OWN_FLAGS", str(own))
+    monkeypatch.setenv("DR_EMIT_COUNTS", str(counts))
+    for kind in ("randn", "ties"):
+        _run_vs_oracle(kind, index, policy, True, True, value)
+
+
+def _run_vs_oracle(kind, index, policy, hint, tma, value):
     from deepreduce_b200.parallel import BucketEngine, BucketPlan, engine_oracle
     plan = BucketPlan(SIZES + [2359296], compress_ratio=0.01, index=index, policy=policy, hint=hint, value=value,
                       poly_min_k=300)
