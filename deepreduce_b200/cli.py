@@ -130,6 +130,10 @@ def main(argv=None):
             out["wire_bytes_per_step_per_rank"] = tr.ddp.wire_bytes_per_step()
             out["dense_bytes"] = tr.ddp.dense_bytes()
             out["relative_volume"] = out["wire_bytes_per_step_per_rank"] / out["dense_bytes"]
+            if getattr(tr.ddp, "fused", False):          # counters the kernel left in the slot headers (last step)
+                st = tr.ddp.exchange_stats()
+                out["exchange_stats"] = {k: st[k] for k in ("k", "n_sel", "n_pos", "false_pos", "value_bytes",
+                                                            "index_bytes", "header_bytes") if k in st}
         if args.log_time:
             out["s_per_step"] = t_fb / args.steps
         from .utils import METRICS

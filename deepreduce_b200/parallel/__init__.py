@@ -1,4 +1,4 @@
 from .plan import BucketPlan, TensorPlan
-from .engine import BucketEngine, engine_oracle
+from .engine import BucketEngine, engine_oracle, stats_from_slot
 
-__all__ = ["BucketPlan", "TensorPlan", "BucketEngine", "engine_oracle"]
+__all__ = ["BucketPlan", "TensorPlan", "BucketEngine", "engine_oracle", "stats_from_slot"]

@@ -226,6 +226,20 @@ class DeepReduceDDP:
     def dense_bytes(self) -> int:
         return sum(p.numel() * 4 for _, p in self.named)
 
+    def exchange_stats(self) -> dict:
+        """Device-side counters of the last exchanged step, summed over the buckets (fused path): shipped
+        coordinates, bloom positives / false positives, value / index / header bytes (``BucketEngine.stats``).
+        Call it after ``finish()`` (i.e. after a training step); it synchronises the device, so every N steps."""
+        if not self.fused:
+            return {"wire_bytes": self.wire_bytes_per_step(), "dense_bytes": self.dense_bytes()}
+        torch.cuda.synchronize(self.device)
+        tot: dict = {}
+        for e in self.engines:
+            for k, v in e.stats()["total"].items():
+                tot[k] = tot.get(k, 0) + v
+        tot["relative_volume"] = tot["wire_bytes"] / max(1, tot["dense_bytes"])
+        return tot
+
     # ---- checkpoint / resume (SURVEY §5) -------------------------------------------
     def state_dict(self):
         if self.fused:

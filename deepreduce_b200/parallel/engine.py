@@ -195,6 +195,44 @@ def engine_oracle(plan: BucketPlan, grads: Sequence[torch.Tensor], resids: Seque
 # ---------------------------------------------------------------------------
 # engine
 # ---------------------------------------------------------------------------
+def stats_from_slot(plan: BucketPlan, slot) -> dict:
+    """Per-step counters of one sender, read from the 4-word dynamic header every tensor carries in the slot
+    (``{n_sel, cutoff, thr_bits, n_pos}``, written on the device by the emit phase — SURVEY §5 "per-step counters
+    accumulated on device"): shipped coordinates, bloom positives / false positives among the universe, the magnitude
+    threshold of the selection, and the wire bytes by component (static, from the plan)."""
+    a = slot.detach().cpu().numpy().view(np.uint32) if torch.is_tensor(slot) else np.asarray(slot, dtype=np.uint32)
+    per, tot = [], {"k": 0, "n_sel": 0, "n_pos": 0, "false_pos": 0, "value_bytes": 0, "index_bytes": 0}
+    for ti, t in enumerate(plan.tensors):
+        d0 = SLOT_HEADER_WORDS + DYN_WORDS * ti
+        n_sel, cutoff, thr_bits, n_pos = (int(x) for x in a[d0:d0 + 4])
+        thr = float(np.array([thr_bits], dtype=np.uint32).view(np.float32)[0])
+        if t.vmode == 1:
+            vbytes = 4 * (22 * (t.poly_degree + 1) + 2) + (4 if t.rank_u32 else 2) * t.val_cap
+        elif t.vmode == 2:
+            vbytes = 4 * ((t.val_cap + 511) // 512) + t.val_cap
+        else:
+            vbytes = 4 * t.val_cap
+        if t.mode == MODE_BLOOM:
+            ibytes = 4 * (t.n_filter_words + t.n_tiles + (4 * t.n_tiles if t.off_hint else 0))
+            false_pos = max(0, n_pos - min(t.k, n_pos))      # positives beyond the K inserted (upper bound under 22-bit ties)
+        elif t.mode == MODE_RLE:
+            ibytes = 4 * ((t.n_tiles + 1) // 2 + rle_stream_words(t.val_cap))
+            false_pos = 0
+        else:
+            ibytes, false_pos = 4 * t.val_cap, 0
+        row = {"name": t.name, "numel": t.numel, "k": t.k, "n_sel": n_sel, "n_pos": n_pos, "false_pos": false_pos,
+               "threshold": thr, "cutoff": None if cutoff == 0xFFFFFFFF else cutoff,
+               "value_bytes": vbytes, "index_bytes": ibytes}
+        per.append(row)
+        for key in tot:
+            tot[key] += row[key]
+    tot["header_bytes"] = 4 * (SLOT_HEADER_WORDS + DYN_WORDS * len(plan.tensors))
+    tot["wire_bytes"] = plan.wire_bytes()
+    tot["dense_bytes"] = plan.dense_bytes()
+    tot["relative_volume"] = tot["wire_bytes"] / max(1, tot["dense_bytes"])
+    return {"tensors": per, "total": tot}
+
+
 class BucketEngine:
     """One flat bucket + its fused exchange kernel."""
 
@@ -363,6 +401,12 @@ class BucketEngine:
         r = self.rank if src_rank is None else src_rank
         off = ARENA_HDR_WORDS + ((e & 1) * self.world + r) * self.plan.slot_words
         return self.arena[off:off + self.plan.payload_words]
+
+    def stats(self, src_rank: Optional[int] = None, epoch: Optional[int] = None) -> dict:
+        """Counters of the last step for one sender (default: this rank): see :func:`stats_from_slot`.  One small
+        device-to-host copy of the slot's header region; call it off the critical path (e.g. every N steps)."""
+        n_hdr = SLOT_HEADER_WORDS + DYN_WORDS * len(self.plan.tensors)
+        return stats_from_slot(self.plan, self.slot(src_rank, epoch)[:n_hdr])
 
     def check_status(self):
         st = self.status.cpu().tolist()

@@ -54,3 +54,38 @@ def test_gradient_accumulation_exchanges_every_n():
     t.step(x, target=y)
     assert any(not torch.equal(a, b) for a, b in zip(before, t.model.parameters()))
     assert t.ddp.step_count == 1
+
+
+def test_diagnostic_writers(tmp_path):
+    """The remaining writers of compression_utils.hpp / integer_compression.cc / logger.cc."""
+    import numpy as np
+    import torch
+    from deepreduce_b200.utils import (StepLogger, bitstream_str, log_bitstream_compressor, log_bitstream_decompressor,
+                                       log_decompressor, log_integer_codec)
+    assert bitstream_str(np.array([1, 128], dtype=np.uint8)).split("[")[1].split("]")[0].split() == \
+        list("1000000000000001")
+    root = str(tmp_path)
+    p = log_decompressor(root, 0, 3, 7, N=16, bloom_words=torch.tensor([5], dtype=torch.int32),
+                         selected_indices=torch.tensor([1, 4]), values=torch.tensor([0.5, -1.0]),
+                         decompressed=torch.zeros(16), policy="leftmost", suffix=1)
+    assert p.endswith("decompressor_logs_leftmost_1.txt") and "Indices Chosen: [1, 4]" in open(p).read()
+    assert log_decompressor(root, 0, 3, 7, N=16, bloom_words=torch.tensor([5], dtype=torch.int32),
+                            selected_indices=torch.tensor([1]), values=torch.tensor([0.5]),
+                            decompressed=torch.zeros(16), verbosity=1) is None
+    enc = torch.tensor([3, 9, 27], dtype=torch.uint8)
+    st = log_bitstream_compressor(root, 0, 3, 8, indices=torch.tensor([2, 3, 9]), encoded=enc, initial_bits=32 * 3,
+                                  runs=torch.tensor([2, 2, 5, 1]), verbosity=2)
+    assert st == {"initial_bits": 96, "final_bits": 3 * 8 + 32}
+    d = tmp_path / "0" / "step_3" / "8"
+    assert (d / "stats.txt").read_text().startswith("Initial_Size: 96  Final_Size: 56")
+    assert "Lengths:" in (d / "RleCompressor_logs.txt").read_text()
+    assert log_bitstream_decompressor(root, 0, 3, 8, encoded=enc, indices=torch.tensor([2, 3, 9]), suffix=2).endswith("_2.txt")
+    assert log_integer_codec(root, 5, 1, input_words=torch.arange(8), encoded_words=torch.arange(3), verbosity=2) is None
+    st = log_integer_codec(root, 4, 1, input_words=torch.arange(8), encoded_words=torch.arange(3), verbosity=2)
+    assert st["initial_bits"] == 256 and st["final_bits"] == 3 * 32 + 32 and abs(st["rate"] - 0.375) < 1e-9
+    lg = StepLogger(root, gradient_id=2, rank=1, verbosity_frequency=10)
+    assert lg(torch.arange(4.0), torch.tensor([1.0, 2.0]), step=7) is False
+    assert lg(torch.arange(4.0), torch.tensor([1.0, 2.0]), step=20) is True
+    vals = (tmp_path / "1" / "step_20" / "2" / "values.csv").read_text().split()
+    assert [float(v) for v in vals] == [0.0, 1.0, 2.0, 3.0]
+    assert StepLogger(root, 2)(torch.zeros(2), torch.zeros(1), step=0) is False      # frequency 0 = never

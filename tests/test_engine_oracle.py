@@ -183,3 +183,26 @@ def test_oracle_rle_index_is_lossless_and_smaller_than_pairs():
         tile_of = np.repeat(np.arange(ta.n_tiles), cnt)
         idx = tile_of * 4096 + rle_unpack12(s1[0][ta.off_idx:], n)
         assert np.array_equal(idx, s2[0][tb.off_idx:tb.off_idx + n].astype(np.int64))
+
+
+def test_stats_from_slot_counts_and_bytes():
+    """Counters read back from the slot's dynamic headers (per-step device counters)."""
+    from deepreduce_b200.parallel import stats_from_slot
+    sizes = [64, 5000, 20000, 100000]
+    for index in ("bloom", "rle", None):
+        plan = BucketPlan(sizes, compress_ratio=0.01, index=index)
+        gen = torch.Generator().manual_seed(9)
+        g = [torch.randn(plan.total_elems, generator=gen)]
+        _, _, slots = engine_oracle(plan, g, [torch.zeros(plan.total_elems)])
+        st = stats_from_slot(plan, slots[0])
+        tot = st["total"]
+        assert tot["k"] == sum(t.k for t in plan.tensors)
+        assert tot["n_sel"] == sum(r["n_sel"] for r in st["tensors"]) and tot["n_sel"] >= 0.9 * tot["k"]
+        assert tot["value_bytes"] + tot["index_bytes"] + tot["header_bytes"] <= tot["wire_bytes"] + 64 * len(sizes)
+        assert 0 < tot["relative_volume"] < 0.05
+        big = st["tensors"][-1]
+        assert big["threshold"] > 1.5          # top 1 % of |N(0,1)| starts near 2.57 (22-bit threshold rounds down)
+        if index == "bloom":
+            assert big["n_pos"] >= big["n_sel"] and big["false_pos"] >= 0
+        else:
+            assert big["false_pos"] == 0
