@@ -223,7 +223,11 @@ deepreduce_wrapper = {'value': ValueCompressor, 'index': IndexCompressor, 'both'
 
 
 def deepreduce_from_params(params):
-    """Factory (reference :28-48).  No hash table is loaded: hashing is on the fly."""
+    """Factory (reference :28-48).  No hash table is loaded: hashing is on the fly.
+    The dict is validated once (``config.DeepReduceConfig``: types, ranges, codec names, typo'd keys) and never
+    written to."""
+    from .config import validate_params
+    validate_params(params)
     grc = grace_from_params(params)
     deepreduce = params.get('deepreduce', None)
     if deepreduce:

@@ -144,3 +144,40 @@ def test_file_loggers(tmp_path):
     assert (d / "fpr.txt").read_text().startswith("FalsePositives: 32")
     log_values(str(tmp_path), 0, 5, 3, g[:10], torch.arange(6.0))
     assert len((d / "values.csv").read_text().splitlines()) == 10
+
+
+def test_config_validation():
+    """params dict -> frozen, range-checked config (SURVEY §5 'Config / flag system')."""
+    import warnings
+
+    import pytest
+
+    from deepreduce_b200 import deepreduce_from_params
+    from deepreduce_b200.config import ConfigError, DeepReduceConfig
+    base = {'compressor': 'topk', 'memory': 'residual', 'communicator': 'allgather', 'compress_ratio': 0.01,
+            'deepreduce': 'index', 'index': 'bloom'}
+    cfg = DeepReduceConfig.from_params(base)
+    assert cfg.compress_ratio == 0.01 and cfg.index == 'bloom' and cfg.policy == 'leftmost'
+    with pytest.raises(Exception):
+        cfg.compress_ratio = 0.5                                  # frozen
+    assert DeepReduceConfig.from_params(cfg.to_params()) == cfg   # round trip
+    before = dict(base)
+    deepreduce_from_params(base)
+    assert base == before                                         # never written to
+    for bad in ({'compress_ratio': 0.0}, {'compress_ratio': 1.5}, {'fpr': 1.0}, {'policy': 'rightmost'},
+                {'deepreduce': 'values'}, {'index': 'bloomm'}, {'communicator': 'allreduce'}, {'poly_degree': 9},
+                {'compressor': 'top-k'}, {'memory': 'momentum'}):
+        with pytest.raises(ConfigError):
+            DeepReduceConfig.from_params({**base, **bad})
+    with pytest.raises(NotImplementedError):
+        DeepReduceConfig.from_params({**base, 'compressor': 'SKCompressGPU'})
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        DeepReduceConfig.from_params({**base, 'compres_ratio': 0.1})
+        assert any('compres_ratio' in str(x.message) for x in w)
+    with pytest.raises(ConfigError):
+        DeepReduceConfig.from_params({**base, 'compres_ratio': 0.1}, strict=True)
+    # randomk with a shared seed may be all-reduced (GRACE); a value/index codec needs a sparsifier
+    DeepReduceConfig.from_params({'compressor': 'randomk', 'communicator': 'allreduce', 'memory': 'none'})
+    with pytest.raises(ConfigError):
+        DeepReduceConfig.from_params({'compressor': 'none', 'communicator': 'allgather', 'deepreduce': 'index'})
