@@ -102,6 +102,7 @@ def _mk_cpu():
         int_encode=lambda cid, a: m.int_encode(int(cid), np.ascontiguousarray(a, dtype=np.uint32)),
         int_decode=lambda cid, w, n: m.int_decode(int(cid), np.ascontiguousarray(w, dtype=np.uint32), int(n)),
         write_csv=lambda path, v: m.write_csv(str(path), np.ascontiguousarray(v, dtype=np.float64)),
+        BloomFilter=m.BloomFilter,      # insert / query / words / num_bytes / num_hashes / hash / compute_false_positives
     )
 
 

@@ -384,10 +384,59 @@ void write_csv(const std::string& path, py::array_t<double, py::array::c_style |
   fclose(f);
 }
 
+// ---------------------------------------------------------------------------
+// Bloom filter object for Python (the surface the reference's ops use of bloom::OrdinaryBloomFilter,
+// reference tensorflow/bloom_filter_compression.cc:102-110,206: insert / query / raw words / byte and hash counts /
+// hash positions / false-positive count over a universe / construction from received raw words)
+// ---------------------------------------------------------------------------
+struct PyBloom {
+  Bloom b;
+  PyBloom(uint32_t k, uint32_t m_bits, uint32_t seed) : b(k, m_bits, seed) {}
+  static PyBloom from_words(py::array_t<uint32_t, py::array::c_style | py::array::forcecast> w, uint32_t k,
+                            uint32_t m_bits, uint32_t seed) {
+    PyBloom f(k, m_bits, seed);
+    if ((size_t)w.size() != f.b.words.size()) throw std::runtime_error("word count does not match m_bits");
+    std::copy(w.data(), w.data() + w.size(), f.b.words.begin());
+    return f;
+  }
+  void insert(py::array_t<int64_t, py::array::c_style | py::array::forcecast> idx) {
+    for (py::ssize_t i = 0; i < idx.size(); ++i) b.insert((uint32_t)idx.data()[i]);
+  }
+  py::array_t<bool> query(py::array_t<int64_t, py::array::c_style | py::array::forcecast> idx) const {
+    py::array_t<bool> out(idx.size());
+    bool* o = out.mutable_data();
+    for (py::ssize_t i = 0; i < idx.size(); ++i) o[i] = b.query((uint32_t)idx.data()[i]);
+    return out;
+  }
+  py::array_t<uint32_t> words() const { return to_np(b.words); }
+  size_t num_bytes() const { return b.words.size() * 4; }
+  uint32_t num_hashes() const { return b.k; }
+  uint32_t hash(uint32_t x, uint32_t j) const { return b.pos(x, j); }
+  // positives in [0, N) that are not in the (sorted or unsorted) inserted set
+  int64_t compute_false_positives(int64_t N, py::array_t<int64_t, py::array::c_style | py::array::forcecast> inserted) const {
+    std::vector<int64_t> t(inserted.data(), inserted.data() + inserted.size());
+    std::sort(t.begin(), t.end());
+    int64_t fp = 0;
+    for (int64_t x = 0; x < N; ++x)
+      if (b.query((uint32_t)x) && !std::binary_search(t.begin(), t.end(), x)) ++fp;
+    return fp;
+  }
+};
+
 }  // namespace
 
 PYBIND11_MODULE(_dr_cpu, m) {
   m.doc() = "DeepReduce-B200 host-side native ops";
+  py::class_<PyBloom>(m, "BloomFilter")
+      .def(py::init<uint32_t, uint32_t, uint32_t>(), py::arg("num_hashes"), py::arg("m_bits"), py::arg("seed"))
+      .def_static("from_words", &PyBloom::from_words)
+      .def("insert", &PyBloom::insert)
+      .def("query", &PyBloom::query)
+      .def("words", &PyBloom::words)
+      .def("num_bytes", &PyBloom::num_bytes)
+      .def("num_hashes", &PyBloom::num_hashes)
+      .def("hash", &PyBloom::hash)
+      .def("compute_false_positives", &PyBloom::compute_false_positives);
   m.def("bloom_insert", &bloom_insert);
   m.def("bloom_select", &bloom_select);
   m.def("conflict_sets", &conflict_sets);

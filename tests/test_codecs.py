@@ -201,3 +201,27 @@ def test_registry_and_custom_codec():
     t = torch.randn(5000)
     out = grc.step(t, "x")
     assert int((out != 0).sum()) == 50
+
+
+def test_native_bloomfilter_object_matches_oracle():
+    """The C++ filter object (surface of the reference's bloom::OrdinaryBloomFilter) vs the torch oracle."""
+    import numpy as np
+    import pytest
+    import torch
+    from deepreduce_b200 import ops, spec
+    from deepreduce_b200.codecs.bloom import bloom_insert_oracle, bloom_query_oracle
+    if not ops.has_cpu_native():
+        pytest.skip("native host extension not built")
+    k, m_bits, d = 7, 2048, 20000
+    gen = torch.Generator().manual_seed(1)
+    idx = torch.sort(torch.randperm(d, generator=gen)[:150]).values
+    f = ops.cpu.BloomFilter(k, m_bits, spec.DEFAULT_SEED)
+    f.insert(idx.numpy())
+    ref = bloom_insert_oracle(idx, k, m_bits, spec.DEFAULT_SEED)
+    assert np.array_equal(f.words(), ref.numpy().view(np.uint32))
+    assert f.num_bytes() == m_bits // 8 and f.num_hashes() == k and all(f.hash(5, j) < m_bits for j in range(k))
+    assert f.query(idx.numpy()).all()                                      # no false negatives
+    positives = bloom_query_oracle(ref, d, k, m_bits, spec.DEFAULT_SEED)
+    assert f.compute_false_positives(d, idx.numpy()) == positives.numel() - idx.numel()
+    g = ops.cpu.BloomFilter.from_words(f.words(), k, m_bits, spec.DEFAULT_SEED)    # receiver side: from raw words
+    assert np.array_equal(g.query(np.arange(d)), np.isin(np.arange(d), positives.numpy()))
