@@ -1,5 +1,10 @@
 // pybind11 / ATen bindings for the sm_100a kernels + the C++ runtime pieces
 // (bucket engine context, background launch thread, IPC arena).
+// The reference's native layer is TensorFlow CPU op glue (tensorflow/bloom_filter_compression.cc,
+// integer_compression.cc, logger.cc); its PyTorch path has no native code and runs strictly after backward with
+// torch.cuda.synchronize() between stages (pytorch/deepreduce.py:71,86,120,140,256,278).  Here the runtime is native:
+// `Engine` owns the kernel parameter block of one bucket, `Scheduler` is the background thread that launches bucket
+// kernels behind a CUDA event while backward is still running.
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <c10/cuda/CUDAStream.h>

@@ -1,5 +1,11 @@
 // Shared device/host helpers for the DeepReduce-B200 kernels (sm_100a).
 // Hash family and bit layout are normative: see deepreduce_b200/spec.py.
+//
+// Parity: the reference looks hashes up in a precomputed MurmurHash3 table `hash_table[d_max, k_max]`
+// (pytorch/deepreduce.py:440,461-463,471; ~1.5 MB for ResNet-20, ~1 GB for NCF — paper p.29) and reduces them
+// `% size`; here the k positions of an index are computed on the fly (two murmur3 finalisers, Kirsch-Mitzenmacher
+// h_j = a + j*b, Lemire multiply-shift range reduction), so d is unbounded and no table is loaded.  The bit array is
+// built bit-packed (uint32 words, LSB first) — the reference's bool array + cupy.packbits step (:446-455,529) is gone.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -1,6 +1,15 @@
 // Bucket plan + engine parameter block shared by host (binding.cpp) and device
 // (engine.cu).  The plan is built in Python (parallel/plan.py) and uploaded as
 // int32 tensors; field order here is normative for that builder.
+//
+// Parity notes (reference = hangxu0304/DeepReduce):
+//  * a TensorDesc carries what the reference recomputes per call from `params`: K = max(1, int(d * ratio))
+//    (GRACE top-k), bloom m / hash count (pytorch/deepreduce.py:495-500,511-512), the 1000-element bypass
+//    (:68,84,114), polyfit degree (:385), QSGD quantum_num / bucket 512 (:857-858);
+//  * a slot replaces the per-tensor wire tuples `(vals, packed bit array)` (:529), `(coefficients, idxs)` (:413-414)
+//    and `(vals', idxs', mapping)` (:267) — all tensors of a bucket in one buffer with static offsets, so the
+//    size all_gather + pad-to-max of the GRACE communicator (tensors_size_are_same=False, :59,108) disappears;
+//  * DynHeader.n_sel/cutoff is policy `leftmost` / `p0` (:479-492) expressed so the receiver needs no sort.
 #pragma once
 #include <stdint.h>
 
@@ -19,7 +28,7 @@ enum TensorMode : uint32_t {
 
 enum Policy : int { kPolicyLeftmost = 0, kPolicyRandom = 1, kPolicyP0 = 2 };
 
-// 16 x uint32 per tensor
+// 32 x uint32 per tensor (kDescWords)
 struct TensorDesc {
   uint32_t elem_off;     // offset into the flat grad/residual buffers (elements, multiple of 4)
   uint32_t numel;        // d_i

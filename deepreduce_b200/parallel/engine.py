@@ -1,14 +1,23 @@
 """Python driver + torch oracle for the fused bucket engine (``ops/csrc/engine.cu``).
 
 ``BucketEngine`` owns the flat gradient / residual buffers of one bucket, the
-select/look-back state, the symmetric arena (CUDA IPC for W>1) and the C++
-``Engine`` context; ``step()`` launches the single persistent kernel that does
-sparsify → encode → P2P push → decode for the whole bucket.
+select state, the symmetric arena (CUDA IPC, or NVLS-capable symmetric memory
+with ``DR_NVLS=1``, for W>1) and the C++ ``Engine`` context; ``step()`` launches
+the single persistent kernel that does sparsify → encode → P2P push → sharded
+decode → slice exchange for the whole bucket.
 
 ``engine_oracle`` is the plain-PyTorch specification of the same step,
 including the wire format of the slot, used by the tests (GPU kernels vs
-oracle: slots bit-exact, dense output allclose) and as the CPU/gloo fallback of
-the bucketed API.
+oracle: slots bit-exact, dense output allclose).
+
+Parity with the reference (hangxu0304/DeepReduce), per tensor of the bucket:
+  * residual compensate / update  — GRACE ResidualMemory, TF twin tensorflow/deepreduce.py:31-52;
+  * top-k select                  — GRACE TopK (``torch.topk(abs(x), k)``), here a 22-bit-threshold radix select;
+  * bloom insert / universe query / policy / FP-aware re-gather — pytorch/deepreduce.py:457-492,505-529;
+  * 'both' (index first, value codec on the re-gathered values, mapping back) — :250-302;
+    polyfit segments / fit / restore — :341-425; QSGD — :861-907;
+  * per-rank decode + aggregate (+ average) — GRACE Allgather communicator, reference README.md:37;
+  * lossless run-length index (``'index': 'rle'``) — :805-846, here tile-local (see ``ops/csrc/plan.h``).
 """
 from __future__ import annotations
 
