@@ -22,7 +22,7 @@ import torch.nn as nn
 
 from .. import spec
 from ..wrappers import deepreduce_from_params
-from .engine import PH_ACCUM, PH_END, BucketEngine
+from .engine import BucketEngine
 from .plan import BucketPlan
 
 
@@ -84,7 +84,8 @@ class DeepReduceDDP:
         self._exchange = True
         if self.fused or (self.dense and self.is_cuda):
             self._build_buckets(bucket_cap_mb, blocks_per_sm, use_history)
-            if self.fused and self.overlap and background_thread:
+            if (self.fused and self.overlap and background_thread
+                    and all(e.transport == "p2p" for e in self.engines)):     # the NCCL transport is issued from Python
                 from .. import ops
                 self.sched = ops.cuda_module().Scheduler(len(self.buckets))
             if self.overlap:
@@ -170,7 +171,7 @@ class DeepReduceDDP:
             if self.sched is not None:
                 self.sched.submit(b, eng.ctx, eng.epoch)
             else:
-                eng.ctx.run(eng.epoch, PH_ACCUM, PH_END)
+                eng.step(eng.epoch)
         else:
             if self.world > 1:
                 self.pending.append(dist.all_reduce(self.flat[b], group=self.group, async_op=True))

@@ -249,7 +249,7 @@ class BucketEngine:
                  average: bool = True, use_history: bool = True, blocks_per_sm: int = 2,
                  seed: int = spec.DEFAULT_SEED, spin_limit: int = 20_000_000, world: Optional[int] = None,
                  rank: Optional[int] = None, filter_smem_bytes: Optional[int] = None, use_tma: bool = True,
-                 hist_shift: int = 23, shard: Optional[bool] = None):
+                 hist_shift: int = 23, shard: Optional[bool] = None, transport: Optional[str] = None):
         from .. import ops
         self.mod = ops.cuda_module()
         self.plan = plan
@@ -264,6 +264,12 @@ class BucketEngine:
         # sharded decode (W > 1): each rank decodes 1/W of the tiles for all senders, then the exact slices are
         # exchanged by a second in-kernel push.  DR_SHARD=0 restores the every-rank-decodes-everything path.
         self.shard = (os.environ.get("DR_SHARD", "1") != "0") if shard is None else bool(shard)
+        # transport of the compressed slots between ranks: 'p2p' = in-kernel stores into peer-mapped arenas (one
+        # NVLink/NVSwitch domain, the default), 'nccl' = encode phases -> ONE in-place NCCL all_gather of the slots per
+        # bucket -> decode phases (ranks on different hosts, or no peer access).  None: DR_TRANSPORT, else auto.
+        self.transport = self._pick_transport(transport)
+        if self.transport == "nccl":
+            self.shard = False
         dev = self.device
         nT, nt = len(plan.tensors), plan.n_tiles
         with torch.cuda.device(dev):
@@ -326,6 +332,11 @@ class BucketEngine:
             self.arena_ptrs = [self.arena.data_ptr()]
             return
         self.multicast_ptr = 0
+        if self.transport == "nccl":          # peers' slots arrive by all_gather into MY arena: nothing to map
+            self._ipc = False
+            self.arena = torch.zeros(words, dtype=torch.int32, device=self.device)
+            self.arena_ptrs = [self.arena.data_ptr()] * self.world      # peer entries are never dereferenced
+            return
         if os.environ.get("DR_NVLS", "0") == "1" and self._setup_arena_nvls(words):
             return
         self.mod.enable_peer_access(torch.cuda.device_count())
@@ -344,6 +355,20 @@ class BucketEngine:
                 self._imported.append(p)
                 self.arena_ptrs.append(p)
         dist.barrier(group=self.group)
+
+    def _pick_transport(self, transport: Optional[str]) -> str:
+        t = transport or os.environ.get("DR_TRANSPORT", "") or "auto"
+        if t not in ("auto", "p2p", "nccl"):
+            raise ValueError(f"transport must be 'p2p', 'nccl' or None/'auto' (got {t!r})")
+        if self.world == 1:
+            return "p2p"
+        if t != "auto":
+            return t
+        # auto: peer-mapped arenas need every rank in one process-visible GPU domain, i.e. on the same host
+        import socket
+        hosts = [None] * self.world
+        dist.all_gather_object(hosts, socket.gethostname(), group=self.group)
+        return "p2p" if len(set(hosts)) == 1 else "nccl"
 
     def _setup_arena_nvls(self, words: int) -> bool:
         """Arena in NVLS-capable symmetric memory (cuMem + multicast object, torch's symmetric-memory rendezvous does the
@@ -391,7 +416,22 @@ class BucketEngine:
         """Launch the fused kernel on the current stream.  In: ``self.grad``
         (local dense grads).  Out: ``self.grad`` (aggregated), ``self.resid``."""
         self.epoch = self.epoch + 1 if epoch is None else int(epoch)
-        self.ctx.run(self.epoch, PH_ACCUM, PH_END)
+        if self.transport == "nccl" and self.world > 1:
+            self._step_nccl()
+        else:
+            self.ctx.run(self.epoch, PH_ACCUM, PH_END)
+
+    def _step_nccl(self):
+        """Multi-host form of the step: the same kernel runs its encode phases, the slots travel by ONE in-place
+        NCCL all_gather per bucket (the slot of rank r sits at index r of the parity's slot array in every arena, so
+        the output buffer is the arena itself), then the kernel runs expand + decode.  Still no per-tensor
+        collectives and no size exchange (static offsets), cf. the reference's 2-3 all_gathers per tensor."""
+        W, sw = self.world, self.plan.slot_words
+        self.ctx.run(self.epoch, PH_ACCUM, PH_PUSH)
+        base = ARENA_HDR_WORDS + (self.epoch & 1) * W * sw
+        out = self.arena[base:base + W * sw]
+        dist.all_gather_into_tensor(out, out[self.rank * sw:(self.rank + 1) * sw], group=self.group)
+        self.ctx.run(self.epoch, PH_EXPAND, PH_COMPACT)
 
     def run_phases(self, begin: int, end: int, epoch: Optional[int] = None):
         """Debug / unfused chain: run a sub-range of phases (one launch)."""

@@ -20,9 +20,14 @@ def main():
                                         ("bloom", "p0", None, True), (None, "leftmost", None, True),
                                         ("rle", "leftmost", None, True), ("rle", "leftmost", None, False),
                                         ("bloom", "leftmost", "polyfit", True), ("bloom", "leftmost", "polyfit", False),
-                                        ("bloom", "leftmost", "qsgd", True)):
+                                        ("bloom", "leftmost", "qsgd", True)) + (
+            # multi-host transport (encode -> one NCCL all_gather of the slots -> decode); opt-in until it has had
+            # its first hardware run: DR_TEST_NCCL_TRANSPORT=1
+            (("bloom", "leftmost", None, "nccl"), ("rle", "leftmost", None, "nccl"), ("bloom", "leftmost", "polyfit", "nccl"))
+            if os.environ.get("DR_TEST_NCCL_TRANSPORT", "0") == "1" else ()):
         plan = BucketPlan(sizes, compress_ratio=0.01, index=index, policy=policy, value=value)
-        eng = BucketEngine(plan, device=f"cuda:{local}", spin_limit=4_000_000, shard=shard)
+        eng = BucketEngine(plan, device=f"cuda:{local}", spin_limit=4_000_000, shard=shard,
+                           transport="nccl" if shard == "nccl" else None)
         if rank == 0:
             print(f"engine index={index} value={value} shard={shard} nvls={bool(getattr(eng, 'multicast_ptr', 0))} "
                   f"{getattr(eng, '_nvls_error', '')}", flush=True)
