@@ -364,7 +364,11 @@ class BucketEngine:
             return "p2p"
         if t != "auto":
             return t
-        # auto: peer-mapped arenas need every rank in one process-visible GPU domain, i.e. on the same host
+        # auto: peer-mapped arenas need every rank on the same host.  torchrun exports LOCAL_WORLD_SIZE: when it equals
+        # the size of the (default) group the answer is known without a collective
+        lws = os.environ.get("LOCAL_WORLD_SIZE", "")
+        if self.group is None and lws.isdigit() and int(lws) == self.world:
+            return "p2p"
         import socket
         hosts = [None] * self.world
         dist.all_gather_object(hosts, socket.gethostname(), group=self.group)
