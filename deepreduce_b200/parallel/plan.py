@@ -217,10 +217,20 @@ class BucketPlan:
         return torch.from_numpy(out.astype(np.uint32).view(np.int32).copy())
 
     def stage2_layout(self, world: int):
-        """(entries, words) of a stage-2 slot for the sharded decode: a rank's slice holds about
-        sum(K) distinct non-zeros (W senders x K/W each); 2x slack + a floor."""
+        """(entries, words) of a stage-2 slot of the sharded decode.  A rank's slice receives what all W senders
+        selected inside it: about sum(K) entries when selections are spread evenly, but up to W * sum(K) (or every
+        element of the slice) when they cluster — e.g. hot embedding rows.  The default capacity is that worst case,
+        so the exchange can never drop entries; the payload actually pushed is only the live count.  DR_S2_SLACK=<f>
+        selects the compact sizing f * sum(K) + 8192 instead (overflow is then reported as engine status 6)."""
+        import os
         k_total = sum(t.val_cap for t in self.tensors)
-        cap = _align(2 * k_total + 8192, 4)
+        slack = os.environ.get("DR_S2_SLACK", "")
+        if slack:
+            cap = int(float(slack) * k_total) + 8192
+        else:
+            slice_elems = (self.n_tiles + world - 1) // world * spec.TILE
+            cap = min(world * k_total, slice_elems) + 64
+        cap = _align(cap, 4)
         return cap, _align(4 + 2 * cap, 64)
 
     def arena_words(self, world: int, shard: bool = True) -> int:

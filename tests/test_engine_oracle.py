@@ -206,3 +206,20 @@ def test_stats_from_slot_counts_and_bytes():
             assert big["n_pos"] >= big["n_sel"] and big["false_pos"] >= 0
         else:
             assert big["false_pos"] == 0
+
+
+def test_stage2_layout_never_overflows_by_construction(monkeypatch):
+    """Sharded decode: the stage-2 slot holds the worst case (all W senders' selections inside one slice)."""
+    sizes = [64, 5000, 20000, 100000, 2359296]
+    plan = BucketPlan(sizes, compress_ratio=0.01)
+    k_total = sum(t.val_cap for t in plan.tensors)
+    for W in (2, 4, 8):
+        cap, words = plan.stage2_layout(W)
+        slice_elems = (plan.n_tiles + W - 1) // W * 4096
+        assert cap % 4 == 0 and words % 64 == 0 and words >= 4 + 2 * cap
+        assert cap >= min(W * k_total, slice_elems)
+        assert plan.arena_words(W, True) == plan.arena_words(W, False) + 2 * W * words
+        assert plan.arena_words(W, True) < 2 ** 32            # word offsets are uint32-safe
+    assert plan.arena_words(1, True) == plan.arena_words(1, False)
+    monkeypatch.setenv("DR_S2_SLACK", "2")
+    assert plan.stage2_layout(8)[0] == ((2 * k_total + 8192 + 3) // 4) * 4
