@@ -181,3 +181,27 @@ def test_config_validation():
     DeepReduceConfig.from_params({'compressor': 'randomk', 'communicator': 'allreduce', 'memory': 'none'})
     with pytest.raises(ConfigError):
         DeepReduceConfig.from_params({'compressor': 'none', 'communicator': 'allgather', 'deepreduce': 'index'})
+
+
+def test_fused_path_gating():
+    """Which params dicts DeepReduceDDP routes to the fused engine (README 'What runs where')."""
+    from deepreduce_b200.parallel.ddp import _fused_supported
+    base = {'compressor': 'topk', 'memory': 'residual', 'communicator': 'allgather', 'compress_ratio': 0.01}
+    yes = [base,
+           {**base, 'deepreduce': 'index', 'index': 'bloom'},
+           {**base, 'deepreduce': 'index', 'index': 'bloom', 'policy': 'p0'},
+           {**base, 'deepreduce': 'index', 'index': 'rle'},
+           {**base, 'deepreduce': 'both', 'index': 'bloom', 'value': 'polyfit'},
+           {**base, 'deepreduce': 'both', 'index': 'bloom', 'value': 'qsgd', 'quantum_num': 127, 'bucket_size': 512}]
+    no = [{**base, 'compressor': 'threshold'}, {**base, 'compressor': 'randomk'},
+          {**base, 'deepreduce': 'index', 'index': 'bloom', 'policy': 'random'},
+          {**base, 'deepreduce': 'index', 'index': 'bloom', 'policy': 'conflict_sets'},
+          {**base, 'deepreduce': 'index', 'index': 'huffman'}, {**base, 'deepreduce': 'index', 'index': 'integer'},
+          {**base, 'deepreduce': 'value', 'value': 'polyfit'}, {**base, 'deepreduce': 'both', 'index': 'rle', 'value': 'polyfit'},
+          {**base, 'deepreduce': 'both', 'index': 'bloom', 'value': 'qsgd', 'quantum_num': 255},
+          {**base, 'deepreduce': 'both', 'index': 'bloom', 'value': 'gzip'},
+          {'compressor': 'none', 'memory': 'none', 'communicator': 'allreduce'}]
+    for p in yes:
+        assert _fused_supported(p), p
+    for p in no:
+        assert not _fused_supported(p), p
