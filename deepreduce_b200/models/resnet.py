@@ -6,7 +6,6 @@ framework's own kernels are the gradient exchange).
 """
 from __future__ import annotations
 
-import torch
 import torch.nn as nn
 import torch.nn.functional as F
 

@@ -14,7 +14,6 @@ import hashlib
 import os
 import shutil
 import subprocess
-import sys
 import sysconfig
 from concurrent.futures import ThreadPoolExecutor
 

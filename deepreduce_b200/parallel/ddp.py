@@ -14,7 +14,7 @@ anything else (CPU/gloo, other codecs)        -> GRACE-compatible per-tensor pat
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional
+from typing import Dict, List
 
 import torch
 import torch.distributed as dist

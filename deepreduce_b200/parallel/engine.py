@@ -24,7 +24,7 @@ from __future__ import annotations
 import os
 
 from collections import OrderedDict
-from typing import List, Optional, Sequence
+from typing import Optional, Sequence
 
 import numpy as np
 import torch
@@ -32,7 +32,7 @@ import torch.distributed as dist
 
 from .. import spec
 from ..codecs.bloom import bloom_insert_oracle, bloom_query_oracle
-from .plan import (ARENA_HDR_WORDS, DYN_WORDS, HIST_BINS, MODE_BLOOM, MODE_RAW, MODE_RLE, NUM_HIST, POLICY_ID,
+from .plan import (ARENA_HDR_WORDS, DYN_WORDS, HIST_BINS, MODE_BLOOM, MODE_RLE, NUM_HIST, POLICY_ID,
                    SLOT_HEADER_WORDS, BucketPlan, rle_stream_words)
 
 (PH_ACCUM, PH_FALLBACK, PH_HIST2, PH_INSERT, PH_QUERY, PH_EMIT, PH_RANK_HIST, PH_RANK_SCAN, PH_RANK_SCATTER,

@@ -1,6 +1,5 @@
 """sm_100a kernels vs the plain-torch oracle (GPU).  SURVEY §4 "Golden parity":
 set equality for S~ / bit-exact slots, allclose for values."""
-import json
 import os
 import subprocess
 import sys
