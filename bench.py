@@ -62,6 +62,28 @@ def parse():
     return ap.parse_args()
 
 
+def exchange_roofline(exchange_ms, dense_bytes, wire_bytes, world):
+    """Achieved fraction of the exchange kernel's roofline = the slower of (a) its unavoidable HBM traffic at the
+    MEASURED copy bandwidth (read g, read r, write r, write the dense result: 4 x dense bytes) and (b) the bytes it
+    sends over NVLink at link bandwidth (the slot to W-1 peers, plus about as much again for the decoded slices of
+    the sharded decode).  Denominators: MEASURED_PEAKS.json (fallback: the profiling recipe's 6 650 GB/s) and the
+    guide's 770 GB/s/direction measured peer copy."""
+    hbm = 6650.0
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")) as f:
+            hbm = float(json.load(f).get("hbm_gbs", hbm))
+    except Exception:
+        pass
+    nvlink = 770.0
+    t_hbm = 4.0 * dense_bytes / (hbm * 1e9) * 1e3
+    nv_bytes = 2.0 * (world - 1) * wire_bytes
+    t_nv = nv_bytes / (nvlink * 1e9) * 1e3
+    return {"hbm_min_bytes": int(4 * dense_bytes), "hbm_gbs_measured": hbm, "hbm_bound_ms": t_hbm,
+            "nvlink_bytes_out": int(nv_bytes), "nvlink_gbs_per_dir": nvlink, "nvlink_bound_ms": t_nv,
+            "bound": "hbm" if t_hbm >= t_nv else "nvlink", "frac_of_roofline": max(t_hbm, t_nv) / exchange_ms,
+            "compressed_allgather_bus_gbs": nv_bytes / (exchange_ms * 1e-3) / 1e9}
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -264,6 +286,8 @@ def run_ours(args, rank, world, local):
         ms_ex, _ = timed(ex, 20, world)
         extra["exchange_ms_per_step"] = ms_ex / 20
         extra["engine_grid"] = tr.ddp.engines[0].grid()
+        extra["roofline"] = exchange_roofline(extra["exchange_ms_per_step"], tr.ddp.dense_bytes(),
+                                              tr.ddp.wire_bytes_per_step(), world)
     wire = tr.ddp.wire_bytes_per_step()
     dense = tr.ddp.dense_bytes()
     names = {"resnet50": "ResNet-50 images/sec (whole job, device-timed, max over ranks)",
