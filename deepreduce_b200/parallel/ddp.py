@@ -213,8 +213,13 @@ class DeepReduceDDP:
         self.step_count += 1
 
     def check(self):
-        for e in self.engines:
-            e.check_status()
+        """Read the engines' device status words (one small D2H each); raises with rank and bucket on a watchdog."""
+        for b, e in enumerate(self.engines):
+            try:
+                e.check_status()
+            except RuntimeError as err:
+                raise RuntimeError(f"[rank {self.rank}/{self.world}] bucket {b} "
+                                   f"({len(self.buckets[b])} tensors, step {self.step_count}): {err}") from err
 
     # ---- accounting -------------------------------------------------------------
     def wire_bytes_per_step(self) -> int:

@@ -24,7 +24,8 @@ class Trainer:
                  weight_decay: float = 1e-4, amp_dtype: Optional[torch.dtype] = torch.bfloat16,
                  channels_last: bool = False, loss_fn: Optional[Callable] = None, optimizer=None,
                  overlap: bool = True, bucket_cap_mb: float = 1e9, background_thread: bool = True,
-                 blocks_per_sm: int = 2, u8_input: bool = False, accum_steps: int = 1, nvtx: bool = False):
+                 blocks_per_sm: int = 2, u8_input: bool = False, accum_steps: int = 1, nvtx: bool = False,
+                 check_every: int = 100):
         self.model = model
         self.device = next(model.parameters()).device
         self.is_cuda = self.device.type == "cuda"
@@ -44,6 +45,10 @@ class Trainer:
         self.u8_input = u8_input
         self.accum_steps = max(1, int(accum_steps))     # reference trainers' --grads_accumulated
         self._micro = 0
+        # failure detection: the kernels' watchdogs (peer-flag wait, grid barrier, TMA, stage-2 overflow) set a device
+        # status word instead of hanging; it is read back every `check_every` optimisation steps (0 = never)
+        self.check_every = max(0, int(check_every))
+        self._opt_steps = 0
         self.nvtx = nvtx and self.is_cuda
         self._copy_stream = torch.cuda.Stream(device=self.device) if self.is_cuda else None
         self._staged = None
@@ -87,6 +92,9 @@ class Trainer:
             with self._range("finish+optimizer"):
                 self.ddp.finish()
                 self.opt.step()
+            self._opt_steps += 1
+            if self.check_every and self._opt_steps % self.check_every == 0:
+                self.ddp.check()                  # raises with rank / bucket / watchdog name
         return loss.detach()
 
     # ---- end-to-end step (host in, host out) -----------------------------------
