@@ -37,7 +37,7 @@ class Gzip(SparseCompressor):
     def decompress(gzip_sparse_tensor, params):
         wire, idxs, shape = gzip_sparse_tensor
         raw = zlib.decompress(wire.cpu().numpy().tobytes())
-        vals = torch.frombuffer(bytearray(raw), dtype=torch.float32).to(idxs.device)
+        vals = torch.frombuffer(bytearray(raw), dtype=torch.float32).to(wire.device)
         return vals, idxs, shape
 
 

@@ -18,9 +18,12 @@ B200-first changes (SURVEY §7.4 "Polyfit numerics"):
   so the normal matrix is diagonal and ``c_k = Σ p_k y / Σ p_k²`` — one fused
   reduction pass, no solve, no host hop, |p_k| ≤ 1 so fp32 is enough.  The
   fitted *values* equal the monomial least-squares fit (same polynomial space).
-* fixed wire layout: ``float32[(deg+1)*MAX_SEGMENTS + 1]`` (unused segments
-  zero, last word = num_pos bit-cast from int32), so ``tensors_size_are_same``
-  is honestly True (latent bug in the reference).
+* wire layout: ``float32[(deg+1)*seg_rows(N) + 1]`` where ``seg_rows(N)`` is the
+  largest segment count ``get_segments`` can produce for N values (a function of N
+  only: unused rows are zero, last word = num_pos bit-cast from int32), so every rank
+  ships the same size and ``tensors_size_are_same`` is honestly True (the reference's
+  size depends on num_pos — a latent bug) while a 368-value tensor
+  carries 6 rows instead of the 22 of the largest table.
 * zero-length / tiny segments are legal (degree clamps to n-1).
 """
 from __future__ import annotations
@@ -46,6 +49,11 @@ def get_segments(N: int, num_pos: int = 0):
         if int(num_neg * r) > 30:
             neg.append(int(num_neg * r))
     return pos[::-1] + [num_pos - sum(pos)] + [num_neg - sum(neg)] + neg
+
+
+def seg_rows(N: int) -> int:
+    """Upper bound of ``len(get_segments(N, p))`` over all p: both halves may use every ratio that passes for N."""
+    return min(MAX_SEGMENTS, 2 * sum(1 for r in RATIOS if int(N * r) > 30) + 2)
 
 
 def gram_basis(n: int, degree: int, device=None, dtype=torch.float64) -> torch.Tensor:
@@ -127,6 +135,7 @@ class PolyFit(SparseCompressor):
             coeffs = ops.polyfit_fit(y_all, segments, degree)
         else:
             coeffs = polyfit_fit_oracle(y_all, segments, degree)
+        coeffs = coeffs[:seg_rows(N) * (degree + 1)]            # rows beyond seg_rows(N) can never be used
         return _pack_num_pos(coeffs, num_pos), idxs, shape
 
     @staticmethod
@@ -136,6 +145,9 @@ class PolyFit(SparseCompressor):
         N = idxs.numel()
         coeffs, num_pos = _split_num_pos(wire)
         segments = get_segments(N, num_pos)
+        full = MAX_SEGMENTS * (degree + 1)
+        if coeffs.numel() < full:                                # kernels / oracle index a MAX_SEGMENTS table
+            coeffs = torch.cat([coeffs, coeffs.new_zeros(full - coeffs.numel())])
         if use_cuda(coeffs):
             from .. import ops
             vals = ops.polyfit_eval(coeffs, segments, degree, N)

@@ -75,10 +75,15 @@ class QSGD(SparseCompressor):
         # K + per*ceil(K/bucket) = n  -> solve for K
         n = wire.numel()
         K = idxs.numel() if idxs is not None and idxs.numel() + per * _nb(idxs.numel(), bucket) == n else None
-        if K is None:
-            K = n * bucket // (bucket + per)
-            while K + per * _nb(K, bucket) < n:
-                K += 1
+        if K is None:                                   # no index list given ('both' ships none): n = K + per*ceil(K/bucket)
+            K, nb_try = 0, max(1, -(-n // (bucket + per)))
+            while n > 0:
+                K = n - per * nb_try
+                if K >= 0 and _nb(K, bucket) == nb_try:
+                    break
+                if K < 0:
+                    raise ValueError(f"QSGD wire of {n} elements is not K + {per}*ceil(K/{bucket}) for any K")
+                nb_try += 1
         nb = _nb(K, bucket)
         lvl = wire[:K]
         norm = wire[K:K + per * nb].clone().view(torch.float32)

@@ -68,6 +68,18 @@ def _report_volume(params, tensors, shape):
         print(f'val_relative_volume: {val_v:.4f}')
 
 
+def _wire_idx(idxs: torch.Tensor, numel: int) -> torch.Tensor:
+    """Indices travel as int32 whenever the tensor has < 2^31 elements (the paper's volume accounting, e.g. Table 2:
+    Top-r 10 % = 0.2033, counts 32-bit keys; GRACE's sparsifier hands out int64)."""
+    if idxs.dtype == torch.int64 and numel < 2 ** 31:
+        return idxs.to(torch.int32)
+    return idxs
+
+
+def _host_idx(idxs: torch.Tensor) -> torch.Tensor:
+    return idxs.long() if idxs.dtype == torch.int32 else idxs
+
+
 class _Wrapper(Compressor):
     def __init__(self, sparsifier, params=None):
         super().__init__(average=getattr(sparsifier, "average", True),
@@ -94,16 +106,17 @@ class ValueCompressor(_Wrapper):
             with _Timer(self.bench, 'val_compression', tensor.device):
                 vals, idxs, shape = self.val_compressor.compress((vals, idxs, tensor.size()), self.params)
             ctx = shape
-        return (vals, idxs), ctx
+        return (vals, _wire_idx(idxs, tensor.numel())), ctx
 
     def decompress(self, tensors, ctx):
         shape = ctx
         vals, idxs = tensors
+        idxs = _host_idx(idxs)
         if shape.numel() > self.min_numel:
             with _Timer(self.bench, 'val_decompression', idxs.device):
                 vals, idxs, shape = self.val_compressor.decompress((vals, idxs, shape), self.params)
             _report_volume(self.params, tensors, shape)
-        return self.sparsifier.decompress((vals, idxs), shape)
+        return self.sparsifier.decompress((vals, _host_idx(idxs)), shape)
 
 
 class IndexCompressor(_Wrapper):
@@ -125,6 +138,8 @@ class IndexCompressor(_Wrapper):
             with _Timer(self.bench, 'idx_compression', tensor.device):
                 vals, idxs, shape = self.idx_compressor.compress((vals, idxs, tensor.size()), call)
             ctx = shape
+        else:
+            idxs = _wire_idx(idxs, tensor.numel())       # small-tensor bypass: plain pairs, 32-bit keys
         return (vals, idxs), ctx
 
     def decompress(self, tensors, ctx):
@@ -134,6 +149,8 @@ class IndexCompressor(_Wrapper):
             with _Timer(self.bench, 'idx_decompression', vals.device):
                 vals, idxs, shape = self.idx_compressor.decompress((vals, idxs, shape), self.params)
             _report_volume(self.params, tensors, shape)
+        else:
+            idxs = _host_idx(idxs)
         return self.sparsifier.decompress((vals, idxs), shape)
 
 
@@ -175,7 +192,12 @@ class DeepReduce(_Wrapper):
                 new_idxs = torch.arange(vals.numel(), device=vals.device)
                 vals_c, mapping, shape = self.val_compressor.compress((vals, new_idxs, shape), self.params)
                 n_map = mapping.numel()
-                if self.pack_mapping:
+                if self.val_compressor.order_preserving:
+                    # the i-th value belongs to the i-th decoded index: there is no permutation to ship (the
+                    # reference always sends `mapping`, :267; the paper's BF+QSGD volumes do not include one)
+                    mapping = torch.empty(0, dtype=torch.uint8 if self.pack_mapping else mapping.dtype,
+                                          device=mapping.device)
+                elif self.pack_mapping:
                     mapping = bitpack.pack(mapping, max_val=max(n_map - 1, 1))
                 if head is not None:
                     # K rides in front of the mapping blob as 4 extra bytes / one extra entry
@@ -184,6 +206,8 @@ class DeepReduce(_Wrapper):
                     mapping = torch.cat([extra.to(mapping.device), mapping])
                 ctx = shape
                 tensors = (vals_c, idxs_c, mapping)
+            else:
+                tensors = (vals, _wire_idx(idxs, tensor.numel()))
         return tensors, ctx
 
     def decompress(self, tensors, ctx):
@@ -200,9 +224,13 @@ class DeepReduce(_Wrapper):
                         head, mapping = mapping[:4].contiguous().view(torch.float32), mapping[4:]
                     else:
                         head, mapping = mapping[:1].float(), mapping[1:]
-                if self.pack_mapping:
-                    mapping = bitpack.unpack(mapping)
-                vals, mapping, _ = self.val_compressor.decompress((vals_c, mapping, shape), self.params)
+                if self.val_compressor.order_preserving:
+                    vals, _, _ = self.val_compressor.decompress((vals_c, None, shape), self.params)
+                    mapping = torch.arange(vals.numel(), device=vals.device)
+                else:
+                    if self.pack_mapping:
+                        mapping = bitpack.unpack(mapping)
+                    vals, mapping, _ = self.val_compressor.decompress((vals_c, mapping, shape), self.params)
                 carrier = vals.new_zeros(mapping.numel()) if head is None else torch.cat(
                     [head.to(vals.dtype), vals.new_zeros(mapping.numel())])
                 _, idxs, _ = self.idx_compressor.decompress((carrier, idxs_c, shape), self.params)
@@ -214,6 +242,7 @@ class DeepReduce(_Wrapper):
                 vals, idxs = vals[:n], idxs[:n]
             else:
                 vals, idxs = tensors
+                idxs = _host_idx(idxs)
         if shape.numel() > self.min_numel:
             _report_volume(self.params, tensors, shape)
         return self.sparsifier.decompress((vals, idxs), shape)

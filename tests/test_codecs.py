@@ -50,7 +50,11 @@ def test_polyfit_equals_monomial_least_squares():
 def test_polyfit_roundtrip_error():
     g, vals, idx, shape = _sparse()
     w, idx2, _ = polyfit.PolyFit.compress((vals, idx, shape), {})
-    assert w.numel() == 6 * MAX_SEGMENTS + 1 and w.dtype == torch.float32
+    # K = 368: only the 1/5 and 1/10 ratios can yield segments > 30 -> at most 2*2+2 rows, a function of K alone
+    assert polyfit.seg_rows(idx.numel()) == 6 and w.numel() == 6 * polyfit.seg_rows(idx.numel()) + 1
+    assert w.dtype == torch.float32 and polyfit.seg_rows(10 ** 7) == MAX_SEGMENTS
+    for p_ in (0, 1, 100, 184, 367, 368):          # never more segments than rows, whatever the sign split
+        assert len(polyfit.get_segments(368, p_)) <= 6
     v, idx3, _ = polyfit.PolyFit.decompress((w, idx2, shape), {})
     dense = torch.zeros(shape.numel()); dense[idx3] = v
     ref = torch.zeros(shape.numel()); ref[idx] = vals

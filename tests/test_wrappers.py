@@ -48,7 +48,10 @@ def test_small_tensor_bypass():
     g = torch.randn(1000)
     grc = dr.deepreduce_from_params(dict(BASE, deepreduce='index', index='bloom'))
     (vals, idxs), ctx = grc.compressor.compress(g, 'b')
-    assert idxs.dtype == torch.int64 and idxs.numel() == 10             # raw pairs for <= 1000 elements (:68,115)
+    assert idxs.numel() == 10 and vals.numel() == 10                    # raw pairs for <= 1000 elements (:68,115)
+    assert idxs.dtype == torch.int32                                    # 32-bit keys on the wire (paper accounting)
+    out = grc.compressor.decompress((vals, idxs), ctx)
+    assert torch.equal(out.flatten()[idxs.long()], vals) and int((out != 0).sum()) == 10
 
 
 def test_both_is_fp_aware_and_packed():
@@ -69,6 +72,7 @@ def test_both_is_fp_aware_and_packed():
     dict(deepreduce='value', value='gzip'), dict(deepreduce='index', index='rle'),
     dict(deepreduce='index', index='huffman'), dict(deepreduce='index', index='integer'),
     dict(deepreduce='both', value='qsgd', policy='p0'), dict(deepreduce='both', value='qsgd', index='rle'),
+    dict(deepreduce='both', value='gzip'), dict(deepreduce='both', value='gzip', index='rle'), dict(deepreduce='value', value='dexp'),
     dict(deepreduce='index', index='bloom', policy='p0'), dict(deepreduce='index', index='bloom', policy='conflict_sets'),
     dict(compressor='threshold', threshold=1.5, memory='none', deepreduce='index', index='bloom', policy='p0', fpr=0.01),
     dict(compressor='threshold', threshold=1.5, memory='none', deepreduce='both', index='bloom', policy='random', fpr=0.01, value='qsgd'),
@@ -83,11 +87,32 @@ def test_configs_run_and_preserve_mass(cfg):
     assert torch.nn.functional.cosine_similarity(out[nz], g[nz], dim=0) > 0.9
 
 
+def test_wire_volumes_follow_the_papers_accounting():
+    """32-bit keys, no mapping for order-preserving value codecs, coefficient rows sized by K (profiles/volume_table.md)."""
+    from deepreduce_b200.grace import tensor_bits
+    g = _grad()                                                            # d = 36 864, K = 368
+    d, K = g.numel(), 368
+
+    def rel(**cfg):
+        tensors, _ = dr.deepreduce_from_params(dict(BASE, **cfg)).compressor.compress(g.clone(), 'w')
+        return tensors, tensor_bits(list(tensors)) / (32.0 * d)
+
+    (coef, idx), v = rel(deepreduce='value', value='polyfit')
+    assert idx.dtype == torch.int32 and coef.numel() == 6 * 6 + 1          # 6 rows for K = 368, not 22
+    assert v < 0.62 * (64.0 * K) / (32.0 * d)                              # paper: Fit-Poly ~40 % below Top-r
+    (q, filt, mapping), v = rel(deepreduce='both', value='qsgd')
+    assert mapping.numel() == 0                                            # QSGD keeps the order: no permutation shipped
+    assert v < 0.5 * (64.0 * K) / (32.0 * d)
+    (_, _, mapping), _ = rel(deepreduce='both', value='polyfit')
+    assert mapping.numel() > 0                                             # the fit sorts: its permutation must travel
+
+
 def test_lossless_modes_equal_plain_topk():
     g = _grad(seed=3)
     plain = dr.grace_from_params(dict(BASE, memory='none')).step(g.clone(), 'w')
     for cfg in (dict(deepreduce='value', value='gzip'), dict(deepreduce='index', index='rle'),
-                dict(deepreduce='index', index='huffman'), dict(deepreduce='index', index='integer')):
+                dict(deepreduce='index', index='huffman'), dict(deepreduce='index', index='integer'),
+                dict(deepreduce='both', value='gzip', index='rle')):
         out = dr.deepreduce_from_params(dict(BASE, memory='none', **cfg)).step(g.clone(), 'w')
         assert torch.equal(out, plain), cfg
 
