@@ -11,7 +11,7 @@ def save_checkpoint(path: str, trainer) -> None:
 
 
 def load_checkpoint(path: str, trainer) -> None:
-    ck = torch.load(path, map_location="cpu", weights_only=False)
+    ck = torch.load(path, map_location="cpu", weights_only=True)
     trainer.model.load_state_dict(ck["model"])
     trainer.opt.load_state_dict(ck["opt"])
     trainer.ddp.load_state_dict(ck["ddp"])
