@@ -47,3 +47,54 @@ def test_compressed_training_tracks_dense():
     no_mem = _train(dict(BASE, memory='none', min_numel=100, deepreduce='index', index='bloom'))
     with_mem = _train(dict(BASE, min_numel=100, deepreduce='index', index='bloom'))
     assert sum(no_mem[-10:]) > 1.3 * sum(with_mem[-10:])                    # measured: 0.0070 vs 0.0023 (dense 0.0028)
+
+
+@pytest.mark.timeout(600)
+def test_fused_engine_semantics_converge_two_ranks():
+    """The bucket-level specification of the fused kernel (`engine_oracle`: 22-bit threshold select, bloom + occupancy
+    hint, FP-aware values, residual memory, average over ranks) drives a 2-rank data-parallel run to the dense loss."""
+    from deepreduce_b200.parallel import BucketPlan, engine_oracle
+    x, y = _data(n=1024, seed=1)
+
+    def run(mode, steps=120):
+        torch.manual_seed(0)
+        model = nn.Sequential(nn.Linear(64, 128), nn.ReLU(), nn.Linear(128, 64), nn.ReLU(), nn.Linear(64, 8))
+        ps = list(model.parameters())
+        plan = None
+        if mode != "dense":
+            plan = BucketPlan([p.numel() for p in ps], compress_ratio=0.05, min_numel=100, **mode)
+            resid = [torch.zeros(plan.total_elems) for _ in range(2)]
+        losses = []
+        for s in range(steps):
+            grads, ls = [], 0.0
+            for r in range(2):
+                i = ((2 * s + r) * 64) % 1024
+                model.zero_grad()
+                loss = nn.functional.cross_entropy(model(x[i:i + 64]), y[i:i + 64])
+                loss.backward()
+                ls += float(loss.detach()) / 2
+                if plan is None:
+                    grads.append([p.grad.clone() for p in ps])
+                else:
+                    flat = torch.zeros(plan.total_elems)
+                    for v, p in zip(plan.views(flat), ps):
+                        v.copy_(p.grad.reshape(v.shape))
+                    grads.append(flat)
+            if plan is None:
+                agg = [(a + b) / 2 for a, b in zip(*grads)]
+            else:
+                out, resid, _ = engine_oracle(plan, grads, resid, epoch=s + 1)
+                agg = [v.clone().reshape(p.shape) for v, p in zip(plan.views(out), ps)]
+            with torch.no_grad():
+                for p, g in zip(ps, agg):
+                    p -= 0.1 * g
+            losses.append(ls)
+        return losses
+
+    dense = run("dense")
+    d_end = sum(dense[-10:]) / 10
+    for mode in (dict(index="bloom"), dict(index="bloom", policy="p0"), dict(index="rle"), dict(index=None),
+                 dict(index="bloom", value="polyfit", poly_min_k=64), dict(index="bloom", value="qsgd")):
+        comp = run(mode)
+        c_end = sum(comp[-10:]) / 10
+        assert c_end < 0.3 * comp[0] and c_end < 2.0 * d_end + 0.15, (mode, d_end, c_end)
