@@ -86,8 +86,18 @@ def _model_for(d: int):
     return lengths, _canonical(lengths)
 
 
-def huffman_encode(data: np.ndarray, lengths: np.ndarray, codes: np.ndarray) -> np.ndarray:
-    """uint8[n] -> uint8 bitstream (MSB-first), 4-byte LE symbol count header."""
+def _native():
+    from .. import ops
+    return ops._cpu_mod if ops.has_cpu_native() and hasattr(ops._cpu_mod, "huffman_decode") else None
+
+
+def huffman_encode(data: np.ndarray, lengths: np.ndarray, codes: np.ndarray, native: bool = True) -> np.ndarray:
+    """uint8[n] -> uint8 bitstream (MSB-first), 4-byte LE symbol count header.  Uses the C++ coder of
+    ``_dr_cpu`` when it is built (``native=False`` forces the numpy reference; both produce the same bytes)."""
+    m = _native() if native else None
+    if m is not None:
+        return m.huffman_encode(np.ascontiguousarray(data, dtype=np.uint8), np.ascontiguousarray(lengths, dtype=np.int64),
+                                np.ascontiguousarray(codes, dtype=np.uint64))
     n = data.size
     L = lengths[data]
     C = codes[data]
@@ -103,7 +113,11 @@ def huffman_encode(data: np.ndarray, lengths: np.ndarray, codes: np.ndarray) -> 
     return np.concatenate([head, body])
 
 
-def huffman_decode(stream: np.ndarray, lengths: np.ndarray, codes: np.ndarray) -> np.ndarray:
+def huffman_decode(stream: np.ndarray, lengths: np.ndarray, codes: np.ndarray, native: bool = True) -> np.ndarray:
+    m = _native() if native else None
+    if m is not None:
+        return m.huffman_decode(np.ascontiguousarray(stream, dtype=np.uint8), np.ascontiguousarray(lengths, dtype=np.int64),
+                                np.ascontiguousarray(codes, dtype=np.uint64))
     n = int(stream[0]) | (int(stream[1]) << 8) | (int(stream[2]) << 16) | (int(stream[3]) << 24)
     bits = np.unpackbits(stream[4:])
     table = {(int(lengths[s]), int(codes[s])): s for s in range(256) if lengths[s] > 0}

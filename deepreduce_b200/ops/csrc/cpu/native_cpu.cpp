@@ -385,6 +385,72 @@ void write_csv(const std::string& path, py::array_t<double, py::array::c_style |
 }
 
 // ---------------------------------------------------------------------------
+// canonical Huffman over bytes (bitstream MSB-first, 4-byte LE symbol-count header) — the native twin of
+// codecs/lossless.py::huffman_encode / huffman_decode (reference pytorch/deepreduce.py:767-802 runs the pure-Python
+// `dahuffman` codec and rebuilds its model on every call)
+// ---------------------------------------------------------------------------
+py::array_t<uint8_t> huffman_encode(py::array_t<uint8_t, py::array::c_style | py::array::forcecast> data,
+                                    py::array_t<int64_t, py::array::c_style | py::array::forcecast> lengths,
+                                    py::array_t<uint64_t, py::array::c_style | py::array::forcecast> codes) {
+  if (lengths.size() != 256 || codes.size() != 256) throw std::runtime_error("need 256 lengths / codes");
+  const uint8_t* d = data.data();
+  const int64_t* L = lengths.data();
+  const uint64_t* C = codes.data();
+  const size_t n = (size_t)data.size();
+  uint64_t total = 0;
+  for (size_t i = 0; i < n; ++i) {
+    if (L[d[i]] <= 0) throw std::runtime_error("symbol without a code");
+    total += (uint64_t)L[d[i]];
+  }
+  std::vector<uint8_t> out(4 + (total + 7) / 8, 0);
+  out[0] = n & 0xFF; out[1] = (n >> 8) & 0xFF; out[2] = (n >> 16) & 0xFF; out[3] = (n >> 24) & 0xFF;
+  uint64_t bit = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const int len = (int)L[d[i]];
+    const uint64_t code = C[d[i]];
+    for (int b = len - 1; b >= 0; --b, ++bit)
+      if ((code >> b) & 1u) out[4 + (bit >> 3)] |= (uint8_t)(0x80u >> (bit & 7));
+  }
+  py::array_t<uint8_t> r(out.size());
+  std::memcpy(r.mutable_data(), out.data(), out.size());
+  return r;
+}
+
+py::array_t<uint8_t> huffman_decode(py::array_t<uint8_t, py::array::c_style | py::array::forcecast> stream,
+                                    py::array_t<int64_t, py::array::c_style | py::array::forcecast> lengths,
+                                    py::array_t<uint64_t, py::array::c_style | py::array::forcecast> codes) {
+  if (lengths.size() != 256 || codes.size() != 256) throw std::runtime_error("need 256 lengths / codes");
+  if (stream.size() < 4) throw std::runtime_error("truncated huffman stream");
+  const uint8_t* s = stream.data();
+  const size_t n = (size_t)s[0] | ((size_t)s[1] << 8) | ((size_t)s[2] << 16) | ((size_t)s[3] << 24);
+  // canonical decoding: per length, first code and the symbols of that length in code order
+  int max_len = 0;
+  for (int i = 0; i < 256; ++i) max_len = std::max<int>(max_len, (int)lengths.data()[i]);
+  std::vector<std::vector<std::pair<uint64_t, uint8_t>>> by_len(max_len + 1);
+  for (int i = 0; i < 256; ++i)
+    if (lengths.data()[i] > 0) by_len[lengths.data()[i]].push_back({codes.data()[i], (uint8_t)i});
+  for (auto& v : by_len) std::sort(v.begin(), v.end());
+  py::array_t<uint8_t> out(n);
+  uint8_t* o = out.mutable_data();
+  const uint64_t total_bits = (uint64_t)(stream.size() - 4) * 8;
+  uint64_t bit = 0, code = 0;
+  int len = 0;
+  size_t j = 0;
+  while (j < n) {
+    if (bit >= total_bits) throw std::runtime_error("huffman stream ended early");
+    code = (code << 1) | ((s[4 + (bit >> 3)] >> (7 - (bit & 7))) & 1u);
+    ++bit; ++len;
+    if (len > max_len) throw std::runtime_error("invalid huffman code");
+    const auto& v = by_len[len];
+    if (!v.empty() && code >= v.front().first && code <= v.back().first) {
+      const size_t k = (size_t)(code - v.front().first);          // canonical: codes of one length are consecutive
+      if (k < v.size() && v[k].first == code) { o[j++] = v[k].second; code = 0; len = 0; }
+    }
+  }
+  return out;
+}
+
+// ---------------------------------------------------------------------------
 // Bloom filter object for Python (the surface the reference's ops use of bloom::OrdinaryBloomFilter,
 // reference tensorflow/bloom_filter_compression.cc:102-110,206: insert / query / raw words / byte and hash counts /
 // hash positions / false-positive count over a universe / construction from received raw words)
@@ -443,4 +509,6 @@ PYBIND11_MODULE(_dr_cpu, m) {
   m.def("int_encode", &int_encode);
   m.def("int_decode", &int_decode);
   m.def("write_csv", &write_csv);
+  m.def("huffman_encode", &huffman_encode);
+  m.def("huffman_decode", &huffman_decode);
 }

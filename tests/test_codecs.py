@@ -229,3 +229,30 @@ def test_native_bloomfilter_object_matches_oracle():
     assert f.compute_false_positives(d, idx.numpy()) == positives.numel() - idx.numel()
     g = ops.cpu.BloomFilter.from_words(f.words(), k, m_bits, spec.DEFAULT_SEED)    # receiver side: from raw words
     assert np.array_equal(g.query(np.arange(d)), np.isin(np.arange(d), positives.numpy()))
+
+
+def test_native_huffman_matches_numpy_reference():
+    import numpy as np
+    import pytest
+    from deepreduce_b200 import ops
+    from deepreduce_b200.codecs import lossless as L
+    if L._native() is None:
+        pytest.skip("native host extension not built")
+    rng = np.random.default_rng(3)
+    for d in (1000, 36864, 2359296):
+        lengths, codes = L._model_for(d)
+        for n in (0, 1, 7, 5000):
+            data = np.sort(rng.integers(0, d, size=n)).astype(np.int32).view(np.uint8)
+            a = L.huffman_encode(data, lengths, codes, native=True)
+            b = L.huffman_encode(data, lengths, codes, native=False)
+            assert np.array_equal(a, b)
+            assert np.array_equal(L.huffman_decode(a, lengths, codes, native=True), data)
+            assert np.array_equal(L.huffman_decode(a, lengths, codes, native=False), data)
+    # a skewed model (long codes) and corrupted input
+    freq = np.ones(256, dtype=np.int64); freq[0] = 10 ** 9; freq[1] = 10 ** 6
+    lengths = L._code_lengths(freq); codes = L._canonical(lengths)
+    data = rng.integers(0, 256, size=2000).astype(np.uint8)
+    enc = L.huffman_encode(data, lengths, codes)
+    assert np.array_equal(L.huffman_decode(enc, lengths, codes), data)
+    with pytest.raises(RuntimeError):
+        ops._cpu_mod.huffman_decode(enc[:20], lengths, codes.astype(np.uint64))      # truncated stream
