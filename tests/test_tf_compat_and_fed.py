@@ -67,3 +67,38 @@ def test_federated_round_reduces_loss_and_volume():
     assert losses[-1] < losses[0]
     v = fed.volumes()
     assert 0 < v["c2s_relative_volume"] < 0.35 and 0 < v["s2c_relative_volume"] < 0.35
+
+
+def test_tf_helper_bases_sparsifiers_and_op_sizing():
+    """Remaining TF-side helpers (tensorflow/deepreduce.py:146-156,273-298; bloom_filter_compression.cc:85-99)."""
+    import math
+
+    import torch
+
+    from deepreduce_b200 import spec
+    from deepreduce_b200 import tf_compat as tfc
+    from deepreduce_b200.codecs.bloom_cpu import tf_bloom_sizes
+    H = tfc.Values_Approximation_Helper
+    X = torch.arange(1, 6, dtype=torch.float64)
+    assert torch.allclose(H.polynomial_basis(X, 3), X ** 3)
+    assert torch.allclose(H.exp_basis(X, 2.0, -0.5), 2.0 * torch.exp(-0.5 * X))
+    assert torch.allclose(H.logit_basis(X, 1.5, 5), 1.5 * torch.log(X / (6 - X)))
+    B = tfc.BloomFilterCompressor
+    g = torch.tensor([0.1, -5.0, 0.3, 4.0, -0.2, 0.0, 2.5, -0.05])
+    assert B.topk_indices(g, 3).tolist() == [1, 3, 6]                       # ascending positions of the top-3 |g|
+    assert B.threshold_indices(g, {"threshold_val": 1.0}).tolist() == [1, 3, 6]
+    assert B.threshold_indices(g, {"threshold_val": 99.0}).tolist() == [1]  # clamped to max |g|
+    B.global_step = 0
+    a = B.randomk_indices("conv1", 1000, 10)
+    B.global_step = 0
+    b = B.randomk_indices("conv1", 1000, 10)
+    c = B.randomk_indices("conv1", 1000, 10)                                # next step: a different draw
+    assert a.tolist() == b.tolist() and a.tolist() != c.tolist()
+    assert a.numel() == 10 and a.unique().numel() == 10 and int(a.max()) < 1000 and (a[1:] > a[:-1]).all()
+    # Python-side sizing uses true division for h, the C++ op integer division (SURVEY Appendix B.1)
+    for K, fpr in ((368, 0.001), (23592, 0.01), (10, 0.5)):
+        m, h = spec.bloom_configuration(K, fpr)
+        m2, h2 = tf_bloom_sizes(K, fpr)
+        assert m == m2 and m >= 1
+        assert h == math.ceil((m * 8 / K) * math.log(2)) and h2 == max(1, math.ceil(((m * 8) // K) * math.log(2)))
+        assert h2 <= h
