@@ -29,6 +29,9 @@ def double_exponential_fit(y: torch.Tensor):
     """y: [K] (ascending |values|) -> (a, b, p, q) float64 on x_i = i/K."""
     K = y.numel()
     y = y.double()
+    if K == 0:                                             # empty selection: the zero curve
+        z = torch.zeros((), dtype=torch.float64, device=y.device)
+        return z, z, z, z
     x = torch.arange(1, K + 1, dtype=torch.float64, device=y.device) / K
     dx = 1.0 / K
     S = _cumtrapz(y, dx)
@@ -57,6 +60,8 @@ def double_exponential_fit(y: torch.Tensor):
 
 def double_exponential_eval(coef: torch.Tensor, K: int) -> torch.Tensor:
     a, b, p, q = coef.double().unbind()
+    if K == 0:
+        return torch.empty(0, dtype=torch.float32, device=coef.device)
     x = torch.arange(1, K + 1, dtype=torch.float64, device=coef.device) / K
     return (a * torch.exp(p * x) + b * torch.exp(q * x)).float()
 

@@ -37,6 +37,8 @@ class Gzip(SparseCompressor):
     def decompress(gzip_sparse_tensor, params):
         wire, idxs, shape = gzip_sparse_tensor
         raw = zlib.decompress(wire.cpu().numpy().tobytes())
+        if len(raw) == 0:                                  # empty selection (threshold sparsifier on a zero gradient)
+            return torch.empty(0, dtype=torch.float32, device=wire.device), idxs, shape
         vals = torch.frombuffer(bytearray(raw), dtype=torch.float32).to(wire.device)
         return vals, idxs, shape
 
