@@ -56,3 +56,51 @@ def test_resnet20_world2_gloo(cfg):
     assert all(l == l and l < 20 for l in ret["losses"])
     if cfg['compressor'] == 'topk':
         assert ret["bytes"] < 0.05 * ret["dense"]          # < 5 % of the dense volume on the wire
+
+
+def _fuzz_worker(rank, world, port, n_iter, seed, ret):
+    import random
+    import warnings
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    warnings.simplefilter("ignore")
+    import deepreduce_b200 as dr
+    rnd = random.Random(seed)                      # the same configuration stream on every rank
+    vals, idxs = ['polyfit', 'qsgd', 'gzip', 'dexp', 'polyfit_cpu'], ['bloom', 'rle', 'huffman', 'integer', 'bloom_cpu']
+    done = 0
+    for it in range(n_iter):
+        d = rnd.choice([7, 999, 1001, 4097, 9001])
+        comp, extra = rnd.choice([('topk', {}), ('threshold', {'threshold': 1.0}), ('randomk', {})])
+        mode = rnd.choice(['value', 'index', 'both', None])
+        cfg = {'compressor': comp, 'memory': rnd.choice(['none', 'residual']), 'communicator': 'allgather',
+               'compress_ratio': rnd.choice([0.01, 0.1, 0.5]), 'value': rnd.choice(vals), 'index': rnd.choice(idxs),
+               'policy': rnd.choice(['leftmost', 'random', 'p0', 'conflict_sets']), 'min_numel': rnd.choice([0, 1000]),
+               **extra}
+        if mode:
+            cfg['deepreduce'] = mode
+        kind = rnd.choice(['randn', 'zero_on_rank1', 'scaled'])
+        g = torch.randn(d, generator=torch.Generator().manual_seed(1000 * it + rank))
+        if kind == 'zero_on_rank1' and rank == 1:
+            g = torch.zeros(d)                     # threshold sparsifier -> an empty selection on one rank only
+        if kind == 'scaled':
+            g = g * (0.1 if rank == 0 else 3.0)    # very different per-rank selection sizes
+        out = dr.deepreduce_from_params(cfg).step(g.clone(), 'w')
+        assert out.shape == g.shape and torch.isfinite(out).all(), cfg
+        gathered = [torch.empty_like(out) for _ in range(world)]
+        dist.all_gather(gathered, out)
+        assert all(torch.equal(gathered[0], o) for o in gathered), ("ranks disagree", cfg)
+        done += 1
+    if rank == 0:
+        ret["done"] = done
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_fuzz_allgather_variable_sizes_world2():
+    """Per-rank payload sizes differ (threshold sparsifier, P0, lossless codecs), one rank may select nothing:
+    the size-gather / pad / slice path of the Allgather communicator must hand every rank the same aggregate."""
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_fuzz_worker, args=(2, _free_port(), 60, 0, ret), nprocs=2, join=True)
+    assert ret["done"] == 60
