@@ -201,6 +201,65 @@ def engine_oracle(plan: BucketPlan, grads: Sequence[torch.Tensor], resids: Seque
     return out, new_resids, slots
 
 
+def decode_slot_oracle(plan: BucketPlan, slot, *, seed=spec.DEFAULT_SEED) -> torch.Tensor:
+    """Receiver-side specification: rebuild one sender's dense contribution (flat, ``plan.total_elems``, unscaled)
+    from NOTHING but the plan and the words of its slot — what ``phase_decode`` does per (tile, sender).  Together
+    with ``encode_tensor_oracle`` this pins the wire format from both ends: the tests check that the sum of the
+    decoded slots equals the aggregate ``engine_oracle`` builds on the sender side."""
+    a = slot.detach().cpu().numpy().view(np.uint32) if torch.is_tensor(slot) else np.asarray(slot, dtype=np.uint32)
+    assert int(a[0]) == MAGIC and int(a[2]) == len(plan.tensors), "not a slot of this plan"
+    out = torch.zeros(plan.total_elems, dtype=torch.float32)
+    for ti, t in enumerate(plan.tensors):
+        d0 = SLOT_HEADER_WORDS + DYN_WORDS * ti
+        n_sel, cutoff = int(a[d0]), int(a[d0 + 1])
+        if n_sel == 0:
+            continue
+        if t.mode == MODE_BLOOM:
+            words = torch.from_numpy(a[t.off_filter:t.off_filter + t.n_filter_words].view(np.int32).copy())
+            pos = bloom_query_oracle(words, t.numel, t.n_hash, t.m_bits, seed)          # ascending positives of the universe
+            if t.off_hint:                                                               # only inside occupied 32-element groups
+                hint = a[t.off_hint:t.off_hint + 4 * t.n_tiles]
+                grp = pos // 32                                                          # group id: tile*128 + (e // 32)
+                tile, gi = grp // 128, grp % 128
+                bit = (torch.from_numpy(hint.astype(np.int64))[tile * 4 + gi // 32] >> (gi % 32)) & 1
+                pos = pos[bit.bool()]
+            if cutoff != 0xFFFFFFFF:
+                pos = pos[pos <= cutoff]
+            idx = pos[:n_sel]
+            # the per-tile prefix table must agree with what the receiver recomputes (the kernel starts ranks from it)
+            starts = torch.arange(t.n_tiles, dtype=torch.int64) * spec.TILE
+            pre = torch.from_numpy(a[t.off_prefix:t.off_prefix + t.n_tiles].astype(np.int64))
+            assert torch.equal(torch.minimum(torch.searchsorted(pos, starts), torch.tensor(n_sel)), pre), t.name
+        elif t.mode == MODE_RLE:
+            cnt = a[t.off_prefix:t.off_prefix + (t.n_tiles + 1) // 2].view(np.uint16)[:t.n_tiles].astype(np.int64)
+            assert int(cnt.sum()) == n_sel, t.name
+            local = rle_unpack12(a[t.off_idx:t.off_idx + rle_stream_words(t.val_cap)], n_sel)
+            idx = torch.from_numpy(np.repeat(np.arange(t.n_tiles, dtype=np.int64), cnt) * spec.TILE + local)
+        else:
+            idx = torch.from_numpy(a[t.off_idx:t.off_idx + n_sel].astype(np.int64))
+        n = int(idx.numel())
+        if t.vmode == 1:
+            from ..codecs.polyfit import MAX_SEGMENTS, get_segments, polyfit_eval_oracle
+            nc = MAX_SEGMENTS * (t.poly_degree + 1)
+            coef = torch.from_numpy(a[t.off_coef:t.off_coef + nc].view(np.float32).copy())
+            num_pos, n_fit = int(a[t.off_coef + nc]), int(a[t.off_coef + nc + 1])
+            curve = polyfit_eval_oracle(coef, get_segments(n_fit, num_pos), t.poly_degree)
+            if t.rank_u32:
+                rank = a[t.off_rankmap:t.off_rankmap + n].astype(np.int64)
+            else:
+                rank = a[t.off_rankmap:t.off_rankmap + (n + 1) // 2].view(np.uint16)[:n].astype(np.int64)
+            vals = curve[torch.from_numpy(rank)]
+        elif t.vmode == 2:
+            from ..codecs.qsgd import qsgd_decode_oracle
+            norms = torch.from_numpy(a[t.off_coef:t.off_coef + (n + 511) // 512].view(np.float32).copy())
+            lvl = torch.from_numpy(a[t.off_rankmap:t.off_rankmap + (n + 3) // 4].view(np.int8)[:n].astype(np.int64))
+            vals = qsgd_decode_oracle(lvl, norms, int(t.poly_degree), 512)
+        else:
+            vals = torch.from_numpy(a[t.off_vals:t.off_vals + n].view(np.float32).copy())
+        out[t.elem_off:t.elem_off + t.numel].index_add_(0, idx, vals.float())
+    return out
+
+
 # ---------------------------------------------------------------------------
 # engine
 # ---------------------------------------------------------------------------

@@ -1,4 +1,5 @@
 """Bucket plan + engine oracle (CPU): the specification the fused kernel is tested against."""
+import pytest
 import numpy as np
 import torch
 
@@ -223,3 +224,38 @@ def test_stage2_layout_never_overflows_by_construction(monkeypatch):
     assert plan.arena_words(1, True) == plan.arena_words(1, False)
     monkeypatch.setenv("DR_S2_SLACK", "2")
     assert plan.stage2_layout(8)[0] == ((2 * k_total + 8192 + 3) // 4) * 4
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_wire_format_is_self_sufficient(seed):
+    """Sender spec (`engine_oracle`) vs an independent receiver (`decode_slot_oracle`, slot words + plan only):
+    every mode, hint on/off, P0, sizes around tile boundaries, ties / sparse gradients, 1-3 ranks, two steps."""
+    import random
+
+    from deepreduce_b200.parallel import decode_slot_oracle
+    rnd = random.Random(seed)
+    for it in range(25):
+        sizes = [rnd.choice([1, 2, 10, 64, 999, 1000, 1001, 4095, 4096, 4097, 8193, 20000, 50000])
+                 for _ in range(rnd.randint(1, 5))]
+        mode = rnd.choice([dict(index='bloom'), dict(index='bloom', policy='p0'), dict(index='bloom', hint=False),
+                           dict(index='rle'), dict(index=None), dict(index='bloom', value='polyfit', poly_min_k=32),
+                           dict(index='bloom', value='qsgd')])
+        W = rnd.choice([1, 2, 3])
+        plan = BucketPlan(sizes, compress_ratio=rnd.choice([0.001, 0.01, 0.1, 0.5]), min_numel=rnd.choice([0, 1000]), **mode)
+        kind = rnd.choice(['randn', 'ties', 'sparse'])
+        gen = torch.Generator().manual_seed(100 * seed + it)
+
+        def mk():
+            g = torch.randn(plan.total_elems, generator=gen)
+            if kind == 'ties':
+                g = torch.randint(-2, 3, (plan.total_elems,), generator=gen).float()
+            if kind == 'sparse':
+                g[torch.rand(plan.total_elems, generator=gen) < 0.99] = 0
+            return g
+        grads = [mk() for _ in range(W)]
+        res = [torch.zeros(plan.total_elems) for _ in range(W)]
+        for step in range(2):
+            out, res, slots = engine_oracle(plan, grads, res, epoch=step + 1)
+            rec = sum(decode_slot_oracle(plan, s) for s in slots) / W
+            tol = (1e-4 if 'value' in mode else 1e-6) * float(out.abs().max() + 1e-30)
+            assert torch.allclose(rec, out, atol=tol, rtol=1e-5), (sizes, mode, W, kind, step)
