@@ -7,6 +7,7 @@ Tables 2/4/5 can be regenerated with any DeepReduce configuration.
 from __future__ import annotations
 
 import copy
+import time
 from typing import Callable, Dict, List
 
 import torch
@@ -28,14 +29,28 @@ class _Link:
         self.memory = grc.memory if params.get('memory', 'residual') == 'residual' else ResidualMemory(0.0, 1.0)
         self.bits = 0
         self.dense_bits = 0
+        self.encode_s = 0.0          # sender side: compensate + compress + memory update (paper Table 2 "encode")
+        self.decode_s = 0.0          # receiver side: decompress ("decode")
+
+    @staticmethod
+    def _now(t: torch.Tensor) -> float:
+        if t.is_cuda:
+            torch.cuda.synchronize(t.device)
+        return time.perf_counter()
 
     def send(self, tensor: torch.Tensor, name: str) -> torch.Tensor:
+        t0 = self._now(tensor)
         t = self.memory.compensate(tensor, name)
         wire, ctx = self.compressor.compress(t, name)
         self.memory.update(t, name, self.compressor, wire, ctx)
+        t1 = self._now(tensor)
         self.bits += tensor_bits(list(wire))
         self.dense_bits += tensor.numel() * 32
-        return self.compressor.decompress(wire, ctx).view_as(tensor)
+        out = self.compressor.decompress(wire, ctx).view_as(tensor)
+        t2 = self._now(tensor)
+        self.encode_s += t1 - t0
+        self.decode_s += t2 - t1
+        return out
 
     def relative_volume(self) -> float:
         return self.bits / max(self.dense_bits, 1)
@@ -86,3 +101,12 @@ class FederatedAveraging:
         s2c = sum(l.bits for l in self.s2c) / max(1, sum(l.dense_bits for l in self.s2c))
         c2s = sum(l.bits for l in self.c2s) / max(1, sum(l.dense_bits for l in self.c2s))
         return {"s2c_relative_volume": s2c, "c2s_relative_volume": c2s}
+
+    def timings(self, rounds: int = 1):
+        """Mean codec wall time per client per round (seconds): the rows of the paper's Table 2
+        (client encode = C2S compress, client decode = S2C decompress; server side likewise)."""
+        n = max(1, self.n_clients * max(1, rounds))
+        return {"client_encode_s": sum(l.encode_s for l in self.c2s) / n,
+                "client_decode_s": sum(l.decode_s for l in self.s2c) / n,
+                "server_encode_s": sum(l.encode_s for l in self.s2c) / n,
+                "server_decode_s": sum(l.decode_s for l in self.c2s) / n}

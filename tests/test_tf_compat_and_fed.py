@@ -66,6 +66,8 @@ def test_federated_round_reduces_loss_and_volume():
     losses = [fed.round(batches(), torch.nn.functional.cross_entropy) for _ in range(12)]
     assert losses[-1] < losses[0]
     v = fed.volumes()
+    tm = fed.timings(rounds=12)
+    assert all(tm[k] > 0 for k in ('client_encode_s', 'client_decode_s', 'server_encode_s', 'server_decode_s'))
     assert 0 < v["c2s_relative_volume"] < 0.35 and 0 < v["s2c_relative_volume"] < 0.35
 
 
