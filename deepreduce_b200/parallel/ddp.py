@@ -112,6 +112,10 @@ class DeepReduceDDP:
             numels = [p.numel() for _, p in items]
             names = [n for n, _ in items]
             shapes = [tuple(p.shape) for _, p in items]
+            owner = list(range(len(items)))
+            if self.fused and self.params.get('split_numel'):      # opt-in: huge tensors enter the plan as tile-aligned chunks
+                from .plan import split_large
+                numels, names, shapes, owner = split_large(numels, names, shapes, int(self.params['split_numel']))
             if self.fused:
                 plan = BucketPlan(numels, names, shapes, compress_ratio=self.params.get('compress_ratio', 0.01),
                                   index=(self.params.get('index', 'bloom') if self.params.get('deepreduce') in ('index', 'both')
@@ -135,9 +139,13 @@ class DeepReduceDDP:
                 flat = torch.zeros(plan.total_elems, dtype=torch.float32, device=self.device)
                 views = plan.views(flat)
             self.flat.append(flat)
-            for (n, p), t in zip(items, plan.tensors):
+            first = {}
+            for j, o in enumerate(owner):
+                first.setdefault(o, plan.tensors[j])                # the first chunk of every parameter
+            for i, (n, p) in enumerate(items):
                 assert p.dtype == torch.float32, "flat buckets hold fp32 master gradients"
-                seg = flat[t.elem_off:t.elem_off + t.numel]
+                t = first[i]
+                seg = flat[t.elem_off:t.elem_off + p.numel()]        # chunks are tile multiples: contiguous
                 # the gradient view mirrors the parameter's own (dense) layout — e.g. channels_last conv
                 # weights — so fused optimizers see identical strides; the bucket is in storage order
                 p.grad = seg.as_strided(p.size(), p.stride()) if _is_dense(p) else seg.view(p.shape)

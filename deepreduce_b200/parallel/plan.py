@@ -40,6 +40,32 @@ def _align(x: int, a: int) -> int:
     return (x + a - 1) // a * a
 
 
+def split_large(numels, names, shapes, split_numel: Optional[int]):
+    """Opt-in chunking of huge tensors (params key ``'split_numel'``): a tensor with more than ``split_numel``
+    elements enters the plan as consecutive chunks of ``split_numel`` (rounded down to whole 4096-element tiles), each
+    with its own top-k, filter and header — so every bloom filter stays small enough to be staged in shared memory
+    (the 31 M-element BERT embedding needs a 560 KB filter as one tensor, 70 KB as eight chunks) and the selection of a
+    single giant tensor is spread over the bucket's tiles.  Chunks are tile multiples, hence contiguous in the flat
+    buffer: the parameter's gradient view spans them.  Semantics: top-k per chunk instead of per tensor (the reference
+    is per tensor) — which is why it is opt-in.  Returns (numels, names, shapes, owner): owner[j] = index of the
+    original tensor chunk j belongs to."""
+    if not split_numel:
+        return list(numels), list(names), list(shapes), list(range(len(numels)))
+    step = max(spec.TILE, (int(split_numel) // spec.TILE) * spec.TILE)
+    out_n, out_names, out_shapes, owner = [], [], [], []
+    for i, (d, nm, sh) in enumerate(zip(numels, names, shapes)):
+        d = int(d)
+        if d <= step:
+            out_n.append(d); out_names.append(nm); out_shapes.append(tuple(sh)); owner.append(i)
+            continue
+        off, c = 0, 0
+        while off < d:
+            n = min(step, d - off)
+            out_n.append(n); out_names.append(f"{nm}#{c}"); out_shapes.append((n,)); owner.append(i)
+            off += n; c += 1
+    return out_n, out_names, out_shapes, owner
+
+
 @dataclass
 class TensorPlan:
     name: str

@@ -259,3 +259,20 @@ def test_wire_format_is_self_sufficient(seed):
             rec = sum(decode_slot_oracle(plan, s) for s in slots) / W
             tol = (1e-4 if 'value' in mode else 1e-6) * float(out.abs().max() + 1e-30)
             assert torch.allclose(rec, out, atol=tol, rtol=1e-5), (sizes, mode, W, kind, step)
+
+
+def test_split_large_chunks_are_contiguous_tile_multiples():
+    from deepreduce_b200.parallel.plan import split_large
+    numels, names, shapes = [64, 31254528, 4096 * 3 + 5, 1000], ["b", "emb", "w", "s"], [(64,), (30522, 1024), (12293,), (1000,)]
+    n2, nm2, sh2, owner = split_large(numels, names, shapes, 4_000_000)
+    step = (4_000_000 // 4096) * 4096
+    assert sum(n2) == sum(numels) and owner == [0] + [1] * 8 + [2, 3]
+    assert n2[1:8] == [step] * 7 and n2[8] == 31254528 - 7 * step and nm2[1] == "emb#0" and sh2[9] == (12293,)
+    plan = BucketPlan(n2, nm2, sh2, compress_ratio=0.01)
+    emb = [t for t, o in zip(plan.tensors, owner) if o == 1]
+    for a, b in zip(emb[:-1], emb[1:]):
+        assert a.elem_off + a.numel == b.elem_off                     # no padding between chunks: one gradient view spans them
+    assert all(t.n_filter_words * 4 <= 88 * 1024 for t in emb)         # every chunk's filter fits the SMEM staging area
+    whole = BucketPlan([31254528], compress_ratio=0.01).tensors[0]
+    assert whole.n_filter_words * 4 > 227 * 1024                       # as one tensor it cannot
+    assert split_large(numels, names, shapes, None)[0] == numels
