@@ -249,3 +249,29 @@ class PolyFitCPU(SparseCompressor):
             coefficients = w[1 + nb:].reshape(len(breaks) - 1, -1)
         vals = restore_curve(coefficients, breaks)
         return torch.tensor(vals, dtype=torch.float32, device=idxs.device), idxs, shape
+
+
+# ----------------------------------------------------------------------------
+# monomial-basis helpers with the reference's module-level names (:308-347).  The codec above does not use them
+# (Gram basis, fp32, no explicit inverse); they exist so code written against the reference keeps working and so the
+# tests can show that both bases span the same fit.
+# ----------------------------------------------------------------------------
+def GetInputMatrix_Polynomial(N: int, degree: int, device=None) -> torch.Tensor:
+    """[N, degree+1] Vandermonde matrix on x = 1..N in float64 (reference :308-323)."""
+    x = torch.arange(1, int(N) + 1, dtype=torch.float64, device=device)
+    return torch.stack([x ** j for j in range(int(degree) + 1)], dim=1)
+
+
+def LeastSquares(X: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """argmin ||X a - y||: the reference forms (X'X)^-1 X'y with the small inverse on the CPU (:326-338); here a
+    rank-revealing solve on the input's own device (columns scaled first: x^5 reaches 1e25 for N = 1e5)."""
+    X = X.double()
+    scale = X.abs().amax(dim=0).clamp_min(1e-300)
+    sol = torch.linalg.lstsq(X / scale, y.double().reshape(-1, 1)).solution[:, 0]
+    return sol / scale
+
+
+def RestoreValues(N: int, coefficients: torch.Tensor) -> torch.Tensor:
+    """X(N) @ coefficients (reference :341-347)."""
+    c = coefficients.double().flatten()
+    return GetInputMatrix_Polynomial(N, c.numel() - 1, c.device) @ c
