@@ -1,4 +1,5 @@
-"""Small engine run for compute-sanitizer (memcheck / racecheck / synccheck): 2 steps, index and 'both' modes."""
+"""Small engine run for compute-sanitizer (memcheck / racecheck / synccheck): 2 steps in every fused mode
+(DR_OWN_FLAGS / DR_EMIT_COUNTS are honoured, so the option paths can be swept too)."""
 import os
 import sys
 
@@ -7,8 +8,9 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from deepreduce_b200.parallel import BucketEngine, BucketPlan, engine_oracle  # noqa: E402
 
-for value in (None, "polyfit"):
-    plan = BucketPlan([5000, 300, 40000, 9000], compress_ratio=0.02, value=value, poly_min_k=100)
+# (index codec, value codec): bloom, bloom + polyfit, bloom + QSGD, run-length, plain pairs
+for index, value in (("bloom", None), ("bloom", "polyfit"), ("bloom", "qsgd"), ("rle", None), (None, None)):
+    plan = BucketPlan([5000, 300, 40000, 9000], compress_ratio=0.02, index=index, value=value, poly_min_k=100)
     eng = BucketEngine(plan, device="cuda:0", world=1, rank=0, spin_limit=200_000_000)
     gen = torch.Generator().manual_seed(0)
     res = torch.zeros(plan.total_elems)
@@ -22,7 +24,7 @@ for value in (None, "polyfit"):
         eng.check_status()
         out, new_res, _ = engine_oracle(plan, [g], [res])
         ok = torch.allclose(eng.grad.cpu(), out, atol=1e-2 if value else 0, rtol=1e-2 if value else 0)
-        print(f"value={value} step={step} matches_oracle={ok}", flush=True)
+        print(f"index={index} value={value} step={step} matches_oracle={ok}", flush=True)
         res = eng.resid.cpu().clone() if value else new_res[0]
     eng.close()
 print("SANITIZE_RUN_DONE")
