@@ -23,7 +23,10 @@ for index, value in (("bloom", None), ("bloom", "polyfit"), ("bloom", "qsgd"), (
         torch.cuda.synchronize()
         eng.check_status()
         out, new_res, _ = engine_oracle(plan, [g], [res])
-        ok = torch.allclose(eng.grad.cpu(), out, atol=1e-2 if value else 0, rtol=1e-2 if value else 0)
+        if value == "qsgd":      # a reduction-order difference may flip a rounding decision: allow a few level flips
+            ok = float(((eng.grad.cpu() - out).abs() > 1e-3 * float(out.abs().max())).float().mean()) < 2e-3
+        else:
+            ok = torch.allclose(eng.grad.cpu(), out, atol=1e-2 if value else 0, rtol=1e-2 if value else 0)
         print(f"index={index} value={value} step={step} matches_oracle={ok}", flush=True)
         res = eng.resid.cpu().clone() if value else new_res[0]
     eng.close()
