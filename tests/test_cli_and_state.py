@@ -89,3 +89,35 @@ def test_diagnostic_writers(tmp_path):
     vals = (tmp_path / "1" / "step_20" / "2" / "values.csv").read_text().split()
     assert [float(v) for v in vals] == [0.0, 1.0, 2.0, 3.0]
     assert StepLogger(root, 2)(torch.zeros(2), torch.zeros(1), step=0) is False      # frequency 0 = never
+
+
+def test_bench_contract_pieces_on_cpu():
+    """bench.py: defaults (N=1, W >= 3), the roofline arithmetic, and the no-GPU answer on stdout as ONE JSON line."""
+    import importlib.util
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec_ = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    b = importlib.util.module_from_spec(spec_)
+    spec_.loader.exec_module(b)
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        a = b.parse()
+    finally:
+        sys.argv = argv
+    assert a.gpus == 1 and a.warmup >= 3 and a.steps >= 1 and a.impl == "ours" and a.config == "bloom" and a.model == "resnet50"
+    r = b.exchange_roofline(0.724, 102228128, 1612608, 8)
+    assert r["bound"] == "hbm" and abs(r["hbm_bound_ms"] - 4 * 102228128 / (r["hbm_gbs_measured"] * 1e9) * 1e3) < 1e-9
+    assert 0.05 < r["frac_of_roofline"] < 0.2 and r["nvlink_bytes_out"] == 2 * 7 * 1612608
+    assert b.exchange_roofline(0.5, 102228128, 1612608, 1)["nvlink_bytes_out"] == 0
+    import torch
+    if not torch.cuda.is_available():
+        for impl in ("ours", "reference"):
+            p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", impl], capture_output=True,
+                               text=True, timeout=300)
+            lines = [ln for ln in p.stdout.splitlines() if ln.strip()]
+            assert p.returncode == 0 and len(lines) == 1, p.stdout + p.stderr[-500:]
+            out = json.loads(lines[0])
+            assert out["impl"] == impl and "unavailable" in out
