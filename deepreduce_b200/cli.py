@@ -139,7 +139,7 @@ def main(argv=None):
         from .utils import METRICS
         out["metrics"] = METRICS.summary()
         print(json.dumps(out), flush=True)
-    if args.train_dir and rank == 0:
+    if args.train_dir:                     # model/optimizer once (rank 0), residual + select state per rank
         os.makedirs(args.train_dir, exist_ok=True)
         save_checkpoint(os.path.join(args.train_dir, "ckpt.pt"), tr)
     tr.close()

@@ -27,7 +27,7 @@ class Memory(ABC):
     def state_dict(self) -> dict:
         return {}
 
-    def load_state_dict(self, state: dict) -> None:
+    def load_state_dict(self, state: dict, device=None) -> None:
         pass
 
 

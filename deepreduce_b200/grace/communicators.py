@@ -74,7 +74,10 @@ class Allreduce(Communicator):
         out = []
         for t in tensors:
             self.bytes_sent += t.numel() * t.element_size()
-            if self.world_size > 1:
+            # only VALUE components are summed: an index component (randomk ships int64 coordinates that are
+            # identical on every rank by construction — same (step, name) seed) must reach decompress() unchanged,
+            # summing it would scatter to W*idx
+            if self.world_size > 1 and torch.is_tensor(t) and t.is_floating_point():
                 dist.all_reduce(t, group=self.group)
             out.append(t)
         dense = self.compressor.decompress(out, ctx)

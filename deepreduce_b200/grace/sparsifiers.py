@@ -17,7 +17,9 @@ from .base import Compressor
 def _desparsify(tensors, shape: torch.Size) -> torch.Tensor:
     values, indices = tensors
     out = torch.zeros(shape.numel(), dtype=values.dtype, device=values.device)
-    out.scatter_(0, indices.long(), values)
+    # index_add_, not scatter_: a sparsifier that found fewer than K non-zeros pads with (index 0, value 0.0); adding
+    # zeros is exact and order-independent, while scatter_ with duplicate indices is nondeterministic
+    out.index_add_(0, indices.long(), values)
     return out.view(shape)
 
 

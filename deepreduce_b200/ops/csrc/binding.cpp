@@ -225,14 +225,14 @@ static torch::Tensor u8_to_nhwc_norm(torch::Tensor in, std::vector<double> mean,
 struct Engine {
   EngineParams P{};
   int grid = 0;
+  int grid_cap = 0;            // > 0: launch at most this many CTAs (overlapped buckets leave SMs to backward)
   int blocks_per_sm = 2;
   int dyn_smem = 64 * 1024;
   int device = 0;
 
   Engine(int64_t tensors, int64_t tiles, int64_t n_tensors, int64_t n_tiles, int64_t slot_words,
          int64_t payload_words, int64_t grad, int64_t resid, int64_t hist, int64_t hist_total, int64_t sel,
-         int64_t tile_count, int64_t flag_buf, int64_t barrier, int64_t status, std::vector<int64_t> arenas, int rank,
-         int world) {
+         int64_t tile_count, int64_t barrier, int64_t status, std::vector<int64_t> arenas, int rank, int world) {
     TORCH_CHECK(world <= dr::kMaxWorld && (int)arenas.size() == world, "bad world/arenas");
     P.tensors = reinterpret_cast<const dr::TensorDesc*>(tensors);
     P.tiles = reinterpret_cast<const dr::TileInfo*>(tiles);
@@ -242,7 +242,6 @@ struct Engine {
     P.hist = reinterpret_cast<uint32_t*>(hist); P.hist_total = reinterpret_cast<uint32_t*>(hist_total);
     P.sel = reinterpret_cast<dr::SelState*>(sel);
     P.tile_count = reinterpret_cast<uint32_t*>(tile_count);
-    P.flag_buf = reinterpret_cast<uint8_t*>(flag_buf);
     P.barrier = reinterpret_cast<uint32_t*>(barrier); P.status = reinterpret_cast<uint32_t*>(status);
     for (int i = 0; i < world; ++i) P.arena[i] = reinterpret_cast<uint32_t*>(arenas[i]);
     P.rank = rank; P.world = world;
@@ -250,7 +249,8 @@ struct Engine {
     P.spin_limit = 20u * 1000u * 1000u;
     P.filter_smem_words = (uint32_t)(dyn_smem / 4);
     P.use_tma = 1; P.hist_shift = 23;
-    P.shard = 0; P.s2_words = 0; P.s2_cap = 0; P.has_rle = 0; P.mc_arena = nullptr; P.own_flags = 0; P.warp_count = nullptr;
+    P.shard = 0; P.s2_words = 0; P.s2_cap = 0; P.has_rle = 0; P.mc_arena = nullptr;
+    P.peer_timeout_ms = 120000u; P.fault = 0;
     cudaGetDevice(&device);
   }
 
@@ -273,9 +273,16 @@ struct Engine {
   }
 
   void set_has_rle(int v) { P.has_rle = v; }
-  void set_opts(int own_flags, int64_t warp_count) {
-    P.own_flags = own_flags; P.warp_count = reinterpret_cast<uint8_t*>(warp_count);
+  // scratch of the candidate / bitmask pipeline (see engine.cu): masks [n_tiles*128] u32 x2, candidate keys
+  // [n_tiles*4096] u32, offsets [n_tiles*4096] u16, counts [n_tiles*16] u32
+  void set_scratch(int64_t pos_mask, int64_t dec_mask, int64_t cand_key, int64_t cand_e, int64_t cand_cnt) {
+    P.pos_mask = reinterpret_cast<uint32_t*>(pos_mask); P.dec_mask = reinterpret_cast<uint32_t*>(dec_mask);
+    P.cand_key = reinterpret_cast<uint32_t*>(cand_key); P.cand_e = reinterpret_cast<uint16_t*>(cand_e);
+    P.cand_cnt = reinterpret_cast<uint32_t*>(cand_cnt);
   }
+  void set_peer_timeout_ms(int64_t ms) { P.peer_timeout_ms = (uint32_t)ms; }
+  void set_fault(int f) { P.fault = f; }
+  void set_grid_cap(int cap) { grid_cap = cap; }
   void set_multicast(int64_t p) { P.mc_arena = reinterpret_cast<uint32_t*>(p); }
 
   void set_shard(int shard, int64_t s2_words, int64_t s2_cap) {
@@ -294,7 +301,10 @@ struct Engine {
   void run_on(uint32_t epoch, int phase_begin, int phase_end, cudaStream_t st) {
     EngineParams Q = P;
     Q.epoch = epoch; Q.phase_begin = phase_begin; Q.phase_end = phase_end;
-    cudaError_t e = dr::engine_launch(Q, get_grid(), blocks_per_sm, dyn_smem, st);
+    TORCH_CHECK(P.pos_mask && P.cand_key, "Engine: set_scratch() was not called");
+    int g = get_grid();
+    if (grid_cap > 0 && grid_cap < g) g = grid_cap;
+    cudaError_t e = dr::engine_launch(Q, g, blocks_per_sm, dyn_smem, st);
     TORCH_CHECK(e == cudaSuccess, "engine launch failed: ", cudaGetErrorString(e));
   }
 
@@ -453,13 +463,16 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
 
   py::class_<Engine>(m, "Engine")
       .def(py::init<int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t,
-                    int64_t, int64_t, int64_t, int64_t, std::vector<int64_t>, int, int>())
+                    int64_t, int64_t, int64_t, std::vector<int64_t>, int, int>())
       .def("configure", &Engine::configure)
       .def("set_buffers", &Engine::set_buffers)
       .def("set_poly", &Engine::set_poly)
       .def("set_shard", &Engine::set_shard)
       .def("set_has_rle", &Engine::set_has_rle)
-      .def("set_opts", &Engine::set_opts)
+      .def("set_scratch", &Engine::set_scratch)
+      .def("set_peer_timeout_ms", &Engine::set_peer_timeout_ms)
+      .def("set_fault", &Engine::set_fault)
+      .def("set_grid_cap", &Engine::set_grid_cap)
       .def("set_multicast", &Engine::set_multicast)
       .def("grid", &Engine::get_grid)
       .def("run", &Engine::run);

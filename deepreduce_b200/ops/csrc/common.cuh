@@ -131,6 +131,12 @@ DR_D void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+DR_D void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+DR_D uint64_t globaltimer_ns() {
+  uint64_t t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t;
+}
 DR_D void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t* status = nullptr) {
   uint32_t ok, spins = 0;
   do {
@@ -145,6 +151,10 @@ DR_D void multimem_st_v4(uint4* mc_addr, uint4 v) {
   asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1,%2,%3,%4};"
                :: "l"(mc_addr), "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)),
                   "f"(__uint_as_float(v.w)) : "memory");
+}
+
+DR_D void multimem_st_b32(uint32_t* mc_addr, uint32_t v) {
+  asm volatile("multimem.st.weak.global.f32 [%0], %1;" :: "l"(mc_addr), "f"(__uint_as_float(v)) : "memory");
 }
 
 // Grid-wide barrier for a co-resident (cooperative-launch) grid.  `counter`

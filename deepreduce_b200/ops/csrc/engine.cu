@@ -1,14 +1,16 @@
-// DeepReduce-B200 fused bucket engine (sm_100a).
+// DeepReduce-B200 fused bucket engine (sm_100a), v11.
 //
 // One persistent, cooperatively-launched kernel runs the whole per-bucket
 // gradient exchange:
 //
-//   accumulate residual -> per-tensor top-k threshold (2-digit radix select on
-//   |g| bits, history-guided lower bound) -> bloom insert -> universe query +
-//   ordered compaction + FP-aware value gather + residual update -> P2P store
-//   of the compressed slot into every peer's arena over NVLink -> release /
-//   acquire flags -> membership-test decode of all W slots, rank->value, sum,
-//   scale, dense write.
+//   accumulate residual (TMA ring) + zero the dense output + candidate lists ->
+//   per-tensor top-k threshold (2-digit radix select, digit 2 over the candidates
+//   only) -> bloom insert + occupancy hint from the candidates -> membership test
+//   of the hinted 32-element groups (two-level survivor queue) -> ordered
+//   compaction from group bitmasks + FP-aware value gather + residual update ->
+//   P2P store of the compressed slot into every peer's arena over NVLink ->
+//   release / acquire flags -> decode of all W slots for this rank's slice ->
+//   second in-kernel exchange of the exact slice lists.
 //
 // It replaces, per tensor, the reference's chain: GRACE residual add, torch.topk,
 // Bloomfilter.add/query/policy (reference pytorch/deepreduce.py:457-492,506-533),
@@ -16,17 +18,16 @@
 // W x zeros+scatter and the sum.  Phases can also be launched
 // one at a time (phase_begin/phase_end) — the "unfused chain" debug mode.
 //
-// Work decomposition: the bucket is cut into 4096-element tiles that never
-// cross a tensor; every phase gives CTA b the same contiguous tile range, so
-// per-tensor work (histogram flush, threshold resolve, filter staging) is paid
-// 1-3 times per CTA instead of once per tile (profiles/ v1->v3 notes).  Ordered
-// ranks need a prefix over tiles: the query phase stores per-thread element
-// flags + per-tile counts, and after one grid barrier the emit phase sums the
-// counts it needs locally — no look-back chain.
-//
-// Latency structure: streaming passes software-prefetch the next tile while
-// the current one is binned; bloom filters are staged in shared memory (every
-// ResNet-50 tensor's filter fits) and probed from there.
+// Work decomposition: the bucket is cut into 4096-element tiles that never cross a
+// tensor; every streaming phase gives CTA b the same contiguous tile range.  The
+// universe is read exactly once (accumulate): everything after it works on
+//   * the candidate list  — the (key, offset) pairs with |x| above a fraction of last
+//     step's threshold, written per (tile, warp) at a fixed location (no allocation,
+//     no overflow); digit 2 of the select and the bloom insert walk it instead of d;
+//   * group bitmasks      — one 32-bit word per 32 consecutive elements: the query
+//     leaves the positives there, emit / decode derive ordered ranks from popcounts.
+// v10 -> v11 (profiles/): 4 passes over d -> 1, per-tile CTA barriers -> mbarrier
+// full/empty ring + warp-private work, probe chains run on dense survivor batches.
 #include "common.cuh"
 #include "plan.h"
 
@@ -41,30 +42,39 @@ long long launch_count() { return g_launches.load(); }
 
 namespace {
 
-constexpr uint32_t kErrLookback = 1u, kErrPeerWait = 2u, kErrResolve = 3u;
+constexpr uint32_t kErrPeerWait = 2u, kErrResolve = 3u, kErrS2Overflow = 6u;
 constexpr uint32_t kNoTensor = 0xFFFFFFFFu;
+constexpr uint32_t kFullMask = 0xFFFFFFFFu;
+constexpr uint32_t kGroupsPerTile = kTile / 32;       // 128 mask words per tile
+constexpr uint32_t kChunk = 256;                      // candidate capacity per (tile, warp) = the elements a warp owns
+constexpr uint32_t kHalf = kTile / 2;                 // elements per ring stage (g half-tile | r half-tile)
+constexpr uint32_t kStageBytes = 2u * kHalf * 4u;     // 16 KB
+constexpr uint32_t kMaxStages = 6;
+constexpr uint32_t kUnsafeWord = 8;                   // P.barrier[8]: tensors whose history bound hid the threshold
 
 struct ScanSmem {
-  alignas(16) uint32_t cnt[2][kPerThread * kWarps];   // double-buffered tile_rank scratch
   uint32_t warp_tot[kWarps];
   uint32_t res[4];                            // resolve results: bin, krem, bincount, spare
-  uint32_t lb;                                // small CTA-wide scratch word
+  uint32_t lb;                                // small CTA-wide scratch word / dynamic work counter
   uint32_t rle_pre[16];                       // kModeRle decode: running entry prefix per sender
 };
 
 struct Smem {
   union {
-    uint32_t hist[kHistBins];
-    float acc[kTile];
+    uint32_t hist[kHistBins];                 // radix-select digit histogram
+    float acc[kTile];                         // raw / rle decode accumulator
+    uint32_t q[kWarps][64];                   // probe passes: per-warp survivor ring
+    uint32_t excl[kTile];                     // emit: exclusive prefixes of a chunk of tiles
+    uint32_t sel[kWarps][32];                 // insert: selected elements of one warp iteration
   } u;
   ScanSmem s;
   TensorDesc td;                              // current tensor
-  uint64_t bar[8];                            // mbarriers of the TMA tile ring
+  uint64_t bar[16];                           // mbarriers of the TMA ring: full[0..8), empty[8..16)
   int seg_start[kMaxSeg + 2];                 // 'both': segment boundaries of the current (tensor, rank)
   int n_seg;
 };
 
-extern __shared__ __align__(16) uint32_t g_filter_smem[];   // dynamic: staged bloom filter
+extern __shared__ __align__(16) uint32_t g_filter_smem[];   // dynamic: staged bloom filter / TMA ring / stage-2 staging
 
 DR_D uint32_t* slot_ptr(uint32_t* arena, const EngineParams& P, uint32_t parity, int src) {
   return arena + kArenaHdrWords + (size_t)(parity * (uint32_t)P.world + (uint32_t)src) * P.slot_words;
@@ -85,6 +95,16 @@ DR_D void decode_span(const EngineParams& P, int owner, uint32_t& s_begin, uint3
   } else { s_begin = 0; s_end = P.n_tiles; }
 }
 
+// this CTA's contiguous share of the decode span (decode and compact use the SAME split, so the CTA that decoded
+// a tile is the one that compacts it — no grid barrier in between)
+DR_D void decode_range(const EngineParams& P, uint32_t& tile, uint32_t& t_end) {
+  uint32_t s_begin, s_end;
+  decode_span(P, P.rank, s_begin, s_end);
+  const uint32_t span = s_end - s_begin;
+  tile = s_begin + (uint32_t)(((uint64_t)span * blockIdx.x) / gridDim.x);
+  t_end = s_begin + (uint32_t)(((uint64_t)span * (blockIdx.x + 1)) / gridDim.x);
+}
+
 struct Tile { uint32_t tensor, base, n, local0, single; };   // `single`: the tensor has exactly one tile
 
 DR_D Tile load_tile(const EngineParams& P, uint32_t tile) {
@@ -102,78 +122,15 @@ DR_D void load_tensor(const EngineParams& P, uint32_t t, Smem& sm) {
   __syncthreads();
 }
 
-// ---------------------------------------------------------------------------
-// ordered in-tile ranks.  Thread `tid` owns elements tid + c*kThreads (c < 8);
-// bit c of `flags` marks element c.  Returns the exclusive rank of every
-// flagged element in element order and the tile total.  ONE __syncthreads:
-// every warp publishes its 8 slot counts, then scans all 128 counts itself.
-// `buf` is a per-thread toggle (double buffering makes a trailing barrier
-// unnecessary: a buffer is rewritten two calls later, after the barrier of the
-// call in between).
-// ---------------------------------------------------------------------------
-DR_D void tile_rank(uint32_t flags, ScanSmem& s, uint32_t& buf, uint32_t (&rank)[kPerThread], uint32_t& total) {
-  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  uint32_t ball[kPerThread];
-#pragma unroll
-  for (int c = 0; c < kPerThread; ++c) ball[c] = __ballot_sync(0xFFFFFFFFu, (flags >> c) & 1u);
-  if (lane == 0) {
-#pragma unroll
-    for (int c = 0; c < kPerThread; ++c) s.cnt[buf][c * kWarps + warp] = __popc(ball[c]);
-  }
-  __syncthreads();
-  // lane l holds counts 4l .. 4l+3 (element order = slot-major, warp-minor)
-  const uint4 v = reinterpret_cast<const uint4*>(s.cnt[buf])[lane];
-  const uint32_t sum = v.x + v.y + v.z + v.w;
-  uint32_t incl = sum;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-    if (lane >= (uint32_t)o) incl += n;
-  }
-  const uint32_t base = incl - sum;
-  const uint32_t sub = warp & 3u;
-  const uint32_t part = (sub > 0 ? v.x : 0u) + (sub > 1 ? v.y : 0u) + (sub > 2 ? v.z : 0u);   // my lane's partials, reused below
-  const uint32_t lt = (1u << lane) - 1u;
-#pragma unroll
-  for (int c = 0; c < kPerThread; ++c) {
-    // prefix of index i = c*16 + warp lives in lane i>>2 = 4c + (warp>>2), at sub-position warp&3
-    const int src = 4 * c + (int)(warp >> 2);
-    const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, base, src);
-    const uint32_t vx = __shfl_sync(0xFFFFFFFFu, v.x, src), vy = __shfl_sync(0xFFFFFFFFu, v.y, src),
-                   vz = __shfl_sync(0xFFFFFFFFu, v.z, src);
-    rank[c] = b0 + (sub > 0 ? vx : 0u) + (sub > 1 ? vy : 0u) + (sub > 2 ? vz : 0u) + __popc(ball[c] & lt);
-  }
-  (void)part;
-  total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-  buf ^= 1u;
-}
+DR_D size_t chunk_of(uint32_t tile, uint32_t warp) { return ((size_t)tile * kWarps + warp) * kChunk; }
 
-// Same ranks from per-(slot, warp) counts that the query phase left in global memory (128 bytes per tile, index
-// c*16 + warp): no shared memory, no CTA barrier — warps drift through their tiles independently.
-DR_D void tile_rank_counts(uint32_t flags, const uint8_t* cnt, uint32_t (&rank)[kPerThread], uint32_t& total) {
-  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const uint32_t w = __ldcg(reinterpret_cast<const uint32_t*>(cnt) + lane);       // counts 4l .. 4l+3
-  const uint32_t vx = w & 0xFFu, vy = (w >> 8) & 0xFFu, vz = (w >> 16) & 0xFFu, vw = w >> 24;
-  const uint32_t sum = vx + vy + vz + vw;
-  uint32_t incl = sum;
+DR_D uint32_t warp_incl_scan(uint32_t v, uint32_t lane) {
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-    if (lane >= (uint32_t)o) incl += n;
+    const uint32_t n = __shfl_up_sync(kFullMask, v, o);
+    if (lane >= (uint32_t)o) v += n;
   }
-  const uint32_t base = incl - sum;
-  const uint32_t sub = warp & 3u;
-  const uint32_t lt = (1u << lane) - 1u;
-#pragma unroll
-  for (int c = 0; c < kPerThread; ++c) {
-    const int src = 4 * c + (int)(warp >> 2);
-    const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, base, src);
-    const uint32_t sx = __shfl_sync(0xFFFFFFFFu, vx, src), sy = __shfl_sync(0xFFFFFFFFu, vy, src),
-                   sz = __shfl_sync(0xFFFFFFFFu, vz, src);
-    const uint32_t ball = __ballot_sync(0xFFFFFFFFu, (flags >> c) & 1u);
-    rank[c] = b0 + (sub > 0 ? sx : 0u) + (sub > 1 ? sy : 0u) + (sub > 2 ? sz : 0u) + __popc(ball & lt);
-  }
-  total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+  return v;
 }
 
 // ---------------------------------------------------------------------------
@@ -197,12 +154,7 @@ DR_D void resolve_bins(LoadFn H, int nbins, uint32_t k, ScanSmem& s) {
     c[i] = (rb < nbins) ? H(nbins - 1 - rb) : 0u;
     sum += c[i];
   }
-  uint32_t incl = sum;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-    if (lane >= (uint32_t)o) incl += n;
-  }
+  const uint32_t incl = warp_incl_scan(sum, lane);
   if (lane == 31) s.warp_tot[warp] = incl;
   __syncthreads();
   uint32_t base = 0;
@@ -264,40 +216,15 @@ DR_D bool finish_digit(const EngineParams& P, Smem& sm, int which, uint32_t t, u
   return last;
 }
 
-// stage a bloom filter (global, 16-byte aligned) into the dynamic SMEM buffer
+// stage a bloom filter (global, 16-byte aligned) into the dynamic SMEM buffer; read through L2: the filter was just
+// built by atomics (own) or by remote stores (peers)
 DR_D void stage_filter(const uint32_t* __restrict__ filter, uint32_t n_words) {
   __syncthreads();                              // previous users of the buffer are done
   const uint4* src = reinterpret_cast<const uint4*>(filter);
   uint4* dst = reinterpret_cast<uint4*>(g_filter_smem);
   const uint32_t n4 = (n_words + 3u) >> 2;
-  for (uint32_t i = threadIdx.x; i < n4; i += kThreads) dst[i] = src[i];
+  for (uint32_t i = threadIdx.x; i < n4; i += kThreads) dst[i] = __ldcg(src + i);
   __syncthreads();
-}
-
-// Occupancy hint: 128 bits per tile, bit (c*16 + warp) covers the 32 consecutive elements that warp `warp`
-// owns in slot c.  valid_from_hint() turns the 4 words into this thread's 8-bit element mask.
-DR_D uint32_t valid_from_hint(const uint32_t (&h)[4]) {
-  const uint32_t warp = threadIdx.x >> 5;
-  uint32_t v = 0;
-#pragma unroll
-  for (int c = 0; c < kPerThread; ++c) v |= ((h[c >> 1] >> (((c & 1) << 4) + warp)) & 1u) << c;
-  return v;
-}
-
-// every warp publishes which of its 8 slots contain a flagged element; 4 words land in `dst` (SMEM scratch in `s`)
-DR_D void build_hint(uint32_t mask, ScanSmem& s, uint32_t* dst) {
-  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  if (threadIdx.x < 4) s.warp_tot[threadIdx.x] = 0;
-  __syncthreads();
-  uint32_t occ = 0;
-#pragma unroll
-  for (int c = 0; c < kPerThread; ++c) if (__ballot_sync(0xFFFFFFFFu, (mask >> c) & 1u)) occ |= 1u << c;
-  if (lane == 0) {
-#pragma unroll
-    for (int c = 0; c < kPerThread; ++c) if ((occ >> c) & 1u) atomicOr(&s.warp_tot[c >> 1], 1u << (((c & 1) << 4) + warp));
-  }
-  __syncthreads();
-  if (threadIdx.x < 4) dst[threadIdx.x] = s.warp_tot[threadIdx.x];
 }
 
 DR_D void tile_range(const EngineParams& P, uint32_t& t_begin, uint32_t& t_end) {
@@ -305,23 +232,23 @@ DR_D void tile_range(const EngineParams& P, uint32_t& t_begin, uint32_t& t_end) 
   t_end = (uint32_t)(((uint64_t)P.n_tiles * (blockIdx.x + 1)) / gridDim.x);
 }
 
-// 8 membership tests per thread (elements idx0 + c*kThreads), early exit per element
-template <typename LoadFn>
-DR_D uint32_t bloom_test8(uint32_t idx0, uint32_t valid, uint32_t seed, uint32_t n_hash, uint32_t m_bits, LoadFn ld) {
-  uint32_t flags = 0;
-#pragma unroll
-  for (int c = 0; c < kPerThread; ++c)
-    if (((valid >> c) & 1u) && bloom_test(idx0 + c * kThreads, seed, n_hash, m_bits, ld)) flags |= 1u << c;
-  return flags;
-}
-
 // ===========================================================================
-// phase 0: accumulate + hist digit 1 (+ the whole select for single-tile tensors)
+// phase 0: accumulate + dense-output zero fill + candidate lists + hist digit 1
+// (+ the whole select for single-tile tensors)
+//
+// g and r tiles arrive through a TMA ring of half-tile stages (cp.async.bulk + full/empty mbarriers): the 16 warps
+// of a CTA drift through the stages independently — a warp releases a stage with one mbarrier arrive, thread 0
+// refills the stage released one item earlier — and meet only where a tensor ends (histogram merge).
+// Thread `tid` owns elements h*2048 + tid*4 .. +3 of a tile (h = half), so warp w owns two runs of 128 consecutive
+// elements and its candidates of a tile go to the fixed chunk (tile*16 + w) * 256.
 // ===========================================================================
 constexpr uint32_t kUnsafe = 0xFFFFFFFFu;   // sel.bin1 marker: history bound hid the threshold -> fallback phase
 
 DR_D void write_digit1(const EngineParams& P, Smem& sm, uint32_t t) {
-  if (threadIdx.x == 0) { P.sel[t].bin1 = sm.s.res[0]; P.sel[t].krem1 = sm.s.res[1]; P.sel[t].done_epoch = 0; }
+  if (threadIdx.x == 0) {
+    P.sel[t].bin1 = sm.s.res[0]; P.sel[t].krem1 = sm.s.res[1]; P.sel[t].done_epoch = 0;
+    if (sm.s.res[0] == kUnsafe) atomicAdd(P.barrier + kUnsafeWord, 1u);
+  }
 }
 
 DR_D void write_final(const EngineParams& P, Smem& sm, uint32_t t, uint32_t bin1) {
@@ -333,77 +260,168 @@ DR_D void write_final(const EngineParams& P, Smem& sm, uint32_t t, uint32_t bin1
   }
 }
 
+// Append this thread's flagged elements (bit j of m: element e0 + j, key key[j]) to the warp's candidate chunk.
+// `cnt` (warp-uniform) is the number of entries already in the chunk.
+DR_D void append_candidates(const EngineParams& P, Smem& sm, uint32_t m, const uint32_t (&key)[4], uint32_t e0,
+                            size_t chunk, uint32_t& cnt, bool do_hist, uint32_t lane) {
+  const uint32_t c = __popc(m);
+  const uint32_t incl = warp_incl_scan(c, lane);
+  const uint32_t tot = __shfl_sync(kFullMask, incl, 31);
+  if (tot == 0u) return;
+  uint32_t off = cnt + incl - c;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if ((m >> j) & 1u) {
+      const uint32_t k = key[j];
+      if (do_hist) atomicAdd(&sm.u.hist[k >> 20], 1u);
+      P.cand_key[chunk + off] = k;
+      P.cand_e[chunk + off] = (uint16_t)(e0 + j);
+      ++off;
+    }
+  }
+  cnt += tot;
+}
+
+DR_D uint32_t round16(uint32_t bytes) { return (bytes + 15u) & ~15u; }
+
 DR_D void phase_accum(const EngineParams& P, Smem& sm) {
-  const uint32_t parity = P.epoch & 1u;
-  uint32_t* my_slot = slot_ptr(P.arena[P.rank], P, parity, P.rank);
-  {  // zero the outgoing slot (filters, headers, prefix tables)
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t parity_slot = P.epoch & 1u;
+  uint32_t* my_slot = slot_ptr(P.arena[P.rank], P, parity_slot, P.rank);
+  {  // zero the outgoing slot (filters, headers, prefix tables, hints)
     uint4* p = reinterpret_cast<uint4*>(my_slot);
     const uint32_t n4 = (P.payload_words + 3u) >> 2;
     const uint4 z = make_uint4(0, 0, 0, 0);
-    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n4; i += gridDim.x * kThreads) p[i] = z;
+    for (uint32_t i = blockIdx.x * kThreads + tid; i < n4; i += gridDim.x * kThreads) p[i] = z;
   }
-  if (sharded(P) && blockIdx.x == 0 && threadIdx.x == 0) *s2_ptr(P.arena[P.rank], P, parity, P.rank) = 0u;
+  if (sharded(P) && blockIdx.x == 0 && tid == 0) *s2_ptr(P.arena[P.rank], P, parity_slot, P.rank) = 0u;
   clear_hist(sm);
   const bool has_resid = (P.beta != 0.0f);
-  uint32_t cur = kNoTensor, lower = 0, n_mine = 0;
-  uint32_t tile, t_end;
-  tile_range(P, tile, t_end);
-  if (tile >= t_end) return;
-  Tile ti = load_tile(P, tile);
-  float4 g[2], r[2];
-  auto issue = [&](const Tile& t, float4 (&gg)[2], float4 (&rr)[2]) {
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const uint32_t e = (c * kThreads + threadIdx.x) * 4u;
-      if (e < t.n) {
-        gg[c] = ld_stream_f4(reinterpret_cast<const float4*>(P.grad + t.base + e));
-        if (has_resid) rr[c] = ld_stream_f4(reinterpret_cast<const float4*>(P.resid + t.base + e));
+  uint32_t t0, t_end;
+  tile_range(P, t0, t_end);
+  if (t0 >= t_end) return;
+  uint8_t* ring = reinterpret_cast<uint8_t*>(g_filter_smem);
+  const uint32_t n_stages = min(kMaxStages, (P.filter_smem_words * 4u) / kStageBytes);   // host guarantees >= 2
+  uint64_t* full = sm.bar;
+  uint64_t* empty = sm.bar + 8;
+  if (tid == 0) {
+    for (uint32_t i = 0; i < n_stages; ++i) {
+      mbar_inval(&full[i]); mbar_init(&full[i], 1);
+      mbar_inval(&empty[i]); mbar_init(&empty[i], kWarps);
+    }
+    mbar_fence_init();
+    fence_proxy_async();
+  }
+  __syncthreads();
+  // ---- producer (thread 0): the item sequence = every non-empty half-tile of my range, in order
+  uint32_t p_tile = t0, p_half = 0, p_item = 0;
+  auto issue_next = [&]() -> bool {
+    while (p_tile < t_end) {
+      const Tile t = load_tile(P, p_tile);
+      const uint32_t off = p_half * kHalf;
+      const uint32_t this_tile = p_tile;
+      if (p_half == 1u) { p_half = 0; ++p_tile; } else { p_half = 1u; }
+      if (off < t.n) {
+        const uint32_t bytes = round16(min(t.n - off, kHalf) * 4u);
+        const uint32_t s = p_item % n_stages;
+        uint8_t* dst = ring + (size_t)s * kStageBytes;
+        mbar_expect_tx(&full[s], has_resid ? 2u * bytes : bytes);
+        bulk_g2s(dst, P.grad + t.base + off, bytes, &full[s]);
+        if (has_resid) bulk_g2s(dst + kHalf * 4u, P.resid + t.base + off, bytes, &full[s]);
+        ++p_item;
+        (void)this_tile;
+        return true;
       }
     }
+    return false;
   };
-  auto finish = [&]() {      // digit 1 of tensor `cur` is complete for this CTA
-    const uint32_t k = __ldg(&P.tensors[cur].k), nt = __ldg(&P.tensors[cur].n_tiles);
-    if (finish_digit(P, sm, 0, cur, n_mine, nt, k)) write_digit1(P, sm, cur);
-  };
-  issue(ti, g, r);
-  while (true) {
-    const uint32_t next = tile + 1;
-    Tile tn = ti;
-    float4 gn[2], rn[2];
-    const bool has_next = next < t_end;
-    if (has_next) { tn = load_tile(P, next); issue(tn, gn, rn); }     // prefetch before binning the current tile
-    if (ti.tensor != cur) {
-      if (cur != kNoTensor) finish();
-      cur = ti.tensor; n_mine = 0;
+  if (tid == 0) for (uint32_t i = 0; i < n_stages; ++i) if (!issue_next()) break;
+  // ---- consumers
+  uint32_t item = 0;
+  uint32_t tile = t0;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  while (tile < t_end) {
+    Tile ti = load_tile(P, tile);
+    const uint32_t cur = ti.tensor;
+    const TensorDesc* tdp = P.tensors + cur;
+    const uint32_t mode = __ldg(&tdp->mode), fixed = __ldg(&tdp->fixed_thr);
+    uint32_t lower;
+    if (fixed) lower = fixed;
+    else {
       const uint32_t prev = P.use_history ? __ldcg(&P.sel[cur].prev_thr) : 0u;
-      lower = (prev > (1u << 23)) ? prev - (1u << P.hist_shift) : 0u;  // a fraction of last step's threshold
+      lower = (prev > (1u << 23)) ? prev - (1u << P.hist_shift) : 0u;      // a fraction of last step's threshold
     }
-    uint32_t key[8];
+    const bool do_hist = (fixed == 0u);
+    const bool single = ti.single != 0u;
+    uint32_t n_mine = 0;
+    uint32_t keys[8];
+    while (true) {                                                         // tiles of this tensor inside my range
+      uint32_t cnt = 0;
+      const size_t chunk = chunk_of(tile, warp);
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const uint32_t e = (c * kThreads + threadIdx.x) * 4u;
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (e < ti.n) {
-        if (has_resid) {
-          a.x = P.beta * r[c].x + P.gamma * g[c].x; a.y = P.beta * r[c].y + P.gamma * g[c].y;
-          a.z = P.beta * r[c].z + P.gamma * g[c].z; a.w = P.beta * r[c].w + P.gamma * g[c].w;
-        } else {
-          a.x = P.gamma * g[c].x; a.y = P.gamma * g[c].y; a.z = P.gamma * g[c].z; a.w = P.gamma * g[c].w;
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t off = (uint32_t)h * kHalf;
+        uint32_t key4[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};   // 0xFFFFFFFF = not an element
+        if (off < ti.n) {                                                  // CTA-uniform
+          const uint32_t s = item % n_stages;
+          mbar_wait(&full[s], (item / n_stages) & 1u, P.status);
+          const float4* sg = reinterpret_cast<const float4*>(ring + (size_t)s * kStageBytes);
+          const float4* sr = sg + kHalf / 4;
+          const uint32_t e0 = off + tid * 4u;
+          uint32_t m = 0;
+          if (e0 < ti.n) {
+            const float4 g = sg[tid];
+            float4 a;
+            if (has_resid) {
+              const float4 r = sr[tid];
+              a.x = P.beta * r.x + P.gamma * g.x; a.y = P.beta * r.y + P.gamma * g.y;
+              a.z = P.beta * r.z + P.gamma * g.z; a.w = P.beta * r.w + P.gamma * g.w;
+            } else {
+              a.x = P.gamma * g.x; a.y = P.gamma * g.y; a.z = P.gamma * g.z; a.w = P.gamma * g.w;
+            }
+            *reinterpret_cast<float4*>(P.resid + ti.base + e0) = a;
+            *reinterpret_cast<float4*>(P.grad + ti.base + e0) = zero4;    // the dense output starts from zero
+            const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (e0 + j < ti.n) {
+                key4[j] = __float_as_uint(av[j]) & 0x7FFFFFFFu;
+                if (key4[j] >= lower) m |= 1u << j;
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[s]);                           // this warp is done with stage s
+          if (tid == 0 && item >= 1u && p_tile < t_end) {                  // refill the stage released one item ago
+            const uint32_t r = item - 1u;
+            mbar_wait(&empty[r % n_stages], (r / n_stages) & 1u, P.status);
+            fence_proxy_async();
+            issue_next();
+          }
+          ++item;
+          append_candidates(P, sm, m, key4, e0, chunk, cnt, do_hist, lane);
         }
-        *reinterpret_cast<float4*>(P.resid + ti.base + e) = a;
-      }
-      const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const bool ok = e + i < ti.n;
-        key[c * 4 + i] = ok ? (__float_as_uint(av[i]) & 0x7FFFFFFFu) : 0xFFFFFFFFu;   // 0xFFFFFFFF = not an element
-        if (ok && key[c * 4 + i] >= lower) atomicAdd(&sm.u.hist[key[c * 4 + i] >> 20], 1u);
+        for (int j = 0; j < 4; ++j) keys[h * 4 + j] = key4[j];
       }
+      if (lane == 0) P.cand_cnt[tile * kWarps + warp] = cnt;
+      if (mode != (uint32_t)kModeBloom && lane < 8u) P.pos_mask[(size_t)tile * kGroupsPerTile + warp * 8u + lane] = 0u;
+      n_mine += 1;
+      ++tile;
+      if (tile >= t_end) break;
+      const Tile tn = load_tile(P, tile);
+      if (tn.tensor != cur) break;
+      ti = tn;
     }
-    n_mine += 1;
-    if (ti.single) {
+    // ---- the tensor (or my part of it) is done
+    if (fixed) {
+      if (tid == 0) {
+        SelState* s = P.sel + cur;
+        s->thr = fixed; s->bin1 = 0; s->krem1 = 0; s->done_epoch = P.epoch;
+      }
+    } else if (single) {
       // one-tile tensor: finish the whole 2-digit select here, from the keys still in registers
-      const uint32_t k = __ldg(&P.tensors[cur].k);
+      const uint32_t k = __ldg(&tdp->k);
       resolve_bins([&](int b) { return sm.u.hist[b]; }, kHistBins, k, sm.s);
       const uint32_t bin1 = sm.s.res[0], krem1 = sm.s.res[1];
       write_digit1(P, sm, cur);
@@ -411,418 +429,83 @@ DR_D void phase_accum(const EngineParams& P, Smem& sm) {
       if (bin1 != kUnsafe) {
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-          if (key[i] != 0xFFFFFFFFu && (key[i] >> 20) == bin1) atomicAdd(&sm.u.hist[(key[i] >> 9) & 0x7FFu], 1u);
+          if (keys[i] != 0xFFFFFFFFu && (keys[i] >> 20) == bin1) atomicAdd(&sm.u.hist[(keys[i] >> 9) & 0x7FFu], 1u);
         resolve_bins([&](int b) { return sm.u.hist[b]; }, kHistBins, krem1, sm.s);
         write_final(P, sm, cur, bin1);
-        if (threadIdx.x == 0) P.sel[cur].done_epoch = P.epoch;
+        if (tid == 0) P.sel[cur].done_epoch = P.epoch;
         clear_hist(sm);
       }
-      cur = kNoTensor; n_mine = 0;
+    } else {
+      const uint32_t k = __ldg(&tdp->k), nt = __ldg(&tdp->n_tiles);
+      if (finish_digit(P, sm, 0, cur, n_mine, nt, k)) write_digit1(P, sm, cur);
     }
-    if (!has_next) break;
-    tile = next; ti = tn;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) { g[c] = gn[c]; r[c] = rn[c]; }
   }
-  if (cur != kNoTensor) finish();
 }
 
-// generic "histogram one digit of the keys" pass over resid with tile prefetch
-//   kWhich 1: digit-1 fallback (all keys, digit = key>>20) for tensors whose history bound was unsafe
-//   kWhich 2: digit 2 (keys with key>>20 == bin1, digit = (key>>9) & 0x7FF)
-template <int kWhich>
-DR_D void hist_tiles(const EngineParams& P, Smem& sm) {
+// ===========================================================================
+// phase 1 (rare): the history bound hid the threshold of some tensor (fewer than K candidates): redo digit 1 over
+// all of its keys and rebuild its candidate lists in full, so the later phases stay candidate-only.
+// ===========================================================================
+DR_D void phase_fallback(const EngineParams& P, Smem& sm) {
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   clear_hist(sm);
-  uint32_t cur = kNoTensor, n_mine = 0, k_cur = 0, nt_cur = 0;
-  bool active = false;
-  uint32_t prefix = 0;
   uint32_t tile, t_end;
   tile_range(P, tile, t_end);
-  if (tile >= t_end) return;
-  Tile ti = load_tile(P, tile);
-  uint4 q[2];
-  auto issue = [&](const Tile& t, uint4 (&qq)[2]) {
+  while (tile < t_end) {
+    const Tile t0 = load_tile(P, tile);
+    const uint32_t cur = t0.tensor;
+    const TensorDesc* tdp = P.tensors + cur;
+    const uint32_t seg_end = min(t_end, __ldg(&tdp->tile_begin) + __ldg(&tdp->n_tiles));
+    const bool active = (__ldcg(&P.sel[cur].bin1) == kUnsafe) && (__ldcg(&P.sel[cur].done_epoch) != P.epoch) &&
+                        (__ldg(&tdp->fixed_thr) == 0u);
+    if (!active) { tile = seg_end; continue; }
+    uint32_t keys[8];
+    for (uint32_t tl = tile; tl < seg_end; ++tl) {
+      const Tile ti = load_tile(P, tl);
+      uint32_t cnt = 0;
+      const size_t chunk = chunk_of(tl, warp);
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const uint32_t e = (c * kThreads + threadIdx.x) * 4u;
-      if (e < t.n) qq[c] = ld_stream_u4(reinterpret_cast<const uint4*>(P.resid + t.base + e));
-    }
-  };
-  auto finish = [&]() {
-    if (!active) return;
-    if (finish_digit(P, sm, kWhich, cur, n_mine, nt_cur, k_cur)) {
-      if (kWhich == 1) {
-        if (threadIdx.x == 0 && sm.s.res[0] == 0xFFFFFFFFu) atomicExch(P.status, kErrResolve);
-        write_digit1(P, sm, cur);
-      } else {
-        write_final(P, sm, cur, prefix);
-      }
-    }
-  };
-  if (kWhich == 2) issue(ti, q);
-  while (true) {
-    const uint32_t next = tile + 1;
-    const bool has_next = next < t_end;
-    Tile tn = ti;
-    uint4 qn[2];
-    if (has_next) { tn = load_tile(P, next); if (kWhich == 2) issue(tn, qn); }
-    if (ti.tensor != cur) {
-      if (cur != kNoTensor) finish();
-      cur = ti.tensor; n_mine = 0;
-      nt_cur = __ldg(&P.tensors[cur].n_tiles);
-      const uint32_t bin1 = __ldcg(&P.sel[cur].bin1);
-      const bool done = __ldcg(&P.sel[cur].done_epoch) == P.epoch;
-      if (kWhich == 1) {
-        active = (bin1 == kUnsafe) && !done;
-        k_cur = __ldg(&P.tensors[cur].k);
-      } else {
-        active = !done;
-        prefix = bin1;
-        k_cur = __ldcg(&P.sel[cur].krem1);
-        if (active && bin1 == kUnsafe && threadIdx.x == 0) atomicExch(P.status, kErrResolve);
-      }
-    }
-    if (active) {
-      if (kWhich == 1) issue(ti, q);            // rare path: no prefetch
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t e0 = (uint32_t)h * kHalf + tid * 4u;
+        uint32_t key4[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+        uint32_t m = 0;
+        if (e0 < ti.n) {
+          const uint4 q = __ldcg(reinterpret_cast<const uint4*>(P.resid + ti.base + e0));
+          const uint32_t kv[4] = {q.x & 0x7FFFFFFFu, q.y & 0x7FFFFFFFu, q.z & 0x7FFFFFFFu, q.w & 0x7FFFFFFFu};
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const uint32_t e = (c * kThreads + threadIdx.x) * 4u;
-        if (e < ti.n) {
-          const uint32_t key[4] = {q[c].x & 0x7FFFFFFFu, q[c].y & 0x7FFFFFFFu, q[c].z & 0x7FFFFFFFu, q[c].w & 0x7FFFFFFFu};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (e + i < ti.n) {
-              if (kWhich == 1) atomicAdd(&sm.u.hist[key[i] >> 20], 1u);
-              else if ((key[i] >> 20) == prefix) atomicAdd(&sm.u.hist[(key[i] >> 9) & 0x7FFu], 1u);
-            }
-          }
+          for (int j = 0; j < 4; ++j) if (e0 + j < ti.n) { key4[j] = kv[j]; m |= 1u << j; }
         }
+        append_candidates(P, sm, m, key4, e0, chunk, cnt, true, lane);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) keys[h * 4 + j] = key4[j];
       }
-      n_mine += 1;
+      if (lane == 0) P.cand_cnt[tl * kWarps + warp] = cnt;
     }
-    if (!has_next) break;
-    tile = next; ti = tn;
-    q[0] = qn[0]; q[1] = qn[1];
-  }
-  if (cur != kNoTensor) finish();
-}
-
-// ===========================================================================
-// phase 3: bloom insert of the selected set (queue-compacted: the ~1 % selected elements of a tile are
-// gathered into an SMEM queue, then every thread sets one (element, hash) bit — no divergent tails)
-// ===========================================================================
-DR_D void phase_insert(const EngineParams& P, Smem& sm) {
-  const uint32_t parity = P.epoch & 1u;
-  uint32_t* my_slot = slot_ptr(P.arena[P.rank], P, parity, P.rank);
-  uint32_t* queue = sm.u.hist;                 // 4096 entries: reuses the histogram/acc union
-  uint32_t cur = kNoTensor, T22 = 1;
-  uint32_t tile, t_end;
-  tile_range(P, tile, t_end);
-  if (tile >= t_end) return;
-  Tile ti = load_tile(P, tile);
-  uint32_t v[kPerThread];
-  auto issue = [&](const Tile& t, uint32_t (&vv)[kPerThread]) {
-#pragma unroll
-    for (int c = 0; c < kPerThread; ++c) {
-      const uint32_t e = c * kThreads + threadIdx.x;
-      vv[c] = (e < t.n) ? (__float_as_uint(__ldcg(P.resid + t.base + e)) & 0x7FFFFFFFu) : 0u;
-    }
-  };
-  issue(ti, v);
-  while (true) {
-    const uint32_t next = tile + 1;
-    const bool has_next = next < t_end;
-    Tile tn = ti;
-    uint32_t vn[kPerThread];
-    if (has_next) { tn = load_tile(P, next); issue(tn, vn); }
-    if (ti.tensor != cur) {
-      cur = ti.tensor;
-      load_tensor(P, cur, sm);
-      T22 = __ldcg(&P.sel[cur].thr) >> 9;
-    }
-    if (sm.td.mode == kModeBloom) {
-      uint32_t mask = 0;
-#pragma unroll
-      for (int c = 0; c < kPerThread; ++c) if ((v[c] >> 9) >= T22) mask |= 1u << c;   // padding lanes hold 0 (< T22 >= 1)
-      if (sm.td.off_hint) build_hint(mask, sm.s, my_slot + sm.td.off_hint + 4u * (tile - sm.td.tile_begin));
-      // slot allocation: warp scan of the per-thread counts + one SMEM atomic per warp
-      const uint32_t lane = threadIdx.x & 31u;
-      const uint32_t cnt = __popc(mask);
-      uint32_t incl = cnt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const uint32_t nb = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += nb; }
-      if (threadIdx.x == 0) sm.s.lb = 0;
-      __syncthreads();
-      uint32_t wbase = 0;
-      if (lane == 31 && incl) wbase = atomicAdd(&sm.s.lb, incl);
-      wbase = __shfl_sync(0xFFFFFFFFu, wbase, 31);
-      uint32_t slot = wbase + incl - cnt;
-#pragma unroll
-      for (int c = 0; c < kPerThread; ++c) if ((mask >> c) & 1u) queue[slot++] = ti.local0 + c * kThreads + threadIdx.x;
-      __syncthreads();
-      const uint32_t total = sm.s.lb, n_hash = sm.td.n_hash, m_bits = sm.td.m_bits;
-      uint32_t* filter = my_slot + sm.td.off_filter;
-      for (uint32_t i = threadIdx.x; i < total * n_hash; i += kThreads) {
-        const uint32_t ent = i / n_hash, j = i - ent * n_hash;
-        const HashAB h = hash_ab(queue[ent], P.seed);
-        const uint32_t pos = mulhi32(h.a + j * h.b, m_bits);
-        atomicOr(filter + (pos >> 5), 1u << (pos & 31u));
-      }
-      __syncthreads();
-    }
-    if (!has_next) break;
-    tile = next; ti = tn;
-#pragma unroll
-    for (int c = 0; c < kPerThread; ++c) v[c] = vn[c];
-  }
-}
-
-// ===========================================================================
-// TMA variants of the streaming phases.  The next tiles are fetched by the TMA unit
-// (cp.async.bulk global->shared, completion on an mbarrier) into a ring carved out of
-// the dynamic SMEM buffer, so the prefetch depth costs no registers (the 64-register
-// build spilled its register prefetch, see profiles/).  One elected thread issues.
-// ===========================================================================
-struct Ring {
-  uint8_t* buf;
-  uint32_t stage_bytes;
-  uint32_t n_stages;
-};
-
-DR_D Ring ring_setup(const EngineParams& P, Smem& sm, uint32_t stage_bytes, uint32_t max_stages) {
-  Ring r;
-  r.buf = reinterpret_cast<uint8_t*>(g_filter_smem);
-  r.stage_bytes = stage_bytes;
-  r.n_stages = min(max_stages, (P.filter_smem_words * 4u) / stage_bytes);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (uint32_t i = 0; i < r.n_stages; ++i) { mbar_inval(&sm.bar[i]); mbar_init(&sm.bar[i], 1); }
-    mbar_fence_init();
-    fence_proxy_async();
-  }
-  __syncthreads();
-  return r;
-}
-
-DR_D uint32_t round16(uint32_t bytes) { return (bytes + 15u) & ~15u; }
-
-DR_D void phase_accum_tma(const EngineParams& P, Smem& sm) {
-  const uint32_t parity_slot = P.epoch & 1u;
-  uint32_t* my_slot = slot_ptr(P.arena[P.rank], P, parity_slot, P.rank);
-  {
-    uint4* p = reinterpret_cast<uint4*>(my_slot);
-    const uint32_t n4 = (P.payload_words + 3u) >> 2;
-    const uint4 z = make_uint4(0, 0, 0, 0);
-    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n4; i += gridDim.x * kThreads) p[i] = z;
-  }
-  if (sharded(P) && blockIdx.x == 0 && threadIdx.x == 0) *s2_ptr(P.arena[P.rank], P, parity_slot, P.rank) = 0u;
-  clear_hist(sm);
-  const bool has_resid = (P.beta != 0.0f);
-  const Ring ring = ring_setup(P, sm, 2u * kTile * 4u, 8u);      // stage = g tile | r tile
-  uint32_t t0, t_end;
-  tile_range(P, t0, t_end);
-  const uint32_t n_my = t_end - t0;
-  auto issue = [&](uint32_t i) {                                  // thread 0 only
-    const Tile t = load_tile(P, t0 + i);
-    const uint32_t s = i % ring.n_stages, bytes = round16(t.n * 4u);
-    uint8_t* dst = ring.buf + (size_t)s * ring.stage_bytes;
-    mbar_expect_tx(&sm.bar[s], has_resid ? 2u * bytes : bytes);
-    bulk_g2s(dst, P.grad + t.base, bytes, &sm.bar[s]);
-    if (has_resid) bulk_g2s(dst + kTile * 4u, P.resid + t.base, bytes, &sm.bar[s]);
-  };
-  if (threadIdx.x == 0) for (uint32_t i = 0; i < min(ring.n_stages, n_my); ++i) issue(i);
-  uint32_t cur = kNoTensor, lower = 0, n_mine = 0;
-  auto finish = [&]() {
-    const uint32_t k = __ldg(&P.tensors[cur].k), nt = __ldg(&P.tensors[cur].n_tiles);
-    if (finish_digit(P, sm, 0, cur, n_mine, nt, k)) write_digit1(P, sm, cur);
-  };
-  for (uint32_t i = 0; i < n_my; ++i) {
-    const Tile ti = load_tile(P, t0 + i);
-    if (ti.tensor != cur) {
-      if (cur != kNoTensor) finish();
-      cur = ti.tensor; n_mine = 0;
-      const uint32_t prev = P.use_history ? __ldcg(&P.sel[cur].prev_thr) : 0u;
-      lower = (prev > (1u << 23)) ? prev - (1u << P.hist_shift) : 0u;
-    }
-    const uint32_t s = i % ring.n_stages;
-    mbar_wait(&sm.bar[s], (i / ring.n_stages) & 1u, P.status);
-    const float4* sg = reinterpret_cast<const float4*>(ring.buf + (size_t)s * ring.stage_bytes);
-    const float4* sr = sg + kTile / 4;
-    uint32_t key[8];
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const uint32_t v4 = c * kThreads + threadIdx.x, e = v4 * 4u;
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (e < ti.n) {
-        const float4 g = sg[v4];
-        if (has_resid) {
-          const float4 r = sr[v4];
-          a.x = P.beta * r.x + P.gamma * g.x; a.y = P.beta * r.y + P.gamma * g.y;
-          a.z = P.beta * r.z + P.gamma * g.z; a.w = P.beta * r.w + P.gamma * g.w;
-        } else {
-          a.x = P.gamma * g.x; a.y = P.gamma * g.y; a.z = P.gamma * g.z; a.w = P.gamma * g.w;
-        }
-        *reinterpret_cast<float4*>(P.resid + ti.base + e) = a;
-      }
-      const float av[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const bool ok = e + j < ti.n;
-        key[c * 4 + j] = ok ? (__float_as_uint(av[j]) & 0x7FFFFFFFu) : 0xFFFFFFFFu;
-        if (ok && key[c * 4 + j] >= lower) atomicAdd(&sm.u.hist[key[c * 4 + j] >> 20], 1u);
-      }
-    }
-    n_mine += 1;
-    __syncthreads();                                               // everyone is done with stage s
-    if (threadIdx.x == 0 && i + ring.n_stages < n_my) { fence_proxy_async(); issue(i + ring.n_stages); }
-    if (ti.single) {
-      const uint32_t k = __ldg(&P.tensors[cur].k);
+    const uint32_t k = __ldg(&tdp->k), nt = __ldg(&tdp->n_tiles);
+    if (t0.single) {
       resolve_bins([&](int b) { return sm.u.hist[b]; }, kHistBins, k, sm.s);
       const uint32_t bin1 = sm.s.res[0], krem1 = sm.s.res[1];
-      write_digit1(P, sm, cur);
+      if (tid == 0) {
+        if (bin1 == kUnsafe) atomicExch(P.status, kErrResolve);
+        P.sel[cur].bin1 = bin1; P.sel[cur].krem1 = krem1;
+      }
       clear_hist(sm);
       if (bin1 != kUnsafe) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (key[j] != 0xFFFFFFFFu && (key[j] >> 20) == bin1) atomicAdd(&sm.u.hist[(key[j] >> 9) & 0x7FFu], 1u);
+        for (int i = 0; i < 8; ++i)
+          if (keys[i] != 0xFFFFFFFFu && (keys[i] >> 20) == bin1) atomicAdd(&sm.u.hist[(keys[i] >> 9) & 0x7FFu], 1u);
         resolve_bins([&](int b) { return sm.u.hist[b]; }, kHistBins, krem1, sm.s);
         write_final(P, sm, cur, bin1);
-        if (threadIdx.x == 0) P.sel[cur].done_epoch = P.epoch;
+        if (tid == 0) P.sel[cur].done_epoch = P.epoch;
         clear_hist(sm);
       }
-      cur = kNoTensor; n_mine = 0;
-    }
-  }
-  if (cur != kNoTensor) finish();
-}
-
-DR_D void phase_hist2_tma(const EngineParams& P, Smem& sm) {
-  clear_hist(sm);
-  const Ring ring = ring_setup(P, sm, kTile * 4u, 8u);
-  uint32_t t0, t_end;
-  tile_range(P, t0, t_end);
-  const uint32_t n_my = t_end - t0;
-  // tiles of tensors that are already done are never fetched: the issue order follows the list of active tiles
-  uint32_t cur = kNoTensor, n_mine = 0, k_cur = 0, nt_cur = 0, prefix = 0;
-  bool active = false;
-  auto tile_active = [&](uint32_t tensor) { return __ldcg(&P.sel[tensor].done_epoch) != P.epoch; };
-  // thread 0 keeps its own cursor over the active tiles to issue; consumers walk the same sequence
-  uint32_t issue_pos = 0, issued = 0;         // thread 0 state
-  auto issue_next = [&]() {                    // thread 0: fetch the next active tile, if any
-    while (issue_pos < n_my) {
-      const Tile t = load_tile(P, t0 + issue_pos);
-      ++issue_pos;
-      if (!tile_active(t.tensor)) continue;
-      const uint32_t s = issued % ring.n_stages, bytes = round16(t.n * 4u);
-      mbar_expect_tx(&sm.bar[s], bytes);
-      bulk_g2s(ring.buf + (size_t)s * ring.stage_bytes, P.resid + t.base, bytes, &sm.bar[s]);
-      ++issued;
-      return;
-    }
-  };
-  if (threadIdx.x == 0) for (uint32_t i = 0; i < ring.n_stages; ++i) issue_next();
-  auto finish = [&]() {
-    if (!active) return;
-    if (finish_digit(P, sm, 2, cur, n_mine, nt_cur, k_cur)) write_final(P, sm, cur, prefix);
-  };
-  uint32_t consumed = 0;
-  for (uint32_t i = 0; i < n_my; ++i) {
-    const Tile ti = load_tile(P, t0 + i);
-    if (ti.tensor != cur) {
-      if (cur != kNoTensor) finish();
-      cur = ti.tensor; n_mine = 0;
-      nt_cur = __ldg(&P.tensors[cur].n_tiles);
-      active = tile_active(cur);
-      prefix = __ldcg(&P.sel[cur].bin1);
-      k_cur = __ldcg(&P.sel[cur].krem1);
-      if (active && prefix == kUnsafe && threadIdx.x == 0) atomicExch(P.status, kErrResolve);
-    }
-    if (!active) continue;
-    const uint32_t s = consumed % ring.n_stages;
-    mbar_wait(&sm.bar[s], (consumed / ring.n_stages) & 1u, P.status);
-    const uint4* sq = reinterpret_cast<const uint4*>(ring.buf + (size_t)s * ring.stage_bytes);
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const uint32_t v4 = c * kThreads + threadIdx.x, e = v4 * 4u;
-      if (e < ti.n) {
-        const uint4 q = sq[v4];
-        const uint32_t key[4] = {q.x & 0x7FFFFFFFu, q.y & 0x7FFFFFFFu, q.z & 0x7FFFFFFFu, q.w & 0x7FFFFFFFu};
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (e + j < ti.n && (key[j] >> 20) == prefix) atomicAdd(&sm.u.hist[(key[j] >> 9) & 0x7FFu], 1u);
+    } else if (finish_digit(P, sm, 1, cur, seg_end - tile, nt, k)) {
+      if (tid == 0) {
+        if (sm.s.res[0] == kUnsafe) atomicExch(P.status, kErrResolve);
+        P.sel[cur].bin1 = sm.s.res[0]; P.sel[cur].krem1 = sm.s.res[1]; P.sel[cur].done_epoch = 0;
       }
     }
-    n_mine += 1;
-    ++consumed;
-    __syncthreads();
-    if (threadIdx.x == 0) { fence_proxy_async(); issue_next(); }
-  }
-  if (cur != kNoTensor) finish();
-}
-
-DR_D void phase_insert_tma(const EngineParams& P, Smem& sm) {
-  const uint32_t parity_slot = P.epoch & 1u;
-  uint32_t* my_slot = slot_ptr(P.arena[P.rank], P, parity_slot, P.rank);
-  uint32_t* queue = sm.u.hist;
-  const Ring ring = ring_setup(P, sm, kTile * 4u, 8u);
-  uint32_t t0, t_end;
-  tile_range(P, t0, t_end);
-  const uint32_t n_my = t_end - t0;
-  auto issue = [&](uint32_t i) {
-    const Tile t = load_tile(P, t0 + i);
-    const uint32_t s = i % ring.n_stages, bytes = round16(t.n * 4u);
-    mbar_expect_tx(&sm.bar[s], bytes);
-    bulk_g2s(ring.buf + (size_t)s * ring.stage_bytes, P.resid + t.base, bytes, &sm.bar[s]);
-  };
-  if (threadIdx.x == 0) for (uint32_t i = 0; i < min(ring.n_stages, n_my); ++i) issue(i);
-  uint32_t cur = kNoTensor, T22 = 1;
-  for (uint32_t i = 0; i < n_my; ++i) {
-    const Tile ti = load_tile(P, t0 + i);
-    if (ti.tensor != cur) {
-      cur = ti.tensor;
-      load_tensor(P, cur, sm);
-      T22 = __ldcg(&P.sel[cur].thr) >> 9;
-    }
-    const uint32_t s = i % ring.n_stages;
-    mbar_wait(&sm.bar[s], (i / ring.n_stages) & 1u, P.status);
-    const uint32_t* sv = reinterpret_cast<const uint32_t*>(ring.buf + (size_t)s * ring.stage_bytes);
-    uint32_t mask = 0;
-    if (sm.td.mode == kModeBloom) {
-#pragma unroll
-      for (int c = 0; c < kPerThread; ++c) {
-        const uint32_t e = c * kThreads + threadIdx.x;
-        if (e < ti.n && ((sv[e] & 0x7FFFFFFFu) >> 9) >= T22) mask |= 1u << c;
-      }
-    }
-    __syncthreads();                                               // stage s consumed
-    if (threadIdx.x == 0 && i + ring.n_stages < n_my) { fence_proxy_async(); issue(i + ring.n_stages); }
-    if (sm.td.mode == kModeBloom && sm.td.off_hint)
-      build_hint(mask, sm.s, my_slot + sm.td.off_hint + 4u * ((t0 + i) - sm.td.tile_begin));
-    if (sm.td.mode == kModeBloom) {
-      const uint32_t lane = threadIdx.x & 31u;
-      const uint32_t cnt = __popc(mask);
-      uint32_t incl = cnt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const uint32_t nb = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += nb; }
-      if (threadIdx.x == 0) sm.s.lb = 0;
-      __syncthreads();
-      uint32_t wbase = 0;
-      if (lane == 31 && incl) wbase = atomicAdd(&sm.s.lb, incl);
-      wbase = __shfl_sync(0xFFFFFFFFu, wbase, 31);
-      uint32_t slot = wbase + incl - cnt;
-#pragma unroll
-      for (int c = 0; c < kPerThread; ++c) if ((mask >> c) & 1u) queue[slot++] = ti.local0 + c * kThreads + threadIdx.x;
-      __syncthreads();
-      const uint32_t total = sm.s.lb, n_hash = sm.td.n_hash, m_bits = sm.td.m_bits;
-      uint32_t* filter = my_slot + sm.td.off_filter;
-      for (uint32_t q = threadIdx.x; q < total * n_hash; q += kThreads) {
-        const uint32_t ent = q / n_hash, j = q - ent * n_hash;
-        const HashAB h = hash_ab(queue[ent], P.seed);
-        const uint32_t pos = mulhi32(h.a + j * h.b, m_bits);
-        atomicOr(filter + (pos >> 5), 1u << (pos & 31u));
-      }
-      __syncthreads();
-    }
+    tile = seg_end;
   }
 }
 
@@ -857,151 +540,425 @@ DR_D void rle_zero_streams(const EngineParams& P) {
 }
 
 // ===========================================================================
-// phase 4: universe query — per-element flags + per-tile counts
+// phase 2: digit 2 of the select over the candidate lists (keys whose digit 1 is the threshold bin)
 // ===========================================================================
-DR_D void phase_query(const EngineParams& P, Smem& sm) {
-  const uint32_t parity = P.epoch & 1u;
-  uint32_t* my_slot = slot_ptr(P.arena[P.rank], P, parity, P.rank);
-  uint32_t cur = kNoTensor, T22 = 1;
-  bool staged = false;
+DR_D void phase_hist2(const EngineParams& P, Smem& sm) {
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  // per-tile counts are accumulated by the insert (raw / rle) and query (bloom) phases of this step
+  for (uint32_t i = blockIdx.x * kThreads + tid; i < P.n_tiles; i += gridDim.x * kThreads) P.tile_count[i] = 0u;
+  clear_hist(sm);
   uint32_t tile, t_end;
   tile_range(P, tile, t_end);
-  for (; tile < t_end; ++tile) {
-    const Tile ti = load_tile(P, tile);
-    if (ti.tensor != cur) {
-      cur = ti.tensor;
-      load_tensor(P, cur, sm);
-      T22 = __ldcg(&P.sel[cur].thr) >> 9;
-      staged = false;
-      if (sm.td.mode == kModeBloom && sm.td.n_filter_words <= P.filter_smem_words) {
-        stage_filter(my_slot + sm.td.off_filter, sm.td.n_filter_words);
-        staged = true;
+  while (tile < t_end) {
+    const Tile t0 = load_tile(P, tile);
+    const uint32_t cur = t0.tensor;
+    const TensorDesc* tdp = P.tensors + cur;
+    const uint32_t nt = __ldg(&tdp->n_tiles);
+    const uint32_t seg_end = min(t_end, __ldg(&tdp->tile_begin) + nt);
+    if (__ldcg(&P.sel[cur].done_epoch) == P.epoch) { tile = seg_end; continue; }     // one-tile / fixed-threshold tensors
+    const uint32_t prefix = __ldcg(&P.sel[cur].bin1), k_cur = __ldcg(&P.sel[cur].krem1);
+    if (prefix == kUnsafe && tid == 0) atomicExch(P.status, kErrResolve);
+    // software pipeline: the next tile's count and first 64 keys are in flight while this tile is binned
+    uint32_t c_n = __ldcg(P.cand_cnt + tile * kWarps + warp);
+    uint32_t ka_n = __ldcg(P.cand_key + chunk_of(tile, warp) + lane), kb_n = __ldcg(P.cand_key + chunk_of(tile, warp) + 32u + lane);
+    for (uint32_t tl = tile; tl < seg_end; ++tl) {
+      const uint32_t c = c_n, ka = ka_n, kb = kb_n;
+      const size_t chunk = chunk_of(tl, warp);
+      if (tl + 1 < seg_end) {
+        c_n = __ldcg(P.cand_cnt + (tl + 1) * kWarps + warp);
+        ka_n = __ldcg(P.cand_key + chunk_of(tl + 1, warp) + lane);
+        kb_n = __ldcg(P.cand_key + chunk_of(tl + 1, warp) + 32u + lane);
+      }
+      if (lane < c && (ka >> 20) == prefix) atomicAdd(&sm.u.hist[(ka >> 9) & 0x7FFu], 1u);
+      if (lane + 32u < c && (kb >> 20) == prefix) atomicAdd(&sm.u.hist[(kb >> 9) & 0x7FFu], 1u);
+      for (uint32_t j = 64u + lane; j < c; j += 32u) {
+        const uint32_t k = __ldcg(P.cand_key + chunk + j);
+        if ((k >> 20) == prefix) atomicAdd(&sm.u.hist[(k >> 9) & 0x7FFu], 1u);
       }
     }
-    uint32_t valid = 0;
-#pragma unroll
-    for (int c = 0; c < kPerThread; ++c) if (c * kThreads + threadIdx.x < ti.n) valid |= 1u << c;
-    uint32_t flags = 0;
-    if (sm.td.mode == kModeBloom) {
-      const uint32_t* filter = my_slot + sm.td.off_filter;
-      if (sm.td.off_hint) {
-        const uint4 hq = __ldcg(reinterpret_cast<const uint4*>(my_slot + sm.td.off_hint + 4u * (tile - sm.td.tile_begin)));
-        const uint32_t h[4] = {hq.x, hq.y, hq.z, hq.w};
-        valid &= valid_from_hint(h);
-      }
-      if (staged) flags = bloom_test8(ti.local0 + threadIdx.x, valid, P.seed, sm.td.n_hash, sm.td.m_bits,
-                                      [&](uint32_t w) { return g_filter_smem[w]; });
-      else flags = bloom_test8(ti.local0 + threadIdx.x, valid, P.seed, sm.td.n_hash, sm.td.m_bits,
-                               [&](uint32_t w) { return filter[w]; });
-    } else {
-#pragma unroll
-      for (int c = 0; c < kPerThread; ++c) {
-        const uint32_t e = c * kThreads + threadIdx.x;
-        if (e < ti.n && ((__float_as_uint(__ldcg(P.resid + ti.base + e)) & 0x7FFFFFFFu) >> 9) >= T22) flags |= 1u << c;
-      }
-    }
-    P.flag_buf[(size_t)tile * kThreads + threadIdx.x] = (uint8_t)flags;
-    // per-tile count: one fire-and-forget RED per warp (tile_count is zeroed by the previous step's decode
-    // phase) — no CTA barrier in this loop, so warps run ahead through their tiles independently
-    if (P.warp_count) {
-      const uint32_t lane = threadIdx.x & 31u;
-      uint32_t pc = 0, mine = 0;
-#pragma unroll
-      for (int c = 0; c < kPerThread; ++c) {
-        const uint32_t n = __popc(__ballot_sync(0xFFFFFFFFu, (flags >> c) & 1u));
-        pc += n;
-        if (lane == (uint32_t)c) mine = n;
-      }
-      if (lane < (uint32_t)kPerThread) P.warp_count[(size_t)tile * 128u + lane * kWarps + (threadIdx.x >> 5)] = (uint8_t)mine;
-      if (lane == 0 && pc) atomicAdd(P.tile_count + tile, pc);
-      continue;
-    }
-    uint32_t pc = __popc(flags);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) pc += __shfl_xor_sync(0xFFFFFFFFu, pc, o);
-    if ((threadIdx.x & 31u) == 0 && pc) atomicAdd(P.tile_count + tile, pc);
+    if (finish_digit(P, sm, 2, cur, seg_end - tile, nt, k_cur)) write_final(P, sm, cur, prefix);
+    tile = seg_end;
   }
 }
 
 // ===========================================================================
-// phase 5: ordered compaction + value gather + residual update
+// phase 3: the selected candidates (key >= threshold) build the index side of the slot.
+//   bloom : occupancy-hint bit of the element's 32-group + n_hash filter bits (RED.OR into the outgoing slot)
+//   raw / rle : the positive masks directly (there is no membership test to run) + per-tile counts
+// Warp-private: a warp walks its own candidate chunks; the selected elements of one iteration are compacted into a
+// 32-entry SMEM row so that every lane sets one (element, hash) bit — no divergent per-element hash loops.
 // ===========================================================================
-// kFull = false compiles the value-codec / run-length branches out of the two hot loops (emit, decode): the
-// index-only kernel (plain pairs, bloom) keeps its registers for the probe loop instead of spilling
-template <bool kFull>
-DR_D void phase_emit(const EngineParams& P, Smem& sm) {
+DR_D void phase_insert(const EngineParams& P, Smem& sm) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t parity = P.epoch & 1u;
   uint32_t* my_slot = slot_ptr(P.arena[P.rank], P, parity, P.rank);
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  uint32_t* row = sm.u.sel[warp];
+  const uint32_t lt = (1u << lane) - 1u;
+  uint32_t tile, t_end;
+  tile_range(P, tile, t_end);
+  if (tile >= t_end) return;
+  uint32_t cur = kNoTensor, thr = 0xFFFFFFFFu, mode = 0, n_hash = 0, m_bits = 0, recip = 0, tile_begin = 0;
+  uint32_t* filter = nullptr;
+  uint32_t* hint = nullptr;
+  auto process = [&](uint32_t tl, uint32_t local0, bool have, uint32_t k, uint32_t e, uint32_t& n_sel_tile) {
+    const bool sel = have && k >= thr;
+    const uint32_t b = __ballot_sync(kFullMask, sel);
+    if (b == 0u) return;
+    if (mode != (uint32_t)kModeBloom) {
+      if (sel) atomicOr(P.pos_mask + (size_t)tl * kGroupsPerTile + (e >> 5), 1u << (e & 31u));
+      n_sel_tile += __popc(b);
+      return;
+    }
+    if (sel) {
+      row[__popc(b & lt)] = local0 + e;
+      if (hint) atomicOr(hint + 4u * (tl - tile_begin) + (e >> 10), 1u << ((e >> 5) & 31u));
+    }
+    __syncwarp();
+    const uint32_t pairs = (uint32_t)__popc(b) * n_hash;
+    for (uint32_t p = lane; p < pairs; p += 32u) {
+      const uint32_t ent = (n_hash == 1u) ? p : __umulhi(p, recip);
+      const uint32_t j = p - ent * n_hash;
+      const HashAB h = hash_ab(row[ent], P.seed);
+      const uint32_t pos = mulhi32(h.a + j * h.b, m_bits);
+      atomicOr(filter + (pos >> 5), 1u << (pos & 31u));
+    }
+    __syncwarp();
+  };
+  uint32_t c_n = __ldcg(P.cand_cnt + tile * kWarps + warp);
+  uint32_t ka_n = __ldcg(P.cand_key + chunk_of(tile, warp) + lane), kb_n = __ldcg(P.cand_key + chunk_of(tile, warp) + 32u + lane);
+  uint32_t ea_n = __ldcg(P.cand_e + chunk_of(tile, warp) + lane), eb_n = __ldcg(P.cand_e + chunk_of(tile, warp) + 32u + lane);
+  for (; tile < t_end; ++tile) {
+    const Tile ti = load_tile(P, tile);
+    const uint32_t c = c_n, ka = ka_n, kb = kb_n, ea = ea_n, eb = eb_n;
+    const size_t chunk = chunk_of(tile, warp);
+    if (tile + 1 < t_end) {
+      const size_t cn = chunk_of(tile + 1, warp);
+      c_n = __ldcg(P.cand_cnt + (tile + 1) * kWarps + warp);
+      ka_n = __ldcg(P.cand_key + cn + lane); kb_n = __ldcg(P.cand_key + cn + 32u + lane);
+      ea_n = __ldcg(P.cand_e + cn + lane); eb_n = __ldcg(P.cand_e + cn + 32u + lane);
+    }
+    if (ti.tensor != cur) {
+      cur = ti.tensor;
+      const TensorDesc* tdp = P.tensors + cur;
+      mode = __ldg(&tdp->mode); n_hash = __ldg(&tdp->n_hash); m_bits = __ldg(&tdp->m_bits);
+      tile_begin = __ldg(&tdp->tile_begin);
+      filter = my_slot + __ldg(&tdp->off_filter);
+      const uint32_t oh = __ldg(&tdp->off_hint);
+      hint = oh ? my_slot + oh : nullptr;
+      recip = n_hash > 1u ? (0xFFFFFFFFu / n_hash) + 1u : 0u;
+      thr = __ldcg(&P.sel[cur].thr);
+    }
+    uint32_t n_sel_tile = 0;
+    if (c) {                                                               // warp-uniform
+      process(tile, ti.local0, lane < c, ka, ea, n_sel_tile);
+      if (c > 32u) process(tile, ti.local0, lane + 32u < c, kb, eb, n_sel_tile);
+      for (uint32_t j0 = 64u; j0 < c; j0 += 32u) {
+        const bool have = j0 + lane < c;
+        const uint32_t k = have ? __ldcg(P.cand_key + chunk + j0 + lane) : 0u;
+        const uint32_t e = have ? (uint32_t)__ldcg(P.cand_e + chunk + j0 + lane) : 0u;
+        process(tile, ti.local0, have, k, e, n_sel_tile);
+      }
+    }
+    if (mode != (uint32_t)kModeBloom && lane == 0 && n_sel_tile) atomicAdd(P.tile_count + tile, n_sel_tile);
+  }
+}
+
+// ===========================================================================
+// Membership test of the hinted 32-element groups of a run of tiles against ONE filter -> group bitmasks.
+//
+// Work item = one hint word (32 groups = a quarter tile), handed out dynamically (SMEM counter) so the 16 warps
+// stay balanced whatever the hint density.  A warp owns whole groups: lane l tests element 32*g + l.
+// Two levels: level 1 runs the first two probes for every element of a hinted group (all lanes busy); the ~25 %
+// survivors are appended to a per-warp ring in SMEM, and whenever 32 have gathered level 2 finishes their probe
+// chains on a dense batch.  A hinted group always holds a true positive, which used to drag its whole warp through
+// all n_hash probes at 1-2 active lanes (v10: 19/32 lane efficiency, ~230 warp-instructions per hinted group).
+// Positives land in mask_out (word = group, bit = lane) by RED.OR; level 1 zeroes the word first.
+// ===========================================================================
+struct ProbeCtx {
+  const uint32_t* hint;     // hint words of this tensor, 4 per tile (nullptr: every group is tested)
+  const uint32_t* prefix;   // decode: the sender's per-tile prefix table (nullptr: query)
+  uint32_t n_sel, cutoff;   // decode gating (query: 0xFFFFFFFF both)
+  uint32_t* mask_out;       // [n_tiles * 128]
+  uint32_t* tile_count;     // query: positives per tile (nullptr: not counted)
+  uint32_t tile_begin;      // first global tile of the tensor
+  uint32_t seg_a, seg_b;    // global tile range handled by this CTA
+  uint32_t n_hash, m_bits, seed;
+};
+
+// caller: sm.s.lb = 0 and __syncthreads() before; __syncthreads() after
+template <typename LoadFn>
+DR_D void probe_segment(const EngineParams& P, Smem& sm, const ProbeCtx& c, LoadFn ld) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  uint32_t* q = sm.u.q[warp];
+  uint32_t qh = 0, qn = 0;
+  const uint32_t lt = (1u << lane) - 1u;
+  const uint32_t n_items = (c.seg_b - c.seg_a) * 4u;
+  const uint32_t m_bits = c.m_bits;
+  auto level2 = [&](uint32_t n_take) {
+    __syncwarp();
+    if (lane < n_take) {
+      const uint32_t gp = q[(qh + lane) & 63u];
+      const uint32_t tile = gp >> 12, e = gp & 4095u;
+      const uint32_t x = ((tile - c.tile_begin) << 12) + e;
+      const HashAB h = hash_ab(x, c.seed);
+      uint32_t v = h.a + 2u * h.b;
+      bool pass = true;
+      uint32_t j = 2;
+      for (; j + 1 < c.n_hash; j += 2) {
+        const uint32_t p0 = mulhi32(v, m_bits), p1 = mulhi32(v + h.b, m_bits);
+        const uint32_t w0 = ld(p0 >> 5), w1 = ld(p1 >> 5);
+        if (!((w0 >> (p0 & 31u)) & (w1 >> (p1 & 31u)) & 1u)) { pass = false; break; }
+        v += 2u * h.b;
+      }
+      if (pass && j < c.n_hash) {
+        const uint32_t p0 = mulhi32(v, m_bits);
+        pass = ((ld(p0 >> 5) >> (p0 & 31u)) & 1u) != 0u;
+      }
+      if (pass) {
+        atomicOr(c.mask_out + (size_t)tile * kGroupsPerTile + (e >> 5), 1u << (e & 31u));
+        if (c.tile_count) atomicAdd(c.tile_count + tile, 1u);
+      }
+    }
+    qh = (qh + n_take) & 63u;
+    qn -= n_take;
+    __syncwarp();
+  };
+  while (true) {
+    uint32_t it = 0;
+    if (lane == 0) it = atomicAdd(&sm.s.lb, 1u);
+    it = __shfl_sync(kFullMask, it, 0);
+    if (it >= n_items) break;
+    const uint32_t tile = c.seg_a + (it >> 2), qd = it & 3u;
+    const Tile ti = load_tile(P, tile);
+    const uint32_t tl = tile - c.tile_begin;
+    if (c.prefix) {
+      const uint32_t pre = __ldcg(c.prefix + tl);
+      if (!(pre < c.n_sel && ti.local0 <= c.cutoff)) continue;             // tile-uniform: nothing of this sender lands here
+    }
+    uint32_t hw = c.hint ? __ldcg(c.hint + 4u * tl + qd) : 0xFFFFFFFFu;
+    const uint32_t n_groups = (ti.n + 31u) >> 5, g0 = qd * 32u;
+    if (g0 >= n_groups) continue;
+    if (n_groups - g0 < 32u) hw &= (1u << (n_groups - g0)) - 1u;
+    while (hw) {
+      const uint32_t j = (uint32_t)__ffs((int)hw) - 1u;
+      hw &= hw - 1u;
+      const uint32_t g = g0 + j, e = g * 32u + lane, x = ti.local0 + e;
+      const bool valid = e < ti.n && x <= c.cutoff;
+      const HashAB h = hash_ab(x, c.seed);
+      const uint32_t p0 = mulhi32(h.a, m_bits);
+      uint32_t ok = ld(p0 >> 5) >> (p0 & 31u);
+      if (c.n_hash >= 2u) {
+        const uint32_t p1 = mulhi32(h.a + h.b, m_bits);
+        ok &= ld(p1 >> 5) >> (p1 & 31u);
+      }
+      const bool pass = valid && (ok & 1u);
+      const uint32_t b = __ballot_sync(kFullMask, pass);
+      const size_t gi = (size_t)tile * kGroupsPerTile + g;
+      if (c.n_hash <= 2u) {
+        if (lane == 0) {
+          c.mask_out[gi] = b;
+          if (c.tile_count && b) atomicAdd(c.tile_count + tile, (uint32_t)__popc(b));
+        }
+      } else {
+        if (lane == 0) c.mask_out[gi] = 0u;
+        if (pass) q[(qh + qn + (uint32_t)__popc(b & lt)) & 63u] = (tile << 12) | e;
+        qn += (uint32_t)__popc(b);
+        if (qn >= 32u) level2(32u);
+      }
+    }
+  }
+  if (qn) level2(qn);
+}
+
+// ===========================================================================
+// phase 4: universe query of my own filter (bloom tensors only) -> pos_mask + tile_count
+// ===========================================================================
+DR_D void phase_query(const EngineParams& P, Smem& sm) {
+  const uint32_t tid = threadIdx.x;
+  {  // the select histograms are free after the insert barrier: zero them for the next step
+    uint4* h = reinterpret_cast<uint4*>(P.hist);
+    const size_t n4 = (size_t)kNumHist * P.n_tensors * kHistBins / 4;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (size_t i = (size_t)blockIdx.x * kThreads + tid; i < n4; i += (size_t)gridDim.x * kThreads) h[i] = z;
+    for (uint32_t i = blockIdx.x * kThreads + tid; i < (uint32_t)kNumHist * P.n_tensors; i += gridDim.x * kThreads)
+      P.hist_total[i] = 0u;
+    if (blockIdx.x == 0 && tid == 0) P.barrier[kUnsafeWord] = 0u;
+  }
+  const uint32_t parity = P.epoch & 1u;
+  uint32_t* my_slot = slot_ptr(P.arena[P.rank], P, parity, P.rank);
+  uint32_t tile, t_end;
+  tile_range(P, tile, t_end);
+  while (tile < t_end) {
+    const Tile t0 = load_tile(P, tile);
+    load_tensor(P, t0.tensor, sm);
+    const uint32_t seg_end = min(t_end, sm.td.tile_begin + sm.td.n_tiles);
+    if (sm.td.mode == (uint32_t)kModeBloom) {
+      const bool fits = sm.td.n_filter_words <= P.filter_smem_words;
+      const uint32_t* filter = my_slot + sm.td.off_filter;
+      if (fits) stage_filter(filter, sm.td.n_filter_words);
+      if (tid == 0) sm.s.lb = 0;
+      __syncthreads();
+      ProbeCtx c;
+      c.hint = sm.td.off_hint ? my_slot + sm.td.off_hint : nullptr;
+      c.prefix = nullptr; c.n_sel = 0xFFFFFFFFu; c.cutoff = 0xFFFFFFFFu;
+      c.mask_out = P.pos_mask; c.tile_count = P.tile_count;
+      c.tile_begin = sm.td.tile_begin; c.seg_a = tile; c.seg_b = seg_end;
+      c.n_hash = sm.td.n_hash; c.m_bits = sm.td.m_bits; c.seed = P.seed;
+      if (fits) probe_segment(P, sm, c, [&](uint32_t w) { return g_filter_smem[w]; });
+      else probe_segment(P, sm, c, [&](uint32_t w) { return __ldcg(filter + w); });
+      __syncthreads();
+    }
+    tile = seg_end;
+  }
+}
+
+// ===========================================================================
+// phase 5: ordered compaction + value gather + residual update, one WARP per tile.
+// The positives of a tile are 128 mask words; lane l owns groups 4l..4l+3, the in-tile rank of an element is a
+// popcount prefix — no per-element flags, no CTA barrier in the tile loop.  The exclusive prefix of every tile of my
+// range (count of positives in the tensor's earlier tiles) comes from one segmented warp scan over tile_count.
+// W == 1 and plain fp32 values: the element is also written into the (zero-filled) dense output — the decode of a
+// rank's own contribution costs nothing extra.
+// ===========================================================================
+DR_D uint32_t hint_nibble(const uint32_t* hint, uint32_t tile_local, uint32_t lane) {
+  if (!hint) return 0xFu;
+  const uint32_t hw = __ldcg(hint + 4u * tile_local + (lane >> 3));
+  return (hw >> ((lane & 7u) * 4u)) & 0xFu;
+}
+
+// this lane's 4 mask words of a tile, restricted to hinted groups that hold real elements
+DR_D void load_masks(const uint32_t* masks, uint32_t tile, uint32_t nib, uint32_t n, uint32_t lane, uint32_t (&mm)[4]) {
+  const uint4 m4 = __ldcg(reinterpret_cast<const uint4*>(masks + (size_t)tile * kGroupsPerTile) + lane);
+  const uint32_t raw[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t g = 4u * lane + (uint32_t)j;
+    mm[j] = (((nib >> j) & 1u) && g * 32u < n) ? raw[j] : 0u;
+  }
+}
+
+template <bool kFull>
+DR_D void phase_emit(const EngineParams& P, Smem& sm) {
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t parity = P.epoch & 1u;
+  uint32_t* my_slot = slot_ptr(P.arena[P.rank], P, parity, P.rank);
+  if (blockIdx.x == 0 && tid == 0) {
     my_slot[0] = kMagic; my_slot[1] = P.epoch; my_slot[2] = P.n_tensors; my_slot[3] = P.payload_words;
     my_slot[4] = (uint32_t)P.rank;
   }
-  uint32_t cur = kNoTensor, T22 = 1, excl = 0, rank_buf = 0;
-  uint32_t tile, t_end;
-  tile_range(P, tile, t_end);
-  for (; tile < t_end; ++tile) {
-    const Tile ti = load_tile(P, tile);
-    if (ti.tensor != cur) {
-      cur = ti.tensor;
-      load_tensor(P, cur, sm);
-      T22 = __ldcg(&P.sel[cur].thr) >> 9;
-      // exclusive prefix at my first tile of this tensor: sum of the counts of the tensor's earlier tiles
+  uint32_t t0, t_end;
+  tile_range(P, t0, t_end);
+  for (uint32_t c0 = t0; c0 < t_end; c0 += (uint32_t)kTile) {
+    const uint32_t n_chunk = min((uint32_t)kTile, t_end - c0);
+    // ---- exclusive prefix of every tile of the chunk inside its tensor
+    const Tile first = load_tile(P, c0);
+    {
+      const uint32_t tb = __ldg(&P.tensors[first.tensor].tile_begin);
       uint32_t part = 0;
-      for (uint32_t j = sm.td.tile_begin + threadIdx.x; j < tile; j += kThreads) part += __ldcg(P.tile_count + j);
+      for (uint32_t j = tb + tid; j < c0; j += kThreads) part += __ldcg(P.tile_count + j);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
-      if (threadIdx.x == 0) sm.s.lb = 0;
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(kFullMask, part, o);
       __syncthreads();
-      if ((threadIdx.x & 31u) == 0 && part) atomicAdd(&sm.s.lb, part);
+      if (tid == 0) sm.s.lb = 0;
       __syncthreads();
-      excl = sm.s.lb;
+      if (lane == 0 && part) atomicAdd(&sm.s.lb, part);
       __syncthreads();
     }
-    const uint32_t tile_local = tile - sm.td.tile_begin;
-    const uint32_t local0 = ti.local0;
-    const size_t base = ti.base;
-    DynHeader* dyn = reinterpret_cast<DynHeader*>(my_slot + kSlotHeaderWords) + cur;
-    const bool last_tile = (tile_local + 1 == sm.td.n_tiles);
-    const uint32_t flags = P.flag_buf[(size_t)tile * kThreads + threadIdx.x];
-    uint32_t rank[kPerThread], total;
-    if (P.warp_count) tile_rank_counts(flags, P.warp_count + (size_t)tile * 128u, rank, total);
-    else tile_rank(flags, sm.s, rank_buf, rank, total);
-    const uint32_t limit = (sm.td.mode == kModeBloom && P.policy != kPolicyP0) ? min(sm.td.k, sm.td.val_cap)
-                                                                               : sm.td.val_cap;
-    float* vals = reinterpret_cast<float*>(my_slot + sm.td.off_vals);
-    uint32_t* idxs = my_slot + sm.td.off_idx;
-    if (excl < limit) {
+    if (warp == 0) {
+      uint32_t carry = sm.s.lb, carry_tensor = first.tensor;
+      for (uint32_t i0 = 0; i0 < n_chunk; i0 += 32u) {
+        const uint32_t i = i0 + lane;
+        const bool valid = i < n_chunk;
+        const uint32_t v = valid ? __ldcg(P.tile_count + c0 + i) : 0u;
+        const uint32_t tens = valid ? load_tile(P, c0 + i).tensor : 0xFFFFFFFEu;
+        uint32_t prev_t = __shfl_up_sync(kFullMask, tens, 1);
+        if (lane == 0) prev_t = carry_tensor;
+        uint32_t fl = (tens != prev_t) ? 1u : 0u;                          // a new tensor starts at this tile
+        uint32_t x = v;
 #pragma unroll
-      for (int c = 0; c < kPerThread; ++c) {
-        if ((flags >> c) & 1u) {
-          const uint32_t rp = excl + rank[c];
-          if (rp < limit) {
-            const uint32_t e = c * kThreads + threadIdx.x;
-            vals[rp] = P.resid[base + e];
-            P.resid[base + e] = 0.0f;                      // residual is exactly 0 on the shipped set
-            if (sm.td.mode == kModeRaw) idxs[rp] = local0 + e;
-            else if (kFull && sm.td.mode == kModeRle) rle_put(idxs, rp, e);
-            if (kFull && sm.td.vmode) my_slot[sm.td.off_selidx + rp] = (uint32_t)(base + e);
-            if (rp == limit - 1u) dyn->cutoff = local0 + e;
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t y = __shfl_up_sync(kFullMask, x, o);
+          const uint32_t g = __shfl_up_sync(kFullMask, fl, o);
+          if (lane >= (uint32_t)o) { if (!fl) x += y; fl |= g; }
+        }
+        if (!fl) x += carry;                                               // still inside the tensor the previous 32 ended in
+        if (valid) sm.u.excl[i] = x - v;
+        carry = __shfl_sync(kFullMask, x, 31);
+        carry_tensor = __shfl_sync(kFullMask, tens, 31);
+      }
+    }
+    __syncthreads();
+    // ---- one warp per tile
+    uint32_t cur = kNoTensor;
+    uint32_t mode = 0, k = 0, val_cap = 0, off_vals = 0, off_idx = 0, off_prefix = 0, tile_begin = 0, n_tiles = 0,
+             vmode = 0, off_selidx = 0, thr = 0;
+    const uint32_t* hint = nullptr;
+    for (uint32_t i = warp; i < n_chunk; i += kWarps) {
+      const uint32_t tile = c0 + i;
+      const Tile ti = load_tile(P, tile);
+      if (ti.tensor != cur) {
+        cur = ti.tensor;
+        const TensorDesc* tdp = P.tensors + cur;
+        mode = __ldg(&tdp->mode); k = __ldg(&tdp->k); val_cap = __ldg(&tdp->val_cap);
+        off_vals = __ldg(&tdp->off_vals); off_idx = __ldg(&tdp->off_idx); off_prefix = __ldg(&tdp->off_prefix);
+        tile_begin = __ldg(&tdp->tile_begin); n_tiles = __ldg(&tdp->n_tiles);
+        vmode = __ldg(&tdp->vmode); off_selidx = __ldg(&tdp->off_selidx);
+        const uint32_t oh = __ldg(&tdp->off_hint);
+        hint = (mode == (uint32_t)kModeBloom && oh) ? my_slot + oh : nullptr;
+        thr = __ldcg(&P.sel[cur].thr);
+      }
+      const uint32_t excl = sm.u.excl[i];
+      const uint32_t tile_local = tile - tile_begin;
+      uint32_t mm[4];
+      load_masks(P.pos_mask, tile, hint_nibble(hint, tile_local, lane), ti.n, lane, mm);
+      const uint32_t c = (uint32_t)(__popc(mm[0]) + __popc(mm[1]) + __popc(mm[2]) + __popc(mm[3]));
+      const uint32_t incl = warp_incl_scan(c, lane);
+      const uint32_t total = __shfl_sync(kFullMask, incl, 31);
+      const uint32_t limit = (mode == (uint32_t)kModeBloom && P.policy != kPolicyP0) ? min(k, val_cap) : val_cap;
+      DynHeader* dyn = reinterpret_cast<DynHeader*>(my_slot + kSlotHeaderWords) + cur;
+      float* vals = reinterpret_cast<float*>(my_slot + off_vals);
+      uint32_t* idxs = my_slot + off_idx;
+      const bool scatter = (P.world == 1) && (vmode == 0u);
+      if (excl < limit && c) {
+        uint32_t rp = excl + incl - c;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t w = mm[j];
+          while (w) {
+            const uint32_t b = (uint32_t)__ffs((int)w) - 1u;
+            w &= w - 1u;
+            if (rp < limit) {
+              const uint32_t e = (4u * lane + (uint32_t)j) * 32u + b;
+              const size_t gi = (size_t)ti.base + e;
+              const float v = __ldcg(P.resid + gi);
+              vals[rp] = v;
+              P.resid[gi] = 0.0f;                                          // residual is exactly 0 on the shipped set
+              if (scatter) P.grad[gi] = v * P.scale;
+              if (mode == (uint32_t)kModeRaw) idxs[rp] = ti.local0 + e;
+              else if (kFull && mode == (uint32_t)kModeRle) rle_put(idxs, rp, e);
+              if (kFull && vmode) my_slot[off_selidx + rp] = (uint32_t)gi;
+              if (rp == limit - 1u) dyn->cutoff = ti.local0 + e;
+            }
+            ++rp;
           }
         }
       }
-    }
-    if (threadIdx.x == 0) {
-      if (sm.td.mode == kModeBloom) my_slot[sm.td.off_prefix + tile_local] = min(excl, limit);
-      else if (kFull && sm.td.mode == kModeRle)
-        reinterpret_cast<uint16_t*>(my_slot + sm.td.off_prefix)[tile_local] =
-            (uint16_t)(excl >= limit ? 0u : min(total, limit - excl));
-      if (last_tile) {
-        const uint32_t incl = excl + total;
-        dyn->n_sel = min(incl, limit);
-        dyn->n_pos = incl;
-        dyn->thr_bits = T22 << 9;
-        if (incl < limit) dyn->cutoff = 0xFFFFFFFFu;
-        P.sel[cur].prev_thr = T22 << 9;
+      if (lane == 0) {
+        if (mode == (uint32_t)kModeBloom) my_slot[off_prefix + tile_local] = min(excl, limit);
+        else if (kFull && mode == (uint32_t)kModeRle)
+          reinterpret_cast<uint16_t*>(my_slot + off_prefix)[tile_local] =
+              (uint16_t)(excl >= limit ? 0u : min(total, limit - excl));
+        if (tile_local + 1u == n_tiles) {
+          const uint32_t all = excl + total;
+          dyn->n_sel = min(all, limit);
+          dyn->n_pos = all;
+          dyn->thr_bits = thr;
+          if (all < limit) dyn->cutoff = 0xFFFFFFFFu;
+          P.sel[cur].prev_thr = thr;
+        }
       }
     }
-    excl += total;
+    __syncthreads();                                                       // sm.u.excl is rewritten by the next chunk
   }
 }
 
@@ -1094,7 +1051,7 @@ DR_D void phase_rank_scan(const EngineParams& P, Smem& sm) {
     for (int i = 0; i < kPer; ++i) { c[i] = __ldcg(cnt + threadIdx.x * kPer + i); sum += c[i]; }
     uint32_t incl = sum;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t nb = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) incl += nb; }
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t nb = __shfl_up_sync(kFullMask, incl, d); if (lane >= (uint32_t)d) incl += nb; }
     __syncthreads();
     if (lane == 31) sm.s.warp_tot[warp] = incl;
     __syncthreads();
@@ -1221,8 +1178,8 @@ DR_D void phase_fit(const EngineParams& P, Smem& sm) {
     for (int k = 0; k <= kMaxDeg; ++k) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
-        num[k] += __shfl_xor_sync(0xFFFFFFFFu, num[k], o);
-        den[k] += __shfl_xor_sync(0xFFFFFFFFu, den[k], o);
+        num[k] += __shfl_xor_sync(kFullMask, num[k], o);
+        den[k] += __shfl_xor_sync(kFullMask, den[k], o);
       }
     }
     float* coef = reinterpret_cast<float*>(my_slot + off_coef) + s * (deg + 1);
@@ -1249,7 +1206,7 @@ DR_D void phase_fix(const EngineParams& P, Smem& sm) {
       const float v = p < nq ? __ldcg(reinterpret_cast<const float*>(my_slot + sm.td.off_vals) + p) : 0.f;
       float ss = v * v;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
+      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(kFullMask, ss, o);
       __syncthreads();
       if ((threadIdx.x & 31u) == 0) sm.s.warp_tot[threadIdx.x >> 5] = __float_as_uint(ss);
       __syncthreads();
@@ -1263,7 +1220,8 @@ DR_D void phase_fix(const EngineParams& P, Smem& sm) {
         const float u = (float)((double)policy_hash(p, 0x51EDu + P.epoch) / 4294967296.0);
         float l = prev + ((u < (lf - prev)) ? 1.f : 0.f);
         l = v > 0.f ? l : (v < 0.f ? -l : 0.f);
-        reinterpret_cast<int8_t*>(my_slot + sm.td.off_rankmap)[p] = (int8_t)l;
+        if (sm.td.rank_u32) reinterpret_cast<int16_t*>(my_slot + sm.td.off_rankmap)[p] = (int16_t)l;   // quantum_num >= 128
+        else reinterpret_cast<int8_t*>(my_slot + sm.td.off_rankmap)[p] = (int8_t)l;
         P.resid[__ldcg(my_slot + sm.td.off_selidx + p)] = v - norm / q * l;
       }
       continue;
@@ -1282,45 +1240,6 @@ DR_D void phase_fix(const EngineParams& P, Smem& sm) {
       P.resid[__ldcg(my_slot + sm.td.off_selidx + p)] = v - fitted;
     }
   }
-}
-
-// ===========================================================================
-// phase 9/10: push + flags
-// ===========================================================================
-DR_D void phase_push(const EngineParams& P) {
-  const uint32_t parity = P.epoch & 1u;
-  const uint4* src = reinterpret_cast<const uint4*>(slot_ptr(P.arena[P.rank], P, parity, P.rank));
-  const uint32_t n4 = (P.payload_words + 3u) >> 2;
-  if (P.mc_arena) {                                      // NVLS: one multimem store lands in every GPU's arena (the switch replicates)
-    uint4* dst = reinterpret_cast<uint4*>(slot_ptr(P.mc_arena, P, parity, P.rank));
-    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n4; i += gridDim.x * kThreads) multimem_st_v4(dst + i, __ldcg(src + i));
-    __threadfence_system();
-    return;
-  }
-  for (int h = 1; h < P.world; ++h) {
-    const int peer = (P.rank + h) % P.world;             // stagger so peers are not hit in lock-step
-    uint4* dst = reinterpret_cast<uint4*>(slot_ptr(P.arena[peer], P, parity, P.rank));
-    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n4; i += gridDim.x * kThreads) {
-      const uint4 v = __ldcg(src + i);
-      asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
-                   :: "l"(dst + i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-    }
-  }
-  __threadfence_system();
-}
-
-DR_D void phase_signal(const EngineParams& P) {
-  const int p = threadIdx.x;
-  if (blockIdx.x == 0 && p < P.world && p != P.rank) st_release_sys(P.arena[p] + P.rank, P.epoch);
-  if (p < P.world && p != P.rank) {
-    const uint32_t* flag = P.arena[P.rank] + p;
-    uint32_t spins = 0;
-    while ((int32_t)(ld_acquire_sys(flag) - P.epoch) < 0) {
-      if (++spins > P.spin_limit) { atomicExch(P.status, kErrPeerWait); atomicExch(P.status + 1, (uint32_t)p); break; }
-      __nanosleep(100);
-    }
-  }
-  __syncthreads();
 }
 
 // phase 14: evaluate every rank's fitted curve once (dense, all lanes busy); decode then gathers fitted[rank]
@@ -1346,10 +1265,95 @@ DR_D void phase_expand(const EngineParams& P, Smem& sm) {
   }
 }
 
+
 // ===========================================================================
-// phase 15: decode.  Contiguous tile range per CTA; rank-major so one staged
-// filter serves all of the CTA's tiles of that tensor; sparse RMW into the
-// zero-filled dense output.
+// push + flags.  Every CTA copies its share of the finished slot into each peer's arena (16-byte P2P stores over
+// NVLink, or ONE multimem store that the NVSwitch replicates), fences at system scope and takes a ticket; the CTA
+// that takes the last ticket releases the epoch flags — the copy needs no grid barrier before the signal.
+// ===========================================================================
+DR_D void phase_push(const EngineParams& P, Smem& sm) {
+  const uint32_t parity = P.epoch & 1u;
+  const uint4* src = reinterpret_cast<const uint4*>(slot_ptr(P.arena[P.rank], P, parity, P.rank));
+  const uint32_t n4 = (P.payload_words + 3u) >> 2;
+  if (P.mc_arena) {                                      // NVLS: one multimem store lands in every GPU's arena (the switch replicates)
+    uint4* dst = reinterpret_cast<uint4*>(slot_ptr(P.mc_arena, P, parity, P.rank));
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n4; i += gridDim.x * kThreads) multimem_st_v4(dst + i, __ldcg(src + i));
+  } else {
+    for (int h = 1; h < P.world; ++h) {
+      const int peer = (P.rank + h) % P.world;             // stagger so peers are not hit in lock-step
+      uint4* dst = reinterpret_cast<uint4*>(slot_ptr(P.arena[peer], P, parity, P.rank));
+      for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n4; i += gridDim.x * kThreads) {
+        const uint4 v = __ldcg(src + i);
+        asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+                     :: "l"(dst + i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+      }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t t = atomicAdd(P.barrier + 1, 1u);
+    sm.s.lb = (t == gridDim.x - 1u) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (sm.s.lb && P.fault != 1) {                         // last CTA: every share of the slot is in the peers' memory
+    __threadfence_system();
+    const int p = threadIdx.x;
+    if (p < P.world && p != P.rank) st_release_sys(P.arena[p] + P.rank, P.epoch);
+  }
+  __syncthreads();
+}
+
+// Wait for every peer's epoch flag (flag word `base + peer` of my arena).  A peer that never shows up is fatal: the
+// wait is bounded by WALL TIME (peer_timeout_ms — a rank can legitimately be seconds late: checkpoint, dataloader
+// stall, first-step autotune), and on expiry the status word is set, the output is poisoned with NaN and the CTA
+// leaves the kernel without decoding slots the peer may still be writing.  Returns false (CTA-uniform) on timeout.
+DR_D bool wait_flags(const EngineParams& P, uint32_t base, uint32_t aux_base) {
+  const int p = threadIdx.x;
+  int bad = 0;
+  if (p < P.world && p != P.rank) {
+    const uint32_t* flag = P.arena[P.rank] + base + p;
+    uint32_t spins = 0;
+    uint64_t t_start = 0;
+    while ((int32_t)(ld_acquire_sys(flag) - P.epoch) < 0) {
+      if ((++spins & 1023u) == 0u) {
+        const uint64_t now = globaltimer_ns();
+        if (t_start == 0) t_start = now;
+        else if (now - t_start > (uint64_t)P.peer_timeout_ms * 1000000ull) { bad = 1; break; }
+      }
+      __nanosleep(64);
+    }
+    if (bad) { atomicExch(P.status, kErrPeerWait); atomicExch(P.status + 1, aux_base + (uint32_t)p); }
+  }
+  const int any_bad = __syncthreads_or(bad);
+  if (any_bad && threadIdx.x == 0) {                     // poison: the aggregate of this step does not exist
+    uint32_t tile, t_end;
+    decode_range(P, tile, t_end);
+    if (tile < t_end) P.grad[load_tile(P, tile).base] = __uint_as_float(0x7FC00000u);
+  }
+  return !any_bad;
+}
+
+
+// value of the p-th shipped coordinate of a sender's tensor under its value codec
+template <bool kFull>
+DR_D float coded_value(const uint32_t* slot, const TensorDesc& td, const float* vals, const float* fitted, uint32_t rp) {
+  if (kFull && td.vmode == 1u) return __ldcg(fitted + load_rank(slot, td, rp));
+  if (kFull && td.vmode == 2u) {
+    const float norm = __ldcg(reinterpret_cast<const float*>(slot + td.off_coef) + (rp >> 9));
+    const float lvl = td.rank_u32 ? (float)__ldcg(reinterpret_cast<const int16_t*>(slot + td.off_rankmap) + rp)
+                                  : (float)__ldcg(reinterpret_cast<const int8_t*>(slot + td.off_rankmap) + rp);
+    return norm / (float)td.poly_degree * lvl;
+  }
+  return __ldcg(vals + rp);
+}
+
+// ===========================================================================
+// phase 15: decode.  Contiguous tile range per CTA (of this rank's slice when sharded); rank-major.
+// bloom: per sender, (1) membership test of its hinted groups against its filter staged in SMEM -> dec_mask
+// (probe_segment; my own positives are already in pos_mask), (2) one warp per tile turns masks into ranks
+// (prefix table + popcounts), fetches the values and accumulates into the zero-filled dense output.  The same warp
+// and lane own an element for every sender, so the sum order is rank-major and deterministic.
 // ===========================================================================
 DR_D uint32_t lower_bound_u32(const uint32_t* a, uint32_t n, uint32_t x) {
   uint32_t lo = 0, hi = n;
@@ -1359,137 +1363,117 @@ DR_D uint32_t lower_bound_u32(const uint32_t* a, uint32_t n, uint32_t x) {
 
 template <bool kFull>
 DR_D void phase_decode(const EngineParams& P, Smem& sm) {
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t parity = P.epoch & 1u;
   uint32_t* arena = P.arena[P.rank];
-  {  // hist arrays are free after the insert phase: zero them for the next step
-    uint4* h = reinterpret_cast<uint4*>(P.hist);
-    const size_t n4 = (size_t)kNumHist * P.n_tensors * kHistBins / 4;
-    const uint4 z = make_uint4(0, 0, 0, 0);
-    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n4; i += (size_t)gridDim.x * kThreads) h[i] = z;
-    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < (uint32_t)kNumHist * P.n_tensors; i += gridDim.x * kThreads)
-      P.hist_total[i] = 0u;
-    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < P.n_tiles; i += gridDim.x * kThreads) P.tile_count[i] = 0u;
-    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < P.n_poly * 2u * kRankBins; i += gridDim.x * kThreads)
+  if (kFull) {
+    for (uint32_t i = blockIdx.x * kThreads + tid; i < P.n_poly * 2u * kRankBins; i += gridDim.x * kThreads)
       P.poly_bins[i] = 0u;
   }
-  uint32_t tile, t_end, rank_buf = 0;
-  {
-    uint32_t s_begin, s_end;
-    decode_span(P, P.rank, s_begin, s_end);
-    const uint32_t span = s_end - s_begin;
-    tile = s_begin + (uint32_t)(((uint64_t)span * blockIdx.x) / gridDim.x);
-    t_end = s_begin + (uint32_t)(((uint64_t)span * (blockIdx.x + 1)) / gridDim.x);
-  }
+  uint32_t tile, t_end;
+  decode_range(P, tile, t_end);
   while (tile < t_end) {
     const Tile t0 = load_tile(P, tile);
     const uint32_t t = t0.tensor;
     load_tensor(P, t, sm);
     const uint32_t seg_end = min(t_end, sm.td.tile_begin + sm.td.n_tiles);
-    if (sm.td.mode == kModeBloom) {
-      // 1) zero-fill my tiles of this tensor (contiguous in the flat buffer)
-      {
-        const Tile tl = load_tile(P, seg_end - 1);
-        const uint32_t n_elems = (tl.base + tl.n) - t0.base;
-        float4* dst = reinterpret_cast<float4*>(P.grad + t0.base);
-        const uint32_t n4 = n_elems >> 2;
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (uint32_t i = threadIdx.x; i < n4; i += kThreads) dst[i] = z;
-        for (uint32_t i = (n4 << 2) + threadIdx.x; i < n_elems; i += kThreads) P.grad[t0.base + i] = 0.f;
-      }
-      __syncthreads();
+    if (P.world == 1 && sm.td.vmode == 0u) { tile = seg_end; continue; }   // emit already scattered my own values
+    if (sm.td.mode == (uint32_t)kModeBloom) {
       const uint32_t n_hash = sm.td.n_hash, m_bits = sm.td.m_bits;
       const bool fits = sm.td.n_filter_words <= P.filter_smem_words;
       for (int r = 0; r < P.world; ++r) {
         const uint32_t* slot = slot_ptr(arena, P, parity, r);
         const DynHeader* dyn = reinterpret_cast<const DynHeader*>(slot + kSlotHeaderWords) + t;
         const uint32_t n_sel = __ldcg(&dyn->n_sel), cutoff = __ldcg(&dyn->cutoff);
-        if (n_sel == 0) continue;
+        if (n_sel == 0) continue;                                          // CTA-uniform
         const uint32_t* filter = slot + sm.td.off_filter;
+        const uint32_t* hint = sm.td.off_hint ? slot + sm.td.off_hint : nullptr;
+        const uint32_t* prefix = slot + sm.td.off_prefix;
         const float* vals = reinterpret_cast<const float*>(slot + sm.td.off_vals);
         const float* fitted = P.expand_buf + (size_t)r * P.poly_total + sm.td.poly_off;   // 'both': rank r's curve
-        const bool own = P.own_flags && r == P.rank;               // my own positives are already in flag_buf (query phase)
-        if (fits && !own) stage_filter(filter, sm.td.n_filter_words);
-        for (uint32_t tl = tile; tl < seg_end; ++tl) {
+        const bool own = (r == P.rank);
+        const uint32_t* masks = own ? P.pos_mask : P.dec_mask;
+        if (!own) {
+          if (fits) stage_filter(filter, sm.td.n_filter_words);
+          __syncthreads();
+          if (tid == 0) sm.s.lb = 0;
+          __syncthreads();
+          ProbeCtx c;
+          c.hint = hint; c.prefix = prefix; c.n_sel = n_sel; c.cutoff = cutoff;
+          c.mask_out = P.dec_mask; c.tile_count = nullptr;
+          c.tile_begin = sm.td.tile_begin; c.seg_a = tile; c.seg_b = seg_end;
+          c.n_hash = n_hash; c.m_bits = m_bits; c.seed = P.seed;
+          if (fits) probe_segment(P, sm, c, [&](uint32_t w) { return g_filter_smem[w]; });
+          else probe_segment(P, sm, c, [&](uint32_t w) { return __ldcg(filter + w); });
+          __syncthreads();                                                 // all masks of this sender are final
+        }
+        for (uint32_t tl = tile + warp; tl < seg_end; tl += kWarps) {
           const Tile ti = load_tile(P, tl);
-          const uint32_t pre = __ldcg(slot + sm.td.off_prefix + (tl - sm.td.tile_begin));
-          if (!(pre < n_sel && ti.local0 <= cutoff)) continue;       // tile-uniform: nothing of rank r lands here
-          uint32_t valid = 0;
+          const uint32_t tile_local = tl - sm.td.tile_begin;
+          const uint32_t pre = __ldcg(prefix + tile_local);
+          if (!(pre < n_sel && ti.local0 <= cutoff)) continue;             // warp-uniform: nothing of rank r lands here
+          uint32_t mm[4];
+          load_masks(masks, tl, hint_nibble(hint, tile_local, lane), ti.n, lane, mm);
+          const uint32_t c = (uint32_t)(__popc(mm[0]) + __popc(mm[1]) + __popc(mm[2]) + __popc(mm[3]));
+          if (__ballot_sync(kFullMask, c != 0u) == 0u) continue;
+          const uint32_t incl = warp_incl_scan(c, lane);
+          uint32_t rp = pre + incl - c;
 #pragma unroll
-          for (int c = 0; c < kPerThread; ++c) {
-            const uint32_t e = c * kThreads + threadIdx.x;
-            if (e < ti.n && ti.local0 + e <= cutoff) valid |= 1u << c;
-          }
-          if (sm.td.off_hint) {
-            const uint4 hq = __ldcg(reinterpret_cast<const uint4*>(slot + sm.td.off_hint + 4u * (tl - sm.td.tile_begin)));
-            if ((hq.x | hq.y | hq.z | hq.w) == 0u) continue;           // tile-uniform: rank r selected nothing here
-            const uint32_t h[4] = {hq.x, hq.y, hq.z, hq.w};
-            valid &= valid_from_hint(h);
-          }
-          uint32_t flags;
-          if (own) flags = (uint32_t)P.flag_buf[(size_t)tl * kThreads + threadIdx.x] & valid;
-          else if (fits) flags = bloom_test8(ti.local0 + threadIdx.x, valid, P.seed, n_hash, m_bits,
-                                             [&](uint32_t w) { return g_filter_smem[w]; });
-          else flags = bloom_test8(ti.local0 + threadIdx.x, valid, P.seed, n_hash, m_bits,
-                                   [&](uint32_t w) { return filter[w]; });
-          uint32_t rank[kPerThread], total;
-          tile_rank(flags, sm.s, rank_buf, rank, total);
-#pragma unroll
-          for (int c = 0; c < kPerThread; ++c) {
-            if ((flags >> c) & 1u) {
-              const uint32_t rp = pre + rank[c];
+          for (int j = 0; j < 4; ++j) {
+            uint32_t w = mm[j];
+            while (w) {
+              const uint32_t b = (uint32_t)__ffs((int)w) - 1u;
+              w &= w - 1u;
               if (rp < n_sel) {
-                float* o = P.grad + ti.base + c * kThreads + threadIdx.x;   // the same thread owns this element for every rank
-                float val;
-                if (kFull && sm.td.vmode == 1) val = __ldcg(fitted + load_rank(slot, sm.td, rp));
-                else if (kFull && sm.td.vmode == 2)
-                  val = __ldcg(reinterpret_cast<const float*>(slot + sm.td.off_coef) + (rp >> 9)) / (float)sm.td.poly_degree *
-                        (float)__ldcg(reinterpret_cast<const int8_t*>(slot + sm.td.off_rankmap) + rp);
-                else val = __ldcg(vals + rp);
-                *o = *o + val * P.scale;
+                const uint32_t e = (4u * lane + (uint32_t)j) * 32u + b;
+                float* o = P.grad + ti.base + e;
+                *o = *o + coded_value<kFull>(slot, sm.td, vals, fitted, rp) * P.scale;
               }
+              ++rp;
             }
           }
         }
+        __syncthreads();                                                   // dec_mask / the filter buffer are reused by the next sender
       }
       tile = seg_end;
-    } else if (kFull && sm.td.mode == kModeRle) {
+    } else if (kFull && sm.td.mode == (uint32_t)kModeRle) {
       // running entry prefix of every sender at my first tile of this tensor = sum of the earlier tiles' counts
       __syncthreads();
-      if (threadIdx.x < 16) sm.s.rle_pre[threadIdx.x] = 0u;
+      if (tid < 16) sm.s.rle_pre[tid] = 0u;
       __syncthreads();
       const uint32_t first_local = tile - sm.td.tile_begin;
       for (int r = 0; r < P.world; ++r) {
         const uint16_t* cnt = reinterpret_cast<const uint16_t*>(slot_ptr(arena, P, parity, r) + sm.td.off_prefix);
         uint32_t part = 0;
-        for (uint32_t j = threadIdx.x; j < first_local; j += kThreads) part += __ldcg(cnt + j);
+        for (uint32_t j = tid; j < first_local; j += kThreads) part += __ldcg(cnt + j);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
-        if ((threadIdx.x & 31u) == 0 && part) atomicAdd(&sm.s.rle_pre[r], part);
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(kFullMask, part, o);
+        if (lane == 0 && part) atomicAdd(&sm.s.rle_pre[r], part);
       }
       for (; tile < seg_end; ++tile) {
         const Tile ti = load_tile(P, tile);
         __syncthreads();
-        for (int j = threadIdx.x; j < kTile; j += kThreads) sm.u.acc[j] = 0.0f;
+        for (int j = tid; j < kTile; j += kThreads) sm.u.acc[j] = 0.0f;
         __syncthreads();
         for (int r = 0; r < P.world; ++r) {
           const uint32_t* slot = slot_ptr(arena, P, parity, r);
           const uint32_t c = __ldcg(reinterpret_cast<const uint16_t*>(slot + sm.td.off_prefix) + (tile - sm.td.tile_begin));
           const uint32_t pre = sm.s.rle_pre[r];
           const float* vals = reinterpret_cast<const float*>(slot + sm.td.off_vals);
-          for (uint32_t j = threadIdx.x; j < c; j += kThreads) {
+          for (uint32_t j = tid; j < c; j += kThreads) {
             const uint32_t rp = pre + j;
             if (rp < sm.td.val_cap) sm.u.acc[rle_get(slot + sm.td.off_idx, rp)] += __ldcg(vals + rp) * P.scale;   // distinct positions per sender
           }
           __syncthreads();                                  // senders are added in rank order: deterministic sums
-          if (threadIdx.x == 0) sm.s.rle_pre[r] = pre + c;
+          if (tid == 0) sm.s.rle_pre[r] = pre + c;
         }
-        for (uint32_t e = threadIdx.x; e < ti.n; e += kThreads) P.grad[ti.base + e] = sm.u.acc[e];
+        for (uint32_t e = tid; e < ti.n; e += kThreads) P.grad[ti.base + e] = sm.u.acc[e];
       }
     } else {
       for (; tile < seg_end; ++tile) {
         const Tile ti = load_tile(P, tile);
         __syncthreads();
-        for (int j = threadIdx.x; j < kTile; j += kThreads) sm.u.acc[j] = 0.0f;
+        for (int j = tid; j < kTile; j += kThreads) sm.u.acc[j] = 0.0f;
         __syncthreads();
         for (int r = 0; r < P.world; ++r) {
           const uint32_t* slot = slot_ptr(arena, P, parity, r);
@@ -1497,113 +1481,108 @@ DR_D void phase_decode(const EngineParams& P, Smem& sm) {
           const uint32_t n_sel = min(__ldcg(&dyn->n_sel), sm.td.val_cap);
           const uint32_t* idxs = slot + sm.td.off_idx;
           const float* vals = reinterpret_cast<const float*>(slot + sm.td.off_vals);
+          const float* fitted = P.expand_buf + (size_t)r * P.poly_total + sm.td.poly_off;
           const uint32_t lo = lower_bound_u32(idxs, n_sel, ti.local0);
           const uint32_t hi = lower_bound_u32(idxs, n_sel, ti.local0 + ti.n);
-          for (uint32_t j = lo + threadIdx.x; j < hi; j += kThreads)
-            atomicAdd(&sm.u.acc[__ldcg(idxs + j) - ti.local0], __ldcg(vals + j) * P.scale);
+          for (uint32_t j = lo + tid; j < hi; j += kThreads)
+            atomicAdd(&sm.u.acc[__ldcg(idxs + j) - ti.local0], coded_value<kFull>(slot, sm.td, vals, fitted, j) * P.scale);
+          __syncthreads();                                  // rank-major: one sender at a time
         }
-        __syncthreads();
-        for (uint32_t e = threadIdx.x; e < ti.n; e += kThreads) P.grad[ti.base + e] = sm.u.acc[e];
+        for (uint32_t e = tid; e < ti.n; e += kThreads) P.grad[ti.base + e] = sm.u.acc[e];
       }
     }
   }
 }
 
 // ===========================================================================
-// sharded decode, stage 2 (W > 1): my decoded slice -> exact (index, value) list -> peers
+// sharded decode, stage 2 (W > 1): my decoded slice -> exact (index, value) list -> straight into every peer's
+// stage-2 slot.  Same tile->CTA split as the decode phase (no grid barrier in between); entries are staged in the
+// dynamic SMEM buffer, a chunk of the list is reserved with one atomic per flush, and the peers' copies are written
+// with coalesced 4-byte P2P stores (or one multimem store).  Last CTA (ticket): entry count + second flag set.
 // ===========================================================================
 DR_D void phase_compact(const EngineParams& P, Smem& sm) {
+  const uint32_t tid = threadIdx.x, lane = tid & 31u;
   const uint32_t parity = P.epoch & 1u;
-  uint32_t my_b, my_e;
-  decode_span(P, P.rank, my_b, my_e);
-  // (a) zero every tile outside my slice (peers' lists are scattered into them later)
-  for (uint32_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-    if (tile >= my_b && tile < my_e) continue;
-    const Tile ti = load_tile(P, tile);
-    float4* dst = reinterpret_cast<float4*>(P.grad + ti.base);
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (uint32_t i = threadIdx.x; i < ((ti.n + 3u) >> 2); i += kThreads) dst[i] = z;   // tensors are padded to 32 floats
-  }
-  // (b) non-zeros of my slice -> my stage-2 slot (unordered: slices are disjoint, receivers only write)
-  uint32_t* s2 = s2_ptr(P.arena[P.rank], P, parity, P.rank);
-  uint32_t* idx_out = s2 + 4;
-  float* val_out = reinterpret_cast<float*>(s2 + 4 + P.s2_cap);
-  const uint32_t lane = threadIdx.x & 31u;
-  for (uint32_t tile = my_b + blockIdx.x; tile < my_e; tile += gridDim.x) {
+  uint32_t* s2 = s2_ptr(P.arena[P.rank], P, parity, P.rank);              // s2[0]: list cursor (zeroed in the accumulate phase)
+  const uint32_t cap = P.filter_smem_words / 2u;
+  uint32_t* st_idx = g_filter_smem;
+  float* st_val = reinterpret_cast<float*>(g_filter_smem + cap);
+  uint32_t tile, t_end;
+  decode_range(P, tile, t_end);
+  __syncthreads();
+  if (tid == 0) sm.s.lb = 0;
+  __syncthreads();
+  auto flush = [&]() {                                                     // CTA-uniform
+    __syncthreads();
+    const uint32_t n = sm.s.lb;
+    if (tid == 0) sm.s.res[0] = n ? atomicAdd(s2, n) : 0u;
+    __syncthreads();
+    const uint32_t gbase = sm.s.res[0];
+    uint32_t n_ok = n;
+    if (gbase + n > P.s2_cap) {
+      if (tid == 0) atomicExch(P.status, kErrS2Overflow);                  // stage-2 capacity exceeded
+      n_ok = gbase < P.s2_cap ? P.s2_cap - gbase : 0u;
+    }
+    if (P.mc_arena) {
+      uint32_t* dst = s2_ptr(P.mc_arena, P, parity, P.rank);
+      for (uint32_t j = tid; j < n_ok; j += kThreads) {
+        multimem_st_b32(dst + 4 + gbase + j, st_idx[j]);
+        multimem_st_b32(dst + 4 + P.s2_cap + gbase + j, __float_as_uint(st_val[j]));
+      }
+    } else {
+      for (int h = 1; h < P.world; ++h) {
+        const int peer = (P.rank + h) % P.world;
+        uint32_t* dst = s2_ptr(P.arena[peer], P, parity, P.rank);
+        for (uint32_t j = tid; j < n_ok; j += kThreads) {
+          dst[4 + gbase + j] = st_idx[j];
+          dst[4 + P.s2_cap + gbase + j] = __float_as_uint(st_val[j]);
+        }
+      }
+    }
+    __syncthreads();
+    if (tid == 0) sm.s.lb = 0;
+    __syncthreads();
+  };
+  for (; tile < t_end; ++tile) {
+    __syncthreads();
+    if (sm.s.lb + (uint32_t)kTile > cap) flush();
     const Tile ti = load_tile(P, tile);
     float v[kPerThread];
     uint32_t nz = 0;
 #pragma unroll
     for (int c = 0; c < kPerThread; ++c) {
-      const uint32_t e = c * kThreads + threadIdx.x;
+      const uint32_t e = c * kThreads + tid;
       v[c] = e < ti.n ? __ldcg(P.grad + ti.base + e) : 0.f;
       if (v[c] != 0.f) nz |= 1u << c;
     }
     const uint32_t cnt = __popc(nz);
-    uint32_t incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t nb = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += nb; }
+    const uint32_t incl = warp_incl_scan(cnt, lane);
     uint32_t wbase = 0;
-    if (lane == 31 && incl) wbase = atomicAdd(s2, incl);          // s2[0] = entry count (zeroed in the accumulate phase)
-    wbase = __shfl_sync(0xFFFFFFFFu, wbase, 31);
+    if (lane == 31 && incl) wbase = atomicAdd(&sm.s.lb, incl);
+    wbase = __shfl_sync(kFullMask, wbase, 31);
     uint32_t pos = wbase + incl - cnt;
 #pragma unroll
     for (int c = 0; c < kPerThread; ++c) {
-      if ((nz >> c) & 1u) {
-        if (pos < P.s2_cap) { idx_out[pos] = ti.base + c * kThreads + threadIdx.x; val_out[pos] = v[c]; }
-        else atomicExch(P.status, 6u);                            // stage-2 capacity exceeded
-        ++pos;
-      }
+      if ((nz >> c) & 1u) { st_idx[pos] = ti.base + c * kThreads + tid; st_val[pos] = v[c]; ++pos; }
     }
   }
-}
-
-DR_D void phase_push2(const EngineParams& P) {
-  const uint32_t parity = P.epoch & 1u;
-  const uint32_t* src = s2_ptr(P.arena[P.rank], P, parity, P.rank);
-  const uint32_t n = min(__ldcg(src), P.s2_cap);
-  if (P.mc_arena) {
-    uint32_t* dst = s2_ptr(P.mc_arena, P, parity, P.rank);
-    const uint32_t gtid = blockIdx.x * kThreads + threadIdx.x, gsz = gridDim.x * kThreads;
-    if (gtid == 0) multimem_st_v4(reinterpret_cast<uint4*>(dst), make_uint4(n, P.epoch, 0u, 0u));
-    const uint4* si = reinterpret_cast<const uint4*>(src + 4);
-    const uint4* sv = reinterpret_cast<const uint4*>(src + 4 + P.s2_cap);
-    uint4* di = reinterpret_cast<uint4*>(dst + 4);
-    uint4* dv = reinterpret_cast<uint4*>(dst + 4 + P.s2_cap);
-    const uint32_t n4 = (n + 3u) >> 2;
-    for (uint32_t i = gtid; i < n4; i += gsz) { multimem_st_v4(di + i, __ldcg(si + i)); multimem_st_v4(dv + i, __ldcg(sv + i)); }
-    __threadfence_system();
-    return;
-  }
-  for (int h = 1; h < P.world; ++h) {
-    const int peer = (P.rank + h) % P.world;
-    uint32_t* dst = s2_ptr(P.arena[peer], P, parity, P.rank);
-    const uint32_t gtid = blockIdx.x * kThreads + threadIdx.x, gsz = gridDim.x * kThreads;
-    if (gtid < 4) dst[gtid] = gtid == 0 ? n : (gtid == 1 ? P.epoch : 0u);
-    // idx block and val block, 16 bytes at a time
-    const uint4* si = reinterpret_cast<const uint4*>(src + 4);
-    const uint4* sv = reinterpret_cast<const uint4*>(src + 4 + P.s2_cap);
-    uint4* di = reinterpret_cast<uint4*>(dst + 4);
-    uint4* dv = reinterpret_cast<uint4*>(dst + 4 + P.s2_cap);
-    const uint32_t n4 = (n + 3u) >> 2;
-    for (uint32_t i = gtid; i < n4; i += gsz) {
-      const uint4 a = __ldcg(si + i), b = __ldcg(sv + i);
-      asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(di + i), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w) : "memory");
-      asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dv + i), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
-    }
-  }
+  flush();
   __threadfence_system();
-}
-
-DR_D void phase_signal2(const EngineParams& P) {
-  const int p = threadIdx.x;
-  if (blockIdx.x == 0 && p < P.world && p != P.rank) st_release_sys(P.arena[p] + kArenaFlagWords + P.rank, P.epoch);
-  if (p < P.world && p != P.rank) {
-    const uint32_t* flag = P.arena[P.rank] + kArenaFlagWords + p;
-    uint32_t spins = 0;
-    while ((int32_t)(ld_acquire_sys(flag) - P.epoch) < 0) {
-      if (++spins > P.spin_limit) { atomicExch(P.status, kErrPeerWait); atomicExch(P.status + 1, 100u + (uint32_t)p); break; }
-      __nanosleep(100);
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t t = atomicAdd(P.barrier + 2, 1u);
+    sm.s.res[1] = (t == gridDim.x - 1u) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (sm.s.res[1]) {                                                       // last CTA: every chunk is in the peers' memory
+    __threadfence_system();
+    const int p = tid;
+    if (p < P.world && p != P.rank) {
+      const uint32_t n = min(__ldcg(s2), P.s2_cap);
+      uint32_t* dst = s2_ptr(P.arena[p], P, parity, P.rank);
+      dst[0] = n; dst[1] = P.epoch;
+      __threadfence_system();
+      st_release_sys(P.arena[p] + kArenaFlagWords + P.rank, P.epoch);
     }
   }
   __syncthreads();
@@ -1622,45 +1601,72 @@ DR_D void phase_scatter(const EngineParams& P) {
   }
 }
 
+// Which phases do anything for this configuration (CTA-uniform, decided before the phase runs so that the grid
+// barrier in front of a phase is only paid when it does).
+template <bool kFull>
+DR_D bool phase_active(const EngineParams& P, int ph) {
+  switch (ph) {
+    case kPhAccum: case kPhHist2: case kPhInsert: case kPhQuery: case kPhEmit: return true;
+    case kPhFallback: return __ldcg(P.barrier + kUnsafeWord) != 0u;
+    case kPhRankHist: case kPhRankScan: case kPhRankScatter: case kPhRankExact: case kPhFit: case kPhExpand:
+      return kFull && P.n_poly != 0u;
+    case kPhFix: return kFull && P.n_poly_tasks != 0u;
+    case kPhPush: case kPhSignal: return P.world > 1;
+    case kPhDecode: return P.world > 1 || (kFull && P.n_poly_tasks != 0u);
+    case kPhCompact: case kPhSignal2: case kPhScatter: return sharded(P);
+    default: return false;
+  }
+}
+
 template <int kMinBlocks, bool kFull>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) dr_engine_kernel(const __grid_constant__ EngineParams P) {
   __shared__ Smem sm;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 8; ++i) mbar_init(&sm.bar[i], 1);
+    for (int i = 0; i < 16; ++i) mbar_init(&sm.bar[i], 1);
     mbar_fence_init();
   }
   __syncthreads();
   uint32_t bar_epoch = 0;
+  bool pending = false;        // a phase ran since the last grid barrier of this launch
+  bool prev_wait = false;      // the previous active phase was a peer-flag wait
   for (int ph = P.phase_begin; ph < P.phase_end; ++ph) {
-    bool ran = true;
+    // the fallback decision reads a word written in the accumulate phase: it is taken after the barrier that the
+    // digit-2 phase needs anyway
+    if (ph == kPhFallback && pending) { grid_barrier(P.barrier, bar_epoch, P.status, P.spin_limit); pending = false; }
+    if (!phase_active<kFull>(P, ph)) continue;
+    const bool is_wait = (ph == kPhSignal || ph == kPhSignal2);
+    // no barrier: in front of a flag wait; after one (every CTA waited itself); compact reads only the tiles this CTA decoded
+    if (pending && !is_wait && !prev_wait && ph != kPhCompact) {
+      grid_barrier(P.barrier, bar_epoch, P.status, P.spin_limit);
+      pending = false;
+    }
     switch (ph) {
-      case kPhAccum: if (P.use_tma) phase_accum_tma(P, sm); else phase_accum(P, sm); break;
-      case kPhFallback: if (P.use_history) hist_tiles<1>(P, sm); else ran = false; break;
+      case kPhAccum: phase_accum(P, sm); break;
+      case kPhFallback: phase_fallback(P, sm); break;
       case kPhHist2:
         if (kFull && P.has_rle) rle_zero_streams(P);
-        if (P.use_tma) phase_hist2_tma(P, sm); else hist_tiles<2>(P, sm);
+        phase_hist2(P, sm);
         break;
-      case kPhInsert: if (P.use_tma) phase_insert_tma(P, sm); else phase_insert(P, sm); break;
+      case kPhInsert: phase_insert(P, sm); break;
       case kPhQuery: phase_query(P, sm); break;
       case kPhEmit: phase_emit<kFull>(P, sm); break;
-      case kPhRankHist: if constexpr (kFull) { if (P.n_poly) phase_rank_hist(P, sm); else ran = false; } else ran = false; break;
-      case kPhRankScan: if constexpr (kFull) { if (P.n_poly) phase_rank_scan(P, sm); else ran = false; } else ran = false; break;
-      case kPhRankScatter: if constexpr (kFull) { if (P.n_poly) phase_rank_scatter(P, sm); else ran = false; } else ran = false; break;
-      case kPhRankExact: if constexpr (kFull) { if (P.n_poly) phase_rank_exact(P, sm); else ran = false; } else ran = false; break;
-      case kPhFit: if constexpr (kFull) { if (P.n_poly) phase_fit(P, sm); else ran = false; } else ran = false; break;
-      case kPhFix: if constexpr (kFull) { if (P.n_poly_tasks) phase_fix(P, sm); else ran = false; } else ran = false; break;
-      case kPhExpand: if constexpr (kFull) { if (P.n_poly) phase_expand(P, sm); else ran = false; } else ran = false; break;
-      case kPhPush: if (P.world > 1) phase_push(P); else ran = false; break;
-      case kPhSignal: if (P.world > 1) phase_signal(P); else ran = false; break;
+      case kPhRankHist: if constexpr (kFull) phase_rank_hist(P, sm); break;
+      case kPhRankScan: if constexpr (kFull) phase_rank_scan(P, sm); break;
+      case kPhRankScatter: if constexpr (kFull) phase_rank_scatter(P, sm); break;
+      case kPhRankExact: if constexpr (kFull) phase_rank_exact(P, sm); break;
+      case kPhFit: if constexpr (kFull) phase_fit(P, sm); break;
+      case kPhFix: if constexpr (kFull) phase_fix(P, sm); break;
+      case kPhExpand: if constexpr (kFull) phase_expand(P, sm); break;
+      case kPhPush: phase_push(P, sm); break;
+      case kPhSignal: if (!wait_flags(P, 0u, 0u)) return; break;
       case kPhDecode: phase_decode<kFull>(P, sm); break;
-      case kPhCompact: if (sharded(P)) phase_compact(P, sm); else ran = false; break;
-      case kPhPush2: if (sharded(P)) phase_push2(P); else ran = false; break;
-      case kPhSignal2: if (sharded(P)) phase_signal2(P); else ran = false; break;
-      case kPhScatter: if (sharded(P)) phase_scatter(P); else ran = false; break;
-      default: ran = false; break;
+      case kPhCompact: phase_compact(P, sm); break;
+      case kPhSignal2: if (!wait_flags(P, kArenaFlagWords, 100u)) return; break;
+      case kPhScatter: phase_scatter(P); break;
+      default: break;
     }
-    // a barrier separates dependent phases; signal->decode needs none (every CTA waits itself)
-    if (ran && ph + 1 < P.phase_end && !(ph == kPhSignal) && !(ph == kPhSignal2)) grid_barrier(P.barrier, bar_epoch, P.status, P.spin_limit);
+    prev_wait = is_wait;
+    pending = true;
   }
 }
 
@@ -1705,7 +1711,8 @@ int engine_max_grid(int blocks_per_sm, int dyn_smem_bytes) {
 
 cudaError_t engine_launch(const EngineParams& P, int grid, int blocks_per_sm, int dyn_smem_bytes, cudaStream_t stream) {
   ensure_attr();
-  cudaError_t e = cudaMemsetAsync(P.barrier, 0, sizeof(uint32_t), stream);
+  if (dyn_smem_bytes < 2 * (int)kStageBytes) return cudaErrorInvalidValue;     // the TMA ring needs two stages
+  cudaError_t e = cudaMemsetAsync(P.barrier, 0, 4 * sizeof(uint32_t), stream);  // grid barrier + the two tickets
   if (e != cudaSuccess) return e;
   void* args[] = {const_cast<EngineParams*>(&P)};
   count_launch(1);

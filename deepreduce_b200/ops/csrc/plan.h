@@ -47,7 +47,8 @@ struct TensorDesc {
   uint32_t n_filter_words;
   uint32_t off_hint;     // 0 = none; else 4 words per tile: bit g set <=> 32-element group g holds a selected element
   // ---- value codec ('both': bloom index + polynomial fit of the values) ----
-  uint32_t vmode;        // 0 = fp32 values on the wire, 1 = piece-wise Gram-polynomial fit + rank map
+  uint32_t vmode;        // 0 = fp32 values on the wire, 1 = piece-wise Gram-polynomial fit + rank map,
+                         // 2 = bucketed QSGD (int8 levels, or int16 when rank_u32 is set: quantum_num >= 128)
   uint32_t off_coef;     // [kMaxSeg * (deg+1)] float coefficients, then {num_pos, n}
   uint32_t off_rankmap;  // rank of the p-th shipped value in the descending sort (u16 if val_cap <= 65536 else u32)
   uint32_t off_selidx;   // scratch (not shipped): element index of the p-th shipped value
@@ -56,7 +57,8 @@ struct TensorDesc {
   uint32_t rank_u32;     // 1: rank map entries are 32-bit
   uint32_t poly_off;     // offset of this tensor's values in the engine's per-value scratch arrays
   uint32_t poly_ord;     // ordinal among the vmode==1 tensors (selects its bin table)
-  uint32_t reserved[7];
+  uint32_t fixed_thr;    // != 0: 'threshold' sparsifier — select key >= fixed_thr (31-bit |x| pattern), no radix select, variable K
+  uint32_t reserved[6];
 };
 static_assert(sizeof(TensorDesc) == 128, "TensorDesc must be 32 words");
 constexpr int kDescWords = 32;
@@ -103,12 +105,12 @@ constexpr uint32_t kArenaHdrWords = 128;
 // i.e. the threshold is resolved to 22 bits (8 exponent + 14 mantissa): at least K elements are
 // selected, plus the few that share the threshold's 22-bit prefix; exact zeros are never selected.
 enum Phase : int {
-  kPhAccum = 0,      // r = beta*r + gamma*g ; zero slot ; hist digit 1 (history lower bound)
-  kPhFallback = 1,   // digit 1 redone without the bound for tensors whose bound was unsafe
-  kPhHist2 = 2,      // digit 2 of the keys in the threshold bin
-  kPhInsert = 3,     // resolve T22, bloom insert of the selected set
-  kPhQuery = 4,      // universe query against my filter: per-element flags + per-tile counts
-  kPhEmit = 5,       // ordered compaction (local prefix of the counts) + value gather + residual zeroing
+  kPhAccum = 0,      // r = beta*r + gamma*g ; dense grad <- 0 ; zero slot ; candidate lists (keys >= history bound) ; hist digit 1
+  kPhFallback = 1,   // (only if some bound was unsafe) digit 1 redone without the bound, candidate lists rebuilt in full
+  kPhHist2 = 2,      // digit 2 of the candidate keys in the threshold bin
+  kPhInsert = 3,     // selected candidates -> bloom filter + occupancy hint (bloom) / positive masks (raw, rle)
+  kPhQuery = 4,      // hinted 32-element groups of the universe vs my filter -> positive masks + per-tile counts
+  kPhEmit = 5,       // ordered compaction from the masks + value gather + residual zeroing (+ dense scatter when W == 1)
   // 'both' (bloom index + polynomial value fit): exact descending rank of every shipped value by a
   // counting sort on 13 key bits + an all-pairs count inside each bin, then the fit
   kPhRankHist = 6,   // bin populations
@@ -117,16 +119,18 @@ enum Phase : int {
   kPhRankExact = 9,  // exact rank inside the bin -> rank map + sorted values + num_pos
   kPhFit = 10,       // per-segment Gram-polynomial least squares on the sorted values
   kPhFix = 11,       // residual <- value - fitted value (error feedback sees the fit error)
-  kPhPush = 12,      // copy the finished slot into every peer's arena (P2P stores over NVLink)
-  kPhSignal = 13,    // release flags to peers, acquire peers' flags
+  kPhPush = 12,      // copy the finished slot into every peer's arena (P2P stores over NVLink); the CTA that finishes last
+                     // (ticket) releases the flags — no grid barrier between the copy and the signal
+  kPhSignal = 13,    // acquire peers' flags
   kPhExpand = 14,    // 'both': evaluate every rank's fitted curve once (dense), decode then only gathers
   kPhDecode = 15,    // membership test on every rank's filter, rank->value, sum, scale, dense write
                      // (sharded mode, W>1: only this rank's 1/W slice of the tiles, for all W senders)
   // sharded decode (W > 1): the decoded slice is exchanged as an exact (index, value) list — decode work per rank
   // no longer grows with W; NVLink carries the extra ~2 MB/rank
-  kPhCompact = 16,   // zero the tiles outside my slice; compact the non-zeros of my decoded slice into my stage-2 slot
-  kPhPush2 = 17,     // P2P stores of the stage-2 slot into every peer's arena
-  kPhSignal2 = 18,   // second flag set (release/acquire)
+  kPhCompact = 16,   // compact the non-zeros of my decoded slice (same CTA that decoded the tile) and store them straight
+                     // into every peer's stage-2 slot; last CTA (ticket) writes the count and releases the second flag set
+  kPhPush2 = 17,     // (folded into kPhCompact; kept so phase numbers stay stable)
+  kPhSignal2 = 18,   // acquire peers' second flags
   kPhScatter = 19,   // write every peer's slice list into the dense gradient
   kPhEnd = 20
 };
@@ -146,9 +150,14 @@ struct EngineParams {
   uint32_t* hist;                // [3][n_tensors][kHistBins]
   uint32_t* hist_total;          // [3][n_tensors] merge tickets (#tiles whose histogram was merged)
   SelState* sel;                 // [n_tensors]
-  uint32_t* tile_count;          // [n_tiles] selected/positive count of every tile (query phase)
-  uint8_t* flag_buf;             // [n_tiles * 512] per-thread 8-bit element flags (query -> emit)
-  uint32_t* barrier;             // grid barrier counter (zeroed by host per launch)
+  uint32_t* tile_count;          // [n_tiles] selected/positive count of every tile (insert / query phase)
+  uint32_t* pos_mask;            // [n_tiles * 128] positives of this rank, one bit per element, one word per 32-element group
+  uint32_t* dec_mask;            // [n_tiles * 128] decode scratch: positives of the sender being decoded
+  uint32_t* cand_key;            // [n_tiles * 4096] candidate keys (|x| patterns >= the history bound), 256 per (tile, warp)
+  uint16_t* cand_e;              // [n_tiles * 4096] in-tile element offset of every candidate
+  uint32_t* cand_cnt;            // [n_tiles * 16] candidates per (tile, warp)
+  uint32_t* barrier;             // [0] grid barrier counter, [1] push ticket, [2] stage-2 ticket (zeroed by the host per
+                                 // launch); [8] number of tensors whose history bound hid the threshold (device-managed)
   uint32_t* status;              // [8] error / watchdog words (device-local)
   uint32_t* arena[kMaxWorld];    // peer-mapped arena base of every rank (arena[rank] is local)
   int rank;
@@ -172,8 +181,8 @@ struct EngineParams {
   uint32_t* bucket_pos;          // [sum K] original position p of the grouped values
   float* expand_buf;             // [world][sum K] fitted curves of every rank
   uint32_t poly_total;           // sum K over the vmode==1 tensors
-  int own_flags;                 // decode takes this rank's own positives from flag_buf instead of re-testing its filter
-  uint8_t* warp_count;           // [n_tiles * 128] per-(slot, warp) positive counts written by query: emit ranks without a CTA barrier (nullptr: off)
+  uint32_t peer_timeout_ms;      // peer-flag waits give up after this long (status 2, output poisoned with NaN, CTA exits)
+  int fault;                     // fault injection (tests): 1 = this rank never releases its stage-1 flags
   uint32_t* mc_arena;            // NVLS multicast mapping of the symmetric arena (nullptr: per-peer P2P stores)
   int has_rle;                   // some tensor uses kModeRle (its bit stream is OR-ed, so it is zeroed every step)
   int shard;                     // 1: sharded decode + stage-2 exchange (when world > 1)

@@ -40,28 +40,55 @@ def _is_dense(p: torch.Tensor) -> bool:
 
 
 def _fused_supported(params: dict) -> bool:
-    if params.get('compressor') != 'topk' or params.get('communicator', 'allgather') != 'allgather':
+    """Which ``params`` dicts the fused bucket engine serves (everything else takes the GRACE-compatible per-tensor
+    path).  Covers every recipe of the reference's launch script (run_deepreduce.sh:35-107): top-k or threshold
+    sparsifier x {no codec, index (bloom leftmost / p0, run-length), value (polyfit, QSGD int8/int16), both}.
+    Not fused: bloom policies 'random' / 'conflict_sets' (per-tensor kernels), host codecs (Huffman, Deflate, dexp,
+    the integer family), 'randomk', non-512 QSGD buckets."""
+    if params.get('compressor') not in ('topk', 'threshold') or params.get('communicator', 'allgather') != 'allgather':
         return False
     dr = params.get('deepreduce', None)
     if dr is None:
         return True
     from ..codecs.bloom import canonical_policy
     pol_ok = canonical_policy(params.get('policy', 'leftmost')) in ('leftmost', 'p0')
+    value_ok = (params.get('value', 'polyfit') == 'polyfit'
+                or (params.get('value') == 'qsgd' and 1 <= int(params.get('quantum_num', 127)) <= 32767
+                    and int(params.get('bucket_size', 512)) == 512))
     if dr == 'index' and params.get('index', 'bloom') == 'bloom':
         return pol_ok
     if dr == 'index' and params.get('index') == 'rle':
         return True                      # lossless tile-local run coding inside the fused kernel
-    if dr == 'both' and params.get('index', 'bloom') == 'bloom' and (
-            params.get('value', 'polyfit') == 'polyfit'
-            or (params.get('value') == 'qsgd' and int(params.get('quantum_num', 127)) < 128
-                and int(params.get('bucket_size', 512)) == 512)):
-        return pol_ok
+    if dr == 'value':
+        return value_ok                  # coded values + plain indices
+    if dr == 'both' and params.get('index', 'bloom') == 'bloom':
+        return pol_ok and value_ok
     return False
+
+
+def plan_kwargs_from_params(params: dict) -> dict:
+    """``params`` dict (the reference's ``--grace_config``) -> BucketPlan keyword arguments."""
+    from ..codecs.bloom import canonical_policy
+    dr = params.get('deepreduce')
+    kw = dict(compress_ratio=params.get('compress_ratio', 0.01),
+              index=(params.get('index', 'bloom') if dr in ('index', 'both') else None),
+              value=(params.get('value', 'polyfit') if dr in ('value', 'both') else None),
+              quantum_num=int(params.get('quantum_num', 127)),
+              poly_degree=int(params.get('poly_degree', 5)),
+              fpr=params.get('fpr', None),
+              policy=canonical_policy(params.get('policy', 'leftmost')),
+              min_numel=int(params.get('min_numel', spec.SMALL_TENSOR_NUMEL)),
+              hint=bool(params.get('hint', True)))
+    if params.get('compressor') == 'threshold':
+        kw.update(sparsifier='threshold', threshold=float(params.get('threshold', 0.0)),
+                  capacity_ratio=params.get('threshold_capacity', None))
+    return kw
 
 
 class DeepReduceDDP:
     def __init__(self, module: nn.Module, params: dict, *, bucket_cap_mb: float = 1e9, overlap: bool = True,
-                 group=None, blocks_per_sm: int = 2, use_history: bool = True, background_thread: bool = True):
+                 group=None, blocks_per_sm: int = 2, use_history: bool = True, background_thread: bool = True,
+                 broadcast_parameters: bool = True, overlap_grid: int | None = None):
         self.module = module
         self.params = dict(params)
         self.group = group
@@ -82,6 +109,15 @@ class DeepReduceDDP:
         self.grc = None
         self._handles = []
         self._exchange = True
+        self._grad_views: Dict[int, torch.Tensor] = {}
+        self._status_host = None          # pinned copies of the engines' status words (async check)
+        self._status_event = None
+        self.overlap_grid_cap = int(overlap_grid if overlap_grid is not None else (self.params.get('overlap_grid', 0) or 0))
+        if self.world > 1 and broadcast_parameters:
+            # replicas must start from the same weights: rank 0's parameters and buffers win (torch DDP does the same)
+            with torch.no_grad():
+                for t in list(module.parameters()) + list(module.buffers()):
+                    dist.broadcast(t.data, 0, group=group)
         if self.fused or (self.dense and self.is_cuda):
             self._build_buckets(bucket_cap_mb, blocks_per_sm, use_history)
             if (self.fused and self.overlap and background_thread
@@ -107,7 +143,6 @@ class DeepReduceDDP:
             cur_n += p.numel()
         if cur:
             self.buckets.append(cur)
-        from ..codecs.bloom import canonical_policy
         for b, items in enumerate(self.buckets):
             numels = [p.numel() for _, p in items]
             names = [n for n, _ in items]
@@ -117,16 +152,7 @@ class DeepReduceDDP:
                 from .plan import split_large
                 numels, names, shapes, owner = split_large(numels, names, shapes, int(self.params['split_numel']))
             if self.fused:
-                plan = BucketPlan(numels, names, shapes, compress_ratio=self.params.get('compress_ratio', 0.01),
-                                  index=(self.params.get('index', 'bloom') if self.params.get('deepreduce') in ('index', 'both')
-                                         else None),
-                                  value=self.params.get('value', 'polyfit') if self.params.get('deepreduce') == 'both' else None,
-                                  quantum_num=int(self.params.get('quantum_num', 127)),
-                                  poly_degree=int(self.params.get('poly_degree', 5)),
-                                  fpr=self.params.get('fpr', None),
-                                  policy=canonical_policy(self.params.get('policy', 'leftmost')),
-                                  min_numel=int(self.params.get('min_numel', spec.SMALL_TENSOR_NUMEL)),
-                                  hint=bool(self.params.get('hint', True)))
+                plan = BucketPlan(numels, names, shapes, **plan_kwargs_from_params(self.params))
                 residual = self.params.get('memory', 'none') == 'residual'
                 eng = BucketEngine(plan, device=self.device, group=self.group,
                                    beta=float(self.params.get('beta', 1.0)) if residual else 0.0,
@@ -149,7 +175,9 @@ class DeepReduceDDP:
                 # the gradient view mirrors the parameter's own (dense) layout — e.g. channels_last conv
                 # weights — so fused optimizers see identical strides; the bucket is in storage order
                 p.grad = seg.as_strided(p.size(), p.stride()) if _is_dense(p) else seg.view(p.shape)
+                self._grad_views[id(p)] = p.grad
                 self.bucket_of[id(p)] = b
+        self._in_backward = False
         self._ready_count = [0] * len(self.buckets)
         self._launched = [False] * len(self.buckets)
         self._bucket_size = [len(it) for it in self.buckets]
@@ -168,7 +196,11 @@ class DeepReduceDDP:
         b = self.bucket_of[id(p)]
         self._ready_count[b] += 1
         if self._ready_count[b] == self._bucket_size[b]:
-            self._launch_bucket(b)
+            self._in_backward = True
+            try:
+                self._launch_bucket(b)
+            finally:
+                self._in_backward = False
 
     def _launch_bucket(self, b):
         self._ready_count[b] = 0
@@ -176,6 +208,11 @@ class DeepReduceDDP:
         if self.fused:
             eng = self.engines[b]
             eng.epoch = self.step_count + 1
+            # buckets that become ready while backward is still running are launched with a capped grid so that the
+            # persistent exchange kernel does not take every SM from cuDNN / cuBLAS; the bucket launched from
+            # finish() (nothing left to overlap with) gets the whole GPU
+            more_to_come = not all(self._launched)
+            eng.ctx.set_grid_cap(self.overlap_grid_cap if (self._in_backward and more_to_come and self.overlap_grid_cap > 0) else 0)
             if self.sched is not None:
                 self.sched.submit(b, eng.ctx, eng.epoch)
             else:
@@ -201,6 +238,7 @@ class DeepReduceDDP:
                 if p.grad is not None:
                     p.grad = self.grc.step(p.grad, n).view_as(p)
         elif self.fused:
+            self._check_grad_views()
             for b in range(len(self.buckets)):        # not overlapped, or a parameter received no gradient this step
                 if not self._launched[b]:
                     self._launch_bucket(b)
@@ -208,6 +246,7 @@ class DeepReduceDDP:
                 self.sched.wait_all()
             self._launched = [False] * len(self.buckets)
         else:
+            self._check_grad_views()
             for b in range(len(self.buckets)):
                 if not self._launched[b]:
                     self._launch_bucket(b)
@@ -219,6 +258,41 @@ class DeepReduceDDP:
                 for f in self.flat:
                     f.div_(self.world)
         self.step_count += 1
+
+    def _check_grad_views(self):
+        """``p.grad`` must still be the view into the flat bucket: ``optimizer.zero_grad(set_to_none=True)`` (torch's
+        default) or ``p.grad = None`` detaches it, autograd then allocates a fresh gradient and the exchange would
+        silently run on stale bucket contents.  Re-attach: copy what autograd produced into the bucket and point
+        ``p.grad`` back at the view."""
+        for _, p in self.named:
+            v = self._grad_views.get(id(p))
+            if v is None or p.grad is v:
+                continue
+            if p.grad is None:
+                v.zero_()                              # no gradient this step: the bucket slice must not keep old data
+            elif p.grad.data_ptr() != v.data_ptr():
+                v.copy_(p.grad)
+            p.grad = v
+
+    def check_async(self):
+        """Per-step failure detection without a host sync: enqueue a copy of every engine's status word to pinned host
+        memory, and inspect the copy enqueued by the PREVIOUS call once its event has completed (it has, a step
+        later).  Raises like :meth:`check` one step after a watchdog fired."""
+        if not self.engines:
+            return
+        if self._status_host is not None and self._status_event.query():
+            st = self._status_host
+            for b in range(len(self.engines)):
+                if int(st[b, 0]) != 0:
+                    from .engine import STATUS_NAMES
+                    raise RuntimeError(f"[rank {self.rank}/{self.world}] bucket {b} (step {self.step_count}): deepreduce "
+                                       f"engine error: {STATUS_NAMES.get(int(st[b, 0]), int(st[b, 0]))} (aux={int(st[b, 1])})")
+        if self._status_host is None:
+            self._status_host = torch.zeros(len(self.engines), 8, dtype=torch.int32).pin_memory()
+            self._status_event = torch.cuda.Event()
+        for b, e in enumerate(self.engines):
+            self._status_host[b].copy_(e.status, non_blocking=True)
+        self._status_event.record()
 
     def check(self):
         """Read the engines' device status words (one small D2H each); raises with rank and bucket on a watchdog."""
@@ -236,6 +310,15 @@ class DeepReduceDDP:
         if self.dense:
             return sum(f.numel() * 4 for f in self.flat)
         return int(self.grc.bytes_sent / max(self.step_count, 1))
+
+    def stage2_bytes_per_step(self) -> int:
+        """Sharded decode (W > 1): bytes of the second in-kernel exchange this rank sent last step — its decoded slice
+        as (index, value) pairs to each of the W-1 peers — read from the live entry count in the stage-2 header.
+        Together with ``wire_bytes_per_step`` this is everything a rank puts on NVLink per step."""
+        if not self.fused or self.world == 1:
+            return 0
+        torch.cuda.synchronize(self.device)
+        return sum(e.stage2_bytes() for e in self.engines)
 
     def dense_bytes(self) -> int:
         return sum(p.numel() * 4 for _, p in self.named)

@@ -83,9 +83,15 @@ def select_topk_oracle(acc: torch.Tensor, k: int):
     return sel, T22 << 9
 
 
+def select_threshold_oracle(acc: torch.Tensor, fixed_thr: int):
+    """'threshold' sparsifier (GRACE: |x| > threshold): every element whose |x| bit pattern is >= fixed_thr."""
+    return torch.nonzero(_abs_keys(acc) >= fixed_thr).flatten(), int(fixed_thr)
+
+
 def encode_tensor_oracle(tp, acc: torch.Tensor, slot: np.ndarray, t_index: int, policy: str, seed: int, epoch: int = 1):
     """Encode one tensor into `slot` (uint32 numpy view); returns new residual."""
-    sel_topk, T = select_topk_oracle(acc, tp.k)
+    sel_topk, T = (select_threshold_oracle(acc, tp.fixed_thr) if getattr(tp, "fixed_thr", 0)
+                   else select_topk_oracle(acc, tp.k))
     dyn = SLOT_HEADER_WORDS + DYN_WORDS * t_index
     resid = acc.clone()
     if tp.mode == MODE_BLOOM:
@@ -160,9 +166,14 @@ def encode_tensor_oracle(tp, acc: torch.Tensor, slot: np.ndarray, t_index: int, 
         dec = qsgd_decode_oracle(lvl, norms, q, 512) if n else vals
         nb = (n + 511) // 512
         slot[tp.off_coef:tp.off_coef + nb] = norms.float().numpy().view(np.uint32)
-        l8 = np.zeros(((n + 3) // 4) * 4, dtype=np.int8)
-        l8[:n] = lvl.numpy().astype(np.int8)
-        slot[tp.off_rankmap:tp.off_rankmap + (n + 3) // 4] = l8.view(np.uint32)
+        if tp.rank_u32:                      # quantum_num >= 128: 16-bit levels
+            l16 = np.zeros(((n + 1) // 2) * 2, dtype=np.int16)
+            l16[:n] = lvl.numpy().astype(np.int16)
+            slot[tp.off_rankmap:tp.off_rankmap + (n + 1) // 2] = l16.view(np.uint32)
+        else:
+            l8 = np.zeros(((n + 3) // 4) * 4, dtype=np.int8)
+            l8[:n] = lvl.numpy().astype(np.int8)
+            slot[tp.off_rankmap:tp.off_rankmap + (n + 3) // 4] = l8.view(np.uint32)
         resid[sel] = vals - dec
         vals = dec
     else:
@@ -252,7 +263,10 @@ def decode_slot_oracle(plan: BucketPlan, slot, *, seed=spec.DEFAULT_SEED) -> tor
         elif t.vmode == 2:
             from ..codecs.qsgd import qsgd_decode_oracle
             norms = torch.from_numpy(a[t.off_coef:t.off_coef + (n + 511) // 512].view(np.float32).copy())
-            lvl = torch.from_numpy(a[t.off_rankmap:t.off_rankmap + (n + 3) // 4].view(np.int8)[:n].astype(np.int64))
+            if t.rank_u32:
+                lvl = torch.from_numpy(a[t.off_rankmap:t.off_rankmap + (n + 1) // 2].view(np.int16)[:n].astype(np.int64))
+            else:
+                lvl = torch.from_numpy(a[t.off_rankmap:t.off_rankmap + (n + 3) // 4].view(np.int8)[:n].astype(np.int64))
             vals = qsgd_decode_oracle(lvl, norms, int(t.poly_degree), 512)
         else:
             vals = torch.from_numpy(a[t.off_vals:t.off_vals + n].view(np.float32).copy())
@@ -277,7 +291,7 @@ def stats_from_slot(plan: BucketPlan, slot) -> dict:
         if t.vmode == 1:
             vbytes = 4 * (22 * (t.poly_degree + 1) + 2) + (4 if t.rank_u32 else 2) * t.val_cap
         elif t.vmode == 2:
-            vbytes = 4 * ((t.val_cap + 511) // 512) + t.val_cap
+            vbytes = 4 * ((t.val_cap + 511) // 512) + t.val_cap * (2 if t.rank_u32 else 1)
         else:
             vbytes = 4 * t.val_cap
         if t.mode == MODE_BLOOM:
@@ -308,7 +322,8 @@ class BucketEngine:
                  average: bool = True, use_history: bool = True, blocks_per_sm: int = 2,
                  seed: int = spec.DEFAULT_SEED, spin_limit: int = 20_000_000, world: Optional[int] = None,
                  rank: Optional[int] = None, filter_smem_bytes: Optional[int] = None, use_tma: bool = True,
-                 hist_shift: int = 23, shard: Optional[bool] = None, transport: Optional[str] = None):
+                 hist_shift: int = 22, shard: Optional[bool] = None, transport: Optional[str] = None,
+                 peer_timeout_ms: Optional[int] = None, fault: int = 0):
         from .. import ops
         self.mod = ops.cuda_module()
         self.plan = plan
@@ -340,15 +355,29 @@ class BucketEngine:
             self.hist_total = torch.zeros(NUM_HIST * nT, dtype=torch.int32, device=dev)
             self.sel = torch.zeros(nT * 8, dtype=torch.int32, device=dev)
             self.tile_count = torch.zeros(nt, dtype=torch.int32, device=dev)
-            self.flag_buf = torch.zeros(nt * 512, dtype=torch.uint8, device=dev)
+            # scratch of the candidate / bitmask pipeline (ops/csrc/engine.cu): one mask word per 32-element group
+            # (own positives, decode scratch) and the candidate lists — (key, in-tile offset) of every element above
+            # the history bound, 256 slots per (tile, warp) at a fixed place (6 B per element, touched sparsely)
+            self.pos_mask = torch.zeros(nt * 128, dtype=torch.int32, device=dev)
+            self.dec_mask = torch.zeros(nt * 128, dtype=torch.int32, device=dev)
+            self.cand_key = torch.empty(nt * 4096, dtype=torch.int32, device=dev)
+            self.cand_e = torch.empty(nt * 4096, dtype=torch.int16, device=dev)
+            self.cand_cnt = torch.zeros(nt * 16, dtype=torch.int32, device=dev)
             self.barrier = torch.zeros(16, dtype=torch.int32, device=dev)
             self.status = torch.zeros(8, dtype=torch.int32, device=dev)
             self._setup_arena()
             self.ctx = self.mod.Engine(
                 self.tensor_table.data_ptr(), self.tile_table.data_ptr(), nT, nt, plan.slot_words, plan.payload_words,
                 self.grad.data_ptr(), self.resid.data_ptr(), self.hist.data_ptr(), self.hist_total.data_ptr(),
-                self.sel.data_ptr(), self.tile_count.data_ptr(), self.flag_buf.data_ptr(),
+                self.sel.data_ptr(), self.tile_count.data_ptr(),
                 self.barrier.data_ptr(), self.status.data_ptr(), self.arena_ptrs, self.rank, self.world)
+            self.ctx.set_scratch(self.pos_mask.data_ptr(), self.dec_mask.data_ptr(), self.cand_key.data_ptr(),
+                                 self.cand_e.data_ptr(), self.cand_cnt.data_ptr())
+            # a peer that does not signal within this wall time is fatal (status 2, output poisoned, see wait_flags)
+            if peer_timeout_ms is None:
+                peer_timeout_ms = int(os.environ.get("DR_PEER_TIMEOUT_MS", "120000"))
+            self.ctx.set_peer_timeout_ms(int(peer_timeout_ms))
+            self.ctx.set_fault(int(fault))
             scale = (1.0 / self.world) if average else 1.0
             if filter_smem_bytes is None:      # <1>: 128 regs, 1 CTA/SM; <2>: 64 regs, 2 CTAs/SM
                 filter_smem_bytes = 160 * 1024 if blocks_per_sm < 2 else 64 * 1024
@@ -357,15 +386,6 @@ class BucketEngine:
                 self.ctx.set_shard(1, s2w, cap)
             if getattr(self, "multicast_ptr", 0):
                 self.ctx.set_multicast(self.multicast_ptr)
-            # DR_OWN_FLAGS: decode takes this rank's own positives from the query phase's flags instead of re-testing
-            # its own filter (W=1: decode 159 -> 104 us, fused 0.545 -> 0.49 ms; bit-identical, tests/test_gpu_engine.py).
-            # Validated on one GPU, so it defaults to on for W == 1 only; DR_OWN_FLAGS=1 forces it for W > 1.
-            # DR_EMIT_COUNTS: the query phase leaves per-(slot, warp) counts so that emit needs no CTA barrier
-            # (emit 75 -> 64 us but query 87 -> 98 us: a wash, so off by default).
-            self.own_flags = os.environ.get("DR_OWN_FLAGS", "1" if self.world == 1 else "0") == "1"
-            self.warp_count = (torch.zeros(nt * 128, dtype=torch.uint8, device=dev)
-                               if os.environ.get("DR_EMIT_COUNTS", "0") == "1" else None)
-            self.ctx.set_opts(int(self.own_flags), self.warp_count.data_ptr() if self.warp_count is not None else 0)
             self.ctx.set_has_rle(int(any(t.mode == MODE_RLE for t in plan.tensors)))
             ids, n_poly, tasks, n_tasks = plan.poly_tables()
             self.poly_ids, self.poly_tasks = ids.to(dev), tasks.to(dev)
@@ -520,6 +540,15 @@ class BucketEngine:
         n_hdr = SLOT_HEADER_WORDS + DYN_WORDS * len(self.plan.tensors)
         return stats_from_slot(self.plan, self.slot(src_rank, epoch)[:n_hdr])
 
+    def stage2_bytes(self) -> int:
+        """Bytes this rank pushed in the stage-2 exchange of the last step (8 B per entry, to W-1 peers)."""
+        if not (self.shard and self.world > 1):
+            return 0
+        cap, s2w = self.plan.stage2_layout(self.world)
+        off = ARENA_HDR_WORDS + 2 * self.world * self.plan.slot_words + ((self.epoch & 1) * self.world + self.rank) * s2w
+        n = min(int(self.arena[off].item()), cap)
+        return 8 * n * (self.world - 1)
+
     def check_status(self):
         st = self.status.cpu().tolist()
         if st[0] != 0:
@@ -547,13 +576,20 @@ _TOPK_CACHE_MAX = 64
 
 
 def topk_select_cuda(flat: torch.Tensor, k: int):
-    """(values fp32[k], indices int64[k] ascending) of the k largest |x|."""
+    """(values[k], indices int64[k] ascending) of the k largest |x| — exact, ties broken towards the smaller index
+    (what ``torch.topk`` on a stable sort would give).
+
+    The engine's radix select resolves the threshold to 22 bits and ships EVERY element sharing that prefix (>= k of
+    them, plan.h "Selection rule"); the slot is provisioned with slack for those extra coordinates and the final k are
+    picked here from that short list by (|x| descending, index ascending).  If the prefix class is larger than the
+    slack (massive ties) the call falls back to ``torch.topk``.  With fewer than k non-zeros the result is padded with
+    (index 0, value 0.0) — harmless for ``index_add_``-style desparsification."""
     d = flat.numel()
     k = max(1, min(int(k), d))
     key = (d, k, flat.device.index)
     eng = _TOPK_CACHE.get(key)
     if eng is None:
-        plan = BucketPlan([d], index=None, ks=[k])
+        plan = BucketPlan([d], index=None, ks=[k], raw_slack=max(64, k // 8), min_numel=d)   # min_numel=d: never value-coded
         eng = BucketEngine(plan, device=flat.device, beta=0.0, gamma=1.0, average=False, use_history=False,
                            world=1, rank=0)
         _TOPK_CACHE[key] = eng
@@ -562,14 +598,28 @@ def topk_select_cuda(flat: torch.Tensor, k: int):
     else:
         _TOPK_CACHE.move_to_end(key)
     tp = eng.plan.tensors[0]
+    x = flat.detach().float().flatten()
     with torch.cuda.device(flat.device):
-        eng.grad[:d].copy_(flat.detach().float().flatten())
+        eng.grad[:d].copy_(x)
         eng.hist.zero_()
         eng.tile_count.zero_()
         eng.hist_total.zero_()
         eng.epoch += 1
         eng.ctx.run(eng.epoch, PH_ACCUM, PH_EMIT + 1)
         slot = eng.slot()
-        vals = slot[tp.off_vals:tp.off_vals + k].view(torch.float32).clone()
-        idxs = slot[tp.off_idx:tp.off_idx + k].to(torch.int64)
+        n_sel, _, _, n_pos = (int(v) for v in slot[SLOT_HEADER_WORDS:SLOT_HEADER_WORDS + 4].tolist())
+        n_sel, n_pos = n_sel & 0xFFFFFFFF, n_pos & 0xFFFFFFFF
+        if n_pos > tp.val_cap:                    # more ties at the 22-bit prefix than the slack: exact fallback
+            idxs = torch.topk(x.abs(), k, sorted=False).indices.sort().values
+            return x[idxs].to(flat.dtype), idxs
+        vals = slot[tp.off_vals:tp.off_vals + n_sel].view(torch.float32).clone()
+        idxs = slot[tp.off_idx:tp.off_idx + n_sel].to(torch.int64)
+        if n_sel > k:                             # drop the smallest of the prefix class; stable => smaller index wins ties
+            order = torch.sort(vals.abs(), descending=True, stable=True).indices[:k]
+            keep = torch.sort(order).values
+            vals, idxs = vals[keep], idxs[keep]
+        elif n_sel < k:                           # fewer than k non-zeros
+            pad = k - n_sel
+            vals = torch.cat([vals, vals.new_zeros(pad)])
+            idxs = torch.cat([idxs, idxs.new_zeros(pad)])
     return vals.to(flat.dtype), idxs

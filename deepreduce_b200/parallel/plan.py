@@ -95,13 +95,14 @@ class TensorPlan:
     rank_u32: int = 0
     poly_off: int = 0
     poly_ord: int = 0
+    fixed_thr: int = 0        # 'threshold' sparsifier: select |x| bit pattern >= fixed_thr (0: top-k radix select)
 
     def words(self) -> List[int]:
         return [self.elem_off, self.numel, self.k, self.tile_begin, self.n_tiles, self.mode, self.m_bits,
                 self.n_hash, self.off_vals, self.off_filter, self.off_prefix, self.off_idx, self.val_cap,
                 self.salt, self.n_filter_words, self.off_hint, self.vmode, self.off_coef, self.off_rankmap,
                 self.off_selidx, self.off_sorted, self.poly_degree, self.rank_u32, self.poly_off, self.poly_ord,
-                0, 0, 0, 0, 0, 0, 0]
+                self.fixed_thr, 0, 0, 0, 0, 0, 0]
 
 
 @dataclass
@@ -121,13 +122,29 @@ class BucketPlan:
     quantum_num: int = 127                # QSGD levels (int8 on the wire)
     poly_degree: int = 5
     poly_min_k: int = 512                 # tensors shipping fewer values keep them as fp32 (the fit header would be larger)
+    sparsifier: str = "topk"              # 'topk' (radix select of the K largest) | 'threshold' (|x| > threshold, variable K)
+    threshold: float = 0.0
+    capacity_ratio: Optional[float] = None   # 'threshold': slot capacity as a fraction of d (default 1.0 = lossless)
+    raw_slack: int = 0                    # plain-pair tensors: room for this many coordinates beyond K (the select keeps
+                                          # every element sharing the threshold's 22-bit prefix; ops.topk_select resolves them)
     tensors: List[TensorPlan] = field(default_factory=list, init=False)
 
     def __post_init__(self):
         if self.index not in (None, "bloom", "rle"):
             raise ValueError(f"fused engine index codecs: None, 'bloom', 'rle'; got {self.index!r}")
         if self.index == "rle" and self.value is not None:
-            raise NotImplementedError("value codecs are fused with the bloom index only")
+            raise NotImplementedError("value codecs are fused with the bloom index or plain indices, not with 'rle'")
+        if self.value not in (None, "polyfit", "qsgd"):
+            raise ValueError(f"fused engine value codecs: None, 'polyfit', 'qsgd'; got {self.value!r}")
+        if self.sparsifier not in ("topk", "threshold"):
+            raise ValueError(f"fused engine sparsifiers: 'topk', 'threshold'; got {self.sparsifier!r}")
+        if self.value == "qsgd" and not (1 <= int(self.quantum_num) <= 32767):
+            raise ValueError("quantum_num must be in [1, 32767]")
+        fixed_thr = 0
+        if self.sparsifier == "threshold":
+            # GRACE threshold: |x| > threshold  <=>  key > bits(threshold)  <=>  key >= bits(threshold) + 1
+            thr = max(0.0, float(self.threshold))
+            fixed_thr = int(np.array([thr], dtype=np.float32).view(np.uint32)[0]) + 1
         if self.policy not in POLICY_ID:
             raise ValueError(f"fused engine supports policies {list(POLICY_ID)}; got {self.policy!r}")
         if self.policy == "random":
@@ -142,10 +159,17 @@ class BucketPlan:
         for i, d in enumerate(self.numels):
             d = int(d)
             assert d > 0
-            k = min(d, spec.topk_k(d, self.compress_ratio)) if self.ks is None else max(1, min(d, int(self.ks[i])))
+            if self.ks is not None:
+                k = max(1, min(d, int(self.ks[i])))
+            elif fixed_thr:                    # variable K: the slot is provisioned for capacity_ratio * d coordinates
+                cr = 1.0 if self.capacity_ratio is None else float(self.capacity_ratio)
+                k = max(1, min(d, int(math.ceil(d * cr))))
+            else:
+                k = min(d, spec.topk_k(d, self.compress_ratio))
             n_tiles = (d + spec.TILE - 1) // spec.TILE
             tp = TensorPlan(name=names[i], numel=d, shape=tuple(shapes[i]), elem_off=elem, k=k, tile_begin=tile,
-                            n_tiles=n_tiles, mode=MODE_RAW, salt=i, poly_degree=int(self.poly_degree))
+                            n_tiles=n_tiles, mode=MODE_RAW, salt=i, poly_degree=int(self.poly_degree),
+                            fixed_thr=fixed_thr)
             if self.index == "bloom" and d > self.min_numel:
                 n_hash, m_bits, n_words = spec.bloom_layout(k, d, self.fpr, self.max_hash)
                 tp.mode = MODE_BLOOM
@@ -155,26 +179,7 @@ class BucketPlan:
                     tp.val_cap = min(d, k + int(math.ceil(2.0 * fpr * d)) + 64)
                 else:
                     tp.val_cap = k
-                if self.value == "polyfit" and k >= self.poly_min_k and tp.val_cap <= MAX_POLY_K:
-                    tp.vmode = 1
-                    tp.rank_u32 = int(tp.val_cap > 65536)
-                    tp.off_coef = word
-                    word = _align(word + MAX_SEGMENTS * (tp.poly_degree + 1) + 2, 4)
-                    tp.off_rankmap = word
-                    word = _align(word + (tp.val_cap if tp.rank_u32 else (tp.val_cap + 1) // 2), 4)
-                    scratch += [(tp, "off_vals", tp.val_cap), (tp, "off_selidx", tp.val_cap), (tp, "off_sorted", tp.val_cap)]
-                elif self.value == "qsgd" and self.quantum_num < 128:
-                    # bucketed QSGD (512 values per bucket): int8 levels + one fp32 norm per bucket
-                    tp.vmode = 2
-                    tp.poly_degree = int(self.quantum_num)      # field re-used: quantum_num
-                    tp.off_coef = word                           # norms
-                    word = _align(word + (tp.val_cap + 511) // 512, 4)
-                    tp.off_rankmap = word                        # levels (int8)
-                    word = _align(word + (tp.val_cap + 3) // 4, 4)
-                    scratch += [(tp, "off_vals", tp.val_cap), (tp, "off_selidx", tp.val_cap)]
-                else:
-                    tp.off_vals = word
-                    word = _align(word + tp.val_cap, 4)
+                word = self._value_region(tp, word, scratch)
                 tp.off_filter = word
                 word = _align(word + n_words, 4)
                 tp.off_prefix = word
@@ -194,11 +199,14 @@ class BucketPlan:
                 tp.off_idx = word
                 word = _align(word + rle_stream_words(k), 4)
             else:
-                tp.val_cap = k
-                tp.off_vals = word
-                word = _align(word + k, 4)
+                tp.val_cap = min(d, k + int(self.raw_slack))
+                if d > self.min_numel:           # value-only mode ('deepreduce': 'value'): coded values + plain indices
+                    word = self._value_region(tp, word, scratch)
+                else:
+                    tp.off_vals = word
+                    word = _align(word + tp.val_cap, 4)
                 tp.off_idx = word
-                word = _align(word + k, 4)
+                word = _align(word + tp.val_cap, 4)
             self.tensors.append(tp)
             elem = _align(elem + d, ALIGN_ELEMS)
             tile += n_tiles
@@ -210,6 +218,32 @@ class BucketPlan:
             word = _align(word + n, 4)
         self.slot_words = _align(word, 64)
         self.poly_tables()                     # assigns poly_off / poly_ord
+
+    def _value_region(self, tp: TensorPlan, word: int, scratch: list) -> int:
+        """Lay out the value side of a tensor's slot region (fp32 values, or a value codec + sender-local scratch)."""
+        if self.value == "polyfit" and tp.k >= self.poly_min_k and tp.val_cap <= MAX_POLY_K:
+            tp.vmode = 1
+            tp.rank_u32 = int(tp.val_cap > 65536)
+            tp.off_coef = word
+            word = _align(word + MAX_SEGMENTS * (tp.poly_degree + 1) + 2, 4)
+            tp.off_rankmap = word
+            word = _align(word + (tp.val_cap if tp.rank_u32 else (tp.val_cap + 1) // 2), 4)
+            scratch += [(tp, "off_vals", tp.val_cap), (tp, "off_selidx", tp.val_cap), (tp, "off_sorted", tp.val_cap)]
+        elif self.value == "qsgd":
+            # bucketed QSGD (512 values per bucket): int8 levels (int16 when quantum_num >= 128, reference
+            # pytorch/deepreduce.py:873) + one fp32 norm per bucket
+            tp.vmode = 2
+            tp.poly_degree = int(self.quantum_num)      # field re-used: quantum_num
+            tp.rank_u32 = int(self.quantum_num >= 128)  # field re-used: 16-bit levels
+            tp.off_coef = word                           # norms
+            word = _align(word + (tp.val_cap + 511) // 512, 4)
+            tp.off_rankmap = word                        # levels
+            word = _align(word + ((tp.val_cap + 1) // 2 if tp.rank_u32 else (tp.val_cap + 3) // 4), 4)
+            scratch += [(tp, "off_vals", tp.val_cap), (tp, "off_selidx", tp.val_cap)]
+        else:
+            tp.off_vals = word
+            word = _align(word + tp.val_cap, 4)
+        return word
 
     def poly_tables(self):
         """(tensor ids with vmode==1, largest K first ; rank-phase tasks {tensor, first value of a 512-chunk})."""

@@ -25,7 +25,7 @@ class Trainer:
                  channels_last: bool = False, loss_fn: Optional[Callable] = None, optimizer=None,
                  overlap: bool = True, bucket_cap_mb: float = 1e9, background_thread: bool = True,
                  blocks_per_sm: int = 2, u8_input: bool = False, accum_steps: int = 1, nvtx: bool = False,
-                 check_every: int = 100):
+                 check_every: int = 100, overlap_grid: Optional[int] = None):
         self.model = model
         self.device = next(model.parameters()).device
         self.is_cuda = self.device.type == "cuda"
@@ -35,7 +35,8 @@ class Trainer:
             self.model = self.model.to(memory_format=torch.channels_last)
         self.loss_fn = loss_fn or F.cross_entropy
         self.ddp = DeepReduceDDP(self.model, params, overlap=overlap, bucket_cap_mb=bucket_cap_mb,
-                                 background_thread=background_thread, blocks_per_sm=blocks_per_sm)
+                                 background_thread=background_thread, blocks_per_sm=blocks_per_sm,
+                                 overlap_grid=overlap_grid)
         if optimizer is None:
             kw = dict(lr=lr, momentum=momentum, weight_decay=weight_decay)
             if self.is_cuda:
@@ -93,6 +94,8 @@ class Trainer:
                 self.ddp.finish()
                 self.opt.step()
             self._opt_steps += 1
+            if self.is_cuda:
+                self.ddp.check_async()            # every step, no host sync: raises one step after a watchdog fired
             if self.check_every and self._opt_steps % self.check_every == 0:
                 self.ddp.check()                  # raises with rank / bucket / watchdog name
         return loss.detach()

@@ -113,23 +113,22 @@ def test_engine_vs_oracle_single_rank(kind, index, policy, hint, tma, value):
     _run_vs_oracle(kind, index, policy, hint, tma, value)
 
 
-@pytest.mark.parametrize("own,counts", [(0, 0), (1, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("hist_shift,bps", [(23, 2), (22, 1), (20, 2)])
 @pytest.mark.parametrize("index,policy,value", [("bloom", "leftmost", None), ("bloom", "p0", None), (None, "leftmost", None),
                                                 ("rle", "leftmost", None), ("bloom", "leftmost", "polyfit")])
-def test_engine_option_flags_vs_oracle(monkeypatch, own, counts, index, policy, value):
-    """DR_OWN_FLAGS (decode reuses the sender's own query flags) and DR_EMIT_COUNTS (barrier-free emit from the
-    query phase's per-warp counts) must not change a single bit of the slot / output / residual."""
-    monkeypatch.setenv("DR_OWN_FLAGS", str(own))
-    monkeypatch.setenv("DR_EMIT_COUNTS", str(counts))
+def test_engine_option_flags_vs_oracle(hist_shift, bps, index, policy, value):
+    """The history bound (how many elements become candidates; 20 = tight -> frequent fallbacks) and the register /
+    occupancy variant of the kernel must not change a single bit of the slot / output / residual."""
     for kind in ("randn", "ties"):
-        _run_vs_oracle(kind, index, policy, True, True, value)
+        _run_vs_oracle(kind, index, policy, True, True, value, hist_shift=hist_shift, bps=bps)
 
 
-def _run_vs_oracle(kind, index, policy, hint, tma, value):
+def _run_vs_oracle(kind, index, policy, hint, tma, value, hist_shift=22, bps=2):
     from deepreduce_b200.parallel import BucketEngine, BucketPlan, engine_oracle
     plan = BucketPlan(SIZES + [2359296], compress_ratio=0.01, index=index, policy=policy, hint=hint, value=value,
                       poly_min_k=300)
-    eng = BucketEngine(plan, device="cuda:0", world=1, rank=0, spin_limit=2_000_000, use_tma=tma)
+    eng = BucketEngine(plan, device="cuda:0", world=1, rank=0, spin_limit=2_000_000, use_tma=tma, hist_shift=hist_shift,
+                       blocks_per_sm=bps)
     gen = torch.Generator().manual_seed(0)
     resid_ref = torch.zeros(plan.total_elems)
     for step in range(3):                       # step 0: no history; steps 1,2: history lower bound (+fallback)
