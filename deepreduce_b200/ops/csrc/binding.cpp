@@ -274,11 +274,10 @@ struct Engine {
 
   void set_has_rle(int v) { P.has_rle = v; }
   // scratch of the candidate / bitmask pipeline (see engine.cu): masks [n_tiles*128] u32 x2, candidate keys
-  // [n_tiles*4096] u32, offsets [n_tiles*4096] u16, counts [n_tiles*16] u32
-  void set_scratch(int64_t pos_mask, int64_t dec_mask, int64_t cand_key, int64_t cand_e, int64_t cand_cnt) {
+  // entries [n_tiles*4096] x {u32 key, u32 offset}, counts [n_tiles*16] u32
+  void set_scratch(int64_t pos_mask, int64_t dec_mask, int64_t cand, int64_t cand_cnt) {
     P.pos_mask = reinterpret_cast<uint32_t*>(pos_mask); P.dec_mask = reinterpret_cast<uint32_t*>(dec_mask);
-    P.cand_key = reinterpret_cast<uint32_t*>(cand_key); P.cand_e = reinterpret_cast<uint16_t*>(cand_e);
-    P.cand_cnt = reinterpret_cast<uint32_t*>(cand_cnt);
+    P.cand = reinterpret_cast<uint2*>(cand); P.cand_cnt = reinterpret_cast<uint32_t*>(cand_cnt);
   }
   void set_peer_timeout_ms(int64_t ms) { P.peer_timeout_ms = (uint32_t)ms; }
   void set_fault(int f) { P.fault = f; }
@@ -301,7 +300,7 @@ struct Engine {
   void run_on(uint32_t epoch, int phase_begin, int phase_end, cudaStream_t st) {
     EngineParams Q = P;
     Q.epoch = epoch; Q.phase_begin = phase_begin; Q.phase_end = phase_end;
-    TORCH_CHECK(P.pos_mask && P.cand_key, "Engine: set_scratch() was not called");
+    TORCH_CHECK(P.pos_mask && P.cand, "Engine: set_scratch() was not called");
     int g = get_grid();
     if (grid_cap > 0 && grid_cap < g) g = grid_cap;
     cudaError_t e = dr::engine_launch(Q, g, blocks_per_sm, dyn_smem, st);

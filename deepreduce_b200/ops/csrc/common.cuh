@@ -123,6 +123,10 @@ DR_D void mbar_inval(uint64_t* bar) {
 }
 DR_D void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 DR_D void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// shared-memory-only variant: orders generic-proxy reads of an SMEM stage before the TMA (async-proxy) write that
+// refills it.  The unqualified fence above lowers to MEMBAR.ALL.GPU + FENCE.VIEW.ASYNC and waits for every global
+// store of the thread — it must stay out of the ring's refill path (profiles/: v11 accumulate phase).
+DR_D void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 DR_D void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
 }

@@ -153,8 +153,8 @@ struct EngineParams {
   uint32_t* tile_count;          // [n_tiles] selected/positive count of every tile (insert / query phase)
   uint32_t* pos_mask;            // [n_tiles * 128] positives of this rank, one bit per element, one word per 32-element group
   uint32_t* dec_mask;            // [n_tiles * 128] decode scratch: positives of the sender being decoded
-  uint32_t* cand_key;            // [n_tiles * 4096] candidate keys (|x| patterns >= the history bound), 256 per (tile, warp)
-  uint16_t* cand_e;              // [n_tiles * 4096] in-tile element offset of every candidate
+  uint2* cand;                   // [n_tiles * 4096] candidates {key = |x| pattern >= the history bound, in-tile element offset},
+                                 // 256 slots per (tile, warp) at a fixed place
   uint32_t* cand_cnt;            // [n_tiles * 16] candidates per (tile, warp)
   uint32_t* barrier;             // [0] grid barrier counter, [1] push ticket, [2] stage-2 ticket (zeroed by the host per
                                  // launch); [8] number of tensors whose history bound hid the threshold (device-managed)

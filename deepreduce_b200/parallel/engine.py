@@ -357,11 +357,10 @@ class BucketEngine:
             self.tile_count = torch.zeros(nt, dtype=torch.int32, device=dev)
             # scratch of the candidate / bitmask pipeline (ops/csrc/engine.cu): one mask word per 32-element group
             # (own positives, decode scratch) and the candidate lists — (key, in-tile offset) of every element above
-            # the history bound, 256 slots per (tile, warp) at a fixed place (6 B per element, touched sparsely)
+            # the history bound, 256 slots per (tile, warp) at a fixed place (8 B per element, touched sparsely)
             self.pos_mask = torch.zeros(nt * 128, dtype=torch.int32, device=dev)
             self.dec_mask = torch.zeros(nt * 128, dtype=torch.int32, device=dev)
-            self.cand_key = torch.empty(nt * 4096, dtype=torch.int32, device=dev)
-            self.cand_e = torch.empty(nt * 4096, dtype=torch.int16, device=dev)
+            self.cand = torch.empty(nt * 4096 * 2, dtype=torch.int32, device=dev)
             self.cand_cnt = torch.zeros(nt * 16, dtype=torch.int32, device=dev)
             self.barrier = torch.zeros(16, dtype=torch.int32, device=dev)
             self.status = torch.zeros(8, dtype=torch.int32, device=dev)
@@ -371,8 +370,8 @@ class BucketEngine:
                 self.grad.data_ptr(), self.resid.data_ptr(), self.hist.data_ptr(), self.hist_total.data_ptr(),
                 self.sel.data_ptr(), self.tile_count.data_ptr(),
                 self.barrier.data_ptr(), self.status.data_ptr(), self.arena_ptrs, self.rank, self.world)
-            self.ctx.set_scratch(self.pos_mask.data_ptr(), self.dec_mask.data_ptr(), self.cand_key.data_ptr(),
-                                 self.cand_e.data_ptr(), self.cand_cnt.data_ptr())
+            self.ctx.set_scratch(self.pos_mask.data_ptr(), self.dec_mask.data_ptr(), self.cand.data_ptr(),
+                                 self.cand_cnt.data_ptr())
             # a peer that does not signal within this wall time is fatal (status 2, output poisoned, see wait_flags)
             if peer_timeout_ms is None:
                 peer_timeout_ms = int(os.environ.get("DR_PEER_TIMEOUT_MS", "120000"))
@@ -380,7 +379,7 @@ class BucketEngine:
             self.ctx.set_fault(int(fault))
             scale = (1.0 / self.world) if average else 1.0
             if filter_smem_bytes is None:      # <1>: 128 regs, 1 CTA/SM; <2>: 64 regs, 2 CTAs/SM
-                filter_smem_bytes = 160 * 1024 if blocks_per_sm < 2 else 64 * 1024
+                filter_smem_bytes = 160 * 1024 if blocks_per_sm < 2 else 80 * 1024
             if self.shard and self.world > 1:
                 cap, s2w = plan.stage2_layout(self.world)
                 self.ctx.set_shard(1, s2w, cap)

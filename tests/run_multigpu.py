@@ -20,12 +20,15 @@ def main():
                                         ("bloom", "p0", None, True), (None, "leftmost", None, True),
                                         ("rle", "leftmost", None, True), ("rle", "leftmost", None, False),
                                         ("bloom", "leftmost", "polyfit", True), ("bloom", "leftmost", "polyfit", False),
-                                        ("bloom", "leftmost", "qsgd", True)) + (
-            # multi-host transport (encode -> one NCCL all_gather of the slots -> decode); opt-in until it has had
-            # its first hardware run: DR_TEST_NCCL_TRANSPORT=1
+                                        ("bloom", "leftmost", "qsgd", True), (None, "leftmost", "polyfit", True),
+                                        ("bloom", "thr", None, True), (None, "thr", "qsgd", False)) + (
+            # multi-host transport (encode -> one NCCL all_gather of the slots -> decode); DR_TEST_NCCL_TRANSPORT=0 skips
             (("bloom", "leftmost", None, "nccl"), ("rle", "leftmost", None, "nccl"), ("bloom", "leftmost", "polyfit", "nccl"))
-            if os.environ.get("DR_TEST_NCCL_TRANSPORT", "0") == "1" else ()):
-        plan = BucketPlan(sizes, compress_ratio=0.01, index=index, policy=policy, value=value)
+            if os.environ.get("DR_TEST_NCCL_TRANSPORT", "1") == "1" else ()):
+        extra = {}
+        if policy == "thr":                      # 'threshold' sparsifier (variable K)
+            policy, extra = "leftmost", dict(sparsifier="threshold", threshold=1.8, capacity_ratio=0.2)
+        plan = BucketPlan(sizes, compress_ratio=0.01, index=index, policy=policy, value=value, **extra)
         eng = BucketEngine(plan, device=f"cuda:{local}", spin_limit=4_000_000, shard=shard,
                            transport="nccl" if shard == "nccl" else None)
         if rank == 0:
@@ -68,6 +71,29 @@ def main():
                 print(f"[rank {rank}] MISMATCH index={index} policy={policy} value={value} shard={shard} step={step} out={same_out} res={same_res} slots={same_slots}",
                       flush=True)
         eng.close()
+    # fault injection: rank 1 never releases its flags -> every peer's wait expires after the wall-time
+    # limit, sets status 2 ("peer flag watchdog"), poisons its output with NaN and leaves the kernel — no hang, and
+    # check_status() raises on the host.  Rank 1 itself waits for nobody that failed, so it completes.
+    if os.environ.get("DR_TEST_FAULT", "1") == "1" and world > 1:
+        plan = BucketPlan(sizes, compress_ratio=0.01, index="bloom")
+        eng = BucketEngine(plan, device=f"cuda:{local}", spin_limit=4_000_000, peer_timeout_ms=1500,
+                           fault=1 if rank == 1 else 0)
+        eng.grad.normal_()
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record(); eng.step(); t1.record()
+        torch.cuda.synchronize()
+        raised = False
+        try:
+            eng.check_status()
+        except RuntimeError as e:
+            raised = "peer flag watchdog" in str(e)
+        ms = t0.elapsed_time(t1)
+        poisoned = bool(torch.isnan(eng.grad).any().item())
+        good = (raised and poisoned and ms < 20000) if rank != 1 else True
+        print(f"[rank {rank}] fault injection: raised={raised} poisoned={poisoned} kernel_ms={ms:.0f} -> {'ok' if good else 'BAD'}", flush=True)
+        ok = ok and good
+        dist.barrier()
+        # eng.close() would barrier + free; the arena is leaked on purpose (peers may still hold mappings of a dead step)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0 and int(flag.item()) == 1:

@@ -276,3 +276,29 @@ def test_split_large_chunks_are_contiguous_tile_multiples():
     whole = BucketPlan([31254528], compress_ratio=0.01).tensors[0]
     assert whole.n_filter_words * 4 > 227 * 1024                       # as one tensor it cannot
     assert split_large(numels, names, shapes, None)[0] == numels
+
+
+def test_selfcheck_torch_decoder_matches_numpy_oracle():
+    """utils/selfcheck.decode_slot_torch (the independent decoder bench.py uses for its multi-GPU check) agrees with
+    the numpy slot decoder on every fp32-value mode, and declines value-coded plans."""
+    import torch
+    from deepreduce_b200.parallel import BucketPlan, engine_oracle
+    from deepreduce_b200.parallel.engine import decode_slot_oracle
+    from deepreduce_b200.utils.selfcheck import decode_slot_torch
+    sizes = [64, 1001, 4097, 36864, 147456]
+    gen = torch.Generator().manual_seed(3)
+    for kw in (dict(index="bloom"), dict(index="bloom", hint=False), dict(index="bloom", policy="p0"), dict(index=None),
+               dict(index="bloom", sparsifier="threshold", threshold=1.0, capacity_ratio=0.5)):
+        plan = BucketPlan(sizes, compress_ratio=0.01, **kw)
+        g = torch.zeros(plan.total_elems)
+        for v in plan.views(g):
+            v.copy_(torch.randn(v.shape, generator=gen))
+        out, _, slots = engine_oracle(plan, [g], [torch.zeros_like(g)])
+        slot_t = torch.from_numpy(slots[0].view("int32").copy())
+        dec = decode_slot_torch(plan, slot_t)
+        assert torch.equal(dec, decode_slot_oracle(plan, slots[0])), kw
+        assert torch.equal(dec, out), kw
+    plan = BucketPlan(sizes, compress_ratio=0.01, index="bloom", value="qsgd")
+    g = torch.randn(plan.total_elems)
+    _, _, slots = engine_oracle(plan, [g], [torch.zeros_like(g)])
+    assert decode_slot_torch(plan, torch.from_numpy(slots[0].view("int32").copy())) is None

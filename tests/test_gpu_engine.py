@@ -123,10 +123,10 @@ def test_engine_option_flags_vs_oracle(hist_shift, bps, index, policy, value):
         _run_vs_oracle(kind, index, policy, True, True, value, hist_shift=hist_shift, bps=bps)
 
 
-def _run_vs_oracle(kind, index, policy, hint, tma, value, hist_shift=22, bps=2):
+def _run_vs_oracle(kind, index, policy, hint, tma, value, hist_shift=22, bps=2, **plan_kw):
     from deepreduce_b200.parallel import BucketEngine, BucketPlan, engine_oracle
     plan = BucketPlan(SIZES + [2359296], compress_ratio=0.01, index=index, policy=policy, hint=hint, value=value,
-                      poly_min_k=300)
+                      poly_min_k=300, **plan_kw)
     eng = BucketEngine(plan, device="cuda:0", world=1, rank=0, spin_limit=2_000_000, use_tma=tma, hist_shift=hist_shift,
                        blocks_per_sm=bps)
     gen = torch.Generator().manual_seed(0)
@@ -154,6 +154,41 @@ def _run_vs_oracle(kind, index, policy, hint, tma, value, hist_shift=22, bps=2):
             assert torch.allclose(eng.resid.cpu(), new_res[0], atol=2e-3 * scale, rtol=1e-2), tag
             resid_ref = eng.resid.cpu().clone()      # follow the GPU trajectory so later steps compare like with like
     eng.close()
+
+
+@pytest.mark.parametrize("index,policy,value,kw", [
+    (None, "leftmost", "polyfit", {}),                                         # value-only mode: coded values + plain indices
+    (None, "leftmost", "qsgd", {}),
+    ("bloom", "leftmost", "qsgd", dict(quantum_num=1000)),                     # int16 QSGD levels
+    ("bloom", "leftmost", None, dict(sparsifier="threshold", threshold=0.0, capacity_ratio=0.5)),
+    (None, "leftmost", None, dict(sparsifier="threshold", threshold=1.5)),
+    ("bloom", "p0", None, dict(sparsifier="threshold", threshold=0.0, fpr=0.01, capacity_ratio=0.3)),
+    ("rle", "leftmost", None, dict(sparsifier="threshold", threshold=2.0, capacity_ratio=0.1)),
+    ("bloom", "leftmost", "qsgd", dict(sparsifier="threshold", threshold=1.0, capacity_ratio=0.5)),
+])
+def test_engine_fused_recipe_modes(index, policy, value, kw):
+    """The reference's launch recipes beyond top-k + bloom (run_deepreduce.sh:66-74): threshold sparsifier (variable K),
+    value-only mode, QSGD with >= 128 levels — all inside the fused kernel, bit-exact against the oracle."""
+    for kind in ("randn", "sparse"):
+        _run_vs_oracle(kind, index, policy, True, True, value, **kw)
+
+
+def test_topk_select_exact_with_ties_and_sparse():
+    """ops.topk_select is exact: ties at the threshold go to the smaller index, fewer than k non-zeros pad with zeros."""
+    from deepreduce_b200 import ops
+    x = torch.tensor([1.0] * 1000 + [100.0])
+    v, i = ops.topk_select(x.cuda(), 2)                 # massive ties: falls back to torch.topk
+    assert sorted(i.cpu().tolist())[-1] == 1000 and float(v.abs().max()) == 100.0
+    g = torch.Generator().manual_seed(5)
+    y = torch.randint(-50, 51, (300000,), generator=g).float()      # many equal magnitudes around the threshold
+    v, i = ops.topk_select(y.cuda(), 3000)
+    ref = torch.sort(y.abs(), descending=True, stable=True).indices[:3000].sort().values
+    assert torch.equal(i.cpu(), ref) and torch.equal(v.cpu(), y[ref])
+    z = torch.zeros(200000); z[[5, 77, 1999]] = torch.tensor([1.0, -2.0, 3.0])
+    v, i = ops.topk_select(z.cuda(), 100)
+    assert v.numel() == 100 and set(i.cpu().tolist()) == {0, 5, 77, 1999} and float(v.abs().sum()) == 6.0
+    from deepreduce_b200.grace.sparsifiers import _desparsify
+    assert torch.equal(_desparsify((v, i), torch.Size([200000])).cpu(), z)
 
 
 def test_engine_resnet50_shapes_and_volume():
