@@ -58,11 +58,15 @@ def parse():
                     help="flat bucket size; on a compute-saturated GPU one bucket launched at the end of backward is fastest (profiles/)")
     ap.add_argument("--blocks-per-sm", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--breakdown", action="store_true", help="also time the exchange kernel alone (extra keys)")
+    ap.add_argument("--breakdown", action="store_true", help="(kept for compatibility: the exchange-kernel timing is always reported)")
+    ap.add_argument("--overlap-grid", type=int, default=0,
+                    help="CTAs for exchange kernels launched while backward is still running (0 = whole GPU)")
+    ap.add_argument("--no-dense-context", action="store_true", help="skip the dense NCCL all-reduce context measurement")
+    ap.add_argument("--no-check", action="store_true", help="skip the multi-GPU correctness self-check (N > 1)")
     return ap.parse_args()
 
 
-def exchange_roofline(exchange_ms, dense_bytes, wire_bytes, world):
+def exchange_roofline(exchange_ms, dense_bytes, wire_bytes, world, stage2_bytes=None):
     """Achieved fraction of the exchange kernel's roofline = the slower of (a) its unavoidable HBM traffic at the
     MEASURED copy bandwidth (read g, read r, write r, write the dense result: 4 x dense bytes) and (b) the bytes it
     sends over NVLink at link bandwidth (the slot to W-1 peers, plus about as much again for the decoded slices of
@@ -76,7 +80,8 @@ def exchange_roofline(exchange_ms, dense_bytes, wire_bytes, world):
         pass
     nvlink = 770.0
     t_hbm = 4.0 * dense_bytes / (hbm * 1e9) * 1e3
-    nv_bytes = 2.0 * (world - 1) * wire_bytes
+    # bytes this rank puts on NVLink: its slot to W-1 peers + its decoded slice lists (live count, or ~ as much again)
+    nv_bytes = (world - 1) * wire_bytes + (stage2_bytes if stage2_bytes is not None else (world - 1) * wire_bytes)
     t_nv = nv_bytes / (nvlink * 1e9) * 1e3
     return {"hbm_min_bytes": int(4 * dense_bytes), "hbm_gbs_measured": hbm, "hbm_bound_ms": t_hbm,
             "nvlink_bytes_out": int(nv_bytes), "nvlink_gbs_per_dir": nvlink, "nvlink_bound_ms": t_nv,
@@ -198,6 +203,51 @@ def timed(fn, steps, world):
     return max_over_ranks(e0.elapsed_time(e1), world), max_over_ranks(wall, world)
 
 
+MEAN = (0.485, 0.456, 0.406)
+STD = (0.229, 0.224, 0.225)
+
+
+def bench_config(args, kind, B, world, cfg):
+    """The `config` object of the JSON line — IDENTICAL in the `ours` and `reference` arms (same model architecture,
+    batch, dtype, optimizer, input pipeline, step counts); everything implementation-specific goes to `harness`."""
+    return {"model": args.model, "global_batch": B * world, "per_gpu_batch": B,
+            "seq_len": args.seq if kind == "bert" else None, "parallelism": f"dp{world}",
+            "gradient_exchange": args.config,
+            "params": {k: v for k, v in cfg.items() if isinstance(v, (str, int, float, bool, type(None)))},
+            "optimizer": "SGD(momentum=0.9, weight_decay=1e-4, fused=True)" if kind != "bert" else "SGD(momentum=0.9, weight_decay=1e-4, fused=True, lr=1e-4)",
+            "input": ("uint8 NHWC batch in pinned host memory -> H2D -> normalise -> bf16 channels_last" if kind.startswith("image")
+                      else "int64 ids in pinned host memory -> H2D"),
+            "e2e": "H2D of the step's batch (prefetched one step ahead on a copy stream) + loss read back to the host, every step",
+            "e2e_steps": args.steps,
+            "l2": "working set (activations + fp32 gradients + residual) exceeds the 126 MB L2 every step"}
+
+
+def synth_batches(kind, B, seq, gen):
+    import torch
+    if kind.startswith("image"):
+        hw = 224 if kind == "image224" else 32
+        ncls = 1000 if kind == "image224" else 10
+        pool = [(torch.randint(0, 256, (B, hw, hw, 3), dtype=torch.uint8, generator=gen),) for _ in range(2)]
+        tgt = [torch.randint(0, ncls, (B,), generator=gen) for _ in range(2)]
+    elif kind == "bert":
+        pool = [(torch.randint(0, 30522, (B, seq), generator=gen),) for _ in range(2)]
+        tgt = [p[0].clone() for p in pool]
+    else:   # ncf
+        pool = [(torch.randint(0, 138493, (B,), generator=gen), torch.randint(0, 26744, (B,), generator=gen)) for _ in range(2)]
+        tgt = [torch.randint(0, 2, (B,), generator=gen).float() for _ in range(2)]
+    return pool, tgt
+
+
+def loss_for(kind):
+    import torch
+    if kind == "bert":
+        return lambda out, y: torch.nn.functional.cross_entropy(
+            (out.logits if hasattr(out, "logits") else out).reshape(-1, 30522).float(), y.reshape(-1))
+    if kind == "ncf":
+        return torch.nn.functional.binary_cross_entropy_with_logits
+    return None
+
+
 def model_spec(args):
     """(model, kind, default per-GPU batch, metric unit)"""
     from deepreduce_b200 import models as M
@@ -212,6 +262,33 @@ def model_spec(args):
     raise ValueError(args.model)
 
 
+def measure_dense_context(args, kind, B, world, pool, tgt):
+    """Dense NCCL all-reduce data parallelism on the same box, same model / batch / optimizer (context row: on NVLink
+    it is the strongest baseline; the compressed path is expected to match it, not beat it)."""
+    import torch
+    from deepreduce_b200.trainer import Trainer
+    model, _, _, _ = model_spec(args)
+    model = model.cuda()
+    amp = torch.bfloat16 if args.dtype == "bf16" else None
+    tr = Trainer(model, dict(CONFIGS["dense"]), lr=0.05 if kind != "bert" else 1e-4, amp_dtype=amp,
+                 channels_last=kind.startswith("image"), bucket_cap_mb=args.bucket_mb, u8_input=kind.startswith("image"),
+                 loss_fn=loss_for(kind))
+    dev_x = [tuple(t.cuda() for t in p) for p in pool]
+    dev_y = [t.cuda() for t in tgt]
+
+    def step(i):
+        tr.step(*dev_x[i & 1], target=dev_y[i & 1])
+
+    for i in range(args.warmup):
+        step(i)
+    ms, _ = timed(step, args.steps, world)
+    tr.close()
+    del tr, model
+    torch.cuda.empty_cache()
+    return {"value": world * B * args.steps / (ms / 1e3), "ms_per_step": ms / args.steps,
+            "what": "dense NCCL all-reduce DDP, same model/batch/optimizer, device-timed, same process"}
+
+
 def run_ours(args, rank, world, local):
     import torch
     from deepreduce_b200 import ops
@@ -224,24 +301,11 @@ def run_ours(args, rank, world, local):
     cfg = dict(CONFIGS[args.config])
     amp = torch.bfloat16 if args.dtype == "bf16" else None
     gen = torch.Generator().manual_seed(77 + rank)
-    loss_fn = None
-    if kind.startswith("image"):
-        hw = 224 if kind == "image224" else 32
-        ncls = 1000 if kind == "image224" else 10
-        pool = [(torch.randint(0, 256, (B, hw, hw, 3), dtype=torch.uint8, generator=gen),) for _ in range(2)]
-        tgt = [torch.randint(0, ncls, (B,), generator=gen) for _ in range(2)]
-    elif kind == "bert":
-        V = 30522
-        pool = [(torch.randint(0, V, (B, args.seq), generator=gen),) for _ in range(2)]
-        tgt = [p[0].clone() for p in pool]
-        loss_fn = lambda out, y: torch.nn.functional.cross_entropy(out.logits.reshape(-1, V).float(), y.reshape(-1))  # noqa: E731
-    else:   # ncf
-        pool = [(torch.randint(0, 138493, (B,), generator=gen), torch.randint(0, 26744, (B,), generator=gen)) for _ in range(2)]
-        tgt = [torch.randint(0, 2, (B,), generator=gen).float() for _ in range(2)]
-        loss_fn = torch.nn.functional.binary_cross_entropy_with_logits
+    pool, tgt = synth_batches(kind, B, args.seq, gen)
     tr = Trainer(model, cfg, lr=0.05 if kind != "bert" else 1e-4, amp_dtype=amp, channels_last=kind.startswith("image"),
                  overlap=not args.no_overlap, bucket_cap_mb=args.bucket_mb, background_thread=not args.no_thread,
-                 blocks_per_sm=args.blocks_per_sm, u8_input=kind.startswith("image"), loss_fn=loss_fn)
+                 blocks_per_sm=args.blocks_per_sm, u8_input=kind.startswith("image"), loss_fn=loss_for(kind),
+                 overlap_grid=args.overlap_grid)
     dev_x = [tuple(t.cuda() for t in p) for p in pool]
     dev_y = [t.cuda() for t in tgt]
 
@@ -277,19 +341,29 @@ def run_ours(args, rank, world, local):
                "h2d_bytes_per_step": int(tr.h2d_bytes), "d2h_bytes_per_step": int(tr.d2h_bytes)}
 
     extra = {}
-    if args.breakdown and tr.ddp.engines:
-        def ex(i):       # exchange kernel alone on the last gradients (all buckets back to back)
+    wire = tr.ddp.wire_bytes_per_step()
+    dense = tr.ddp.dense_bytes()
+    if tr.ddp.engines:
+        def ex(i):       # the exchange kernels alone, on the last gradients (all buckets back to back)
             for e in tr.ddp.engines:
+                e.ctx.set_grid_cap(0)
                 e.step()
         for i in range(3):
             ex(i)
         ms_ex, _ = timed(ex, 20, world)
+        stage2 = tr.ddp.stage2_bytes_per_step()
         extra["exchange_ms_per_step"] = ms_ex / 20
         extra["engine_grid"] = tr.ddp.engines[0].grid()
-        extra["roofline"] = exchange_roofline(extra["exchange_ms_per_step"], tr.ddp.dense_bytes(),
-                                              tr.ddp.wire_bytes_per_step(), world)
-    wire = tr.ddp.wire_bytes_per_step()
-    dense = tr.ddp.dense_bytes()
+        extra["stage2_bytes_per_step_per_rank"] = int(stage2)
+        extra["nvlink_bytes_out_per_step_per_rank"] = int((world - 1) * wire + stage2)
+        extra["roofline"] = exchange_roofline(extra["exchange_ms_per_step"], dense, wire, world, stage2)
+        extra["compressed_allgather_bus_gbs"] = extra["roofline"]["compressed_allgather_bus_gbs"]
+        if world > 1 and not args.no_check:
+            from deepreduce_b200.utils.selfcheck import multi_gpu_check
+            chk = multi_gpu_check(tr.ddp.engines[0])
+            extra["multi_gpu_check"] = chk["status"]
+            extra["multi_gpu_check_detail"] = {k: v for k, v in chk.items() if k != "status"}
+        tr.ddp.check()
     names = {"resnet50": "ResNet-50 images/sec (whole job, device-timed, max over ranks)",
              "bert_large": "BERT-large sequences/sec (whole job, device-timed, max over ranks)",
              "ncf": "NCF (MovieLens-20M shapes) samples/sec (whole job, device-timed, max over ranks)"}
@@ -298,23 +372,59 @@ def run_ours(args, rank, world, local):
         "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic (shapes of the named benchmark, random-init weights)", "impl": "ours",
-        "config": {"model": args.model, "global_batch": B * world, "per_gpu_batch": B,
-                   "seq_len": args.seq if kind == "bert" else None,
-                   "parallelism": f"dp{world}", "gradient_exchange": args.config, "params": cfg,
-                   "l2": "working set (activations + fp32 gradients + residual) exceeds the 126 MB L2 every step",
-                   "overlap": not args.no_overlap, "buckets": len(tr.ddp.flat), "bucket_mb": args.bucket_mb},
+        "config": bench_config(args, kind, B, world, cfg),
+        "harness": {"model_impl": "deepreduce_b200.models", "exchange": "fused bucket engine (one persistent kernel per bucket, in-kernel P2P)",
+                    "overlap": not args.no_overlap, "buckets": len(tr.ddp.flat), "bucket_mb": args.bucket_mb,
+                    "overlap_grid": args.overlap_grid, "input_kernel": "u8_to_nhwc_norm (own)"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "wire_bytes_per_step_per_rank": int(wire), "dense_bytes": int(dense),
         "relative_volume": wire / dense, "wall_ms_per_step": wall / args.steps,
     }
     out.update(extra)
     tr.close()
+    del tr, model
+    torch.cuda.empty_cache()
+    if args.config != "dense" and not args.no_dense_context:
+        out["dense_allreduce_context"] = measure_dense_context(args, kind, B, world, pool, tgt)
+        out["dense_allreduce_context"]["ours_over_dense"] = out["value"] / out["dense_allreduce_context"]["value"]
     return out
+
+
+class _RefNeuMF:
+    """Plain-torch NeuMF of the MovieLens-20M shapes for the REFERENCE arm (the reference's NCF trainer is the external
+    grace-benchmarks ``ncf_grace.py``; nothing of deepreduce_b200 may run on that path)."""
+
+    @staticmethod
+    def build():
+        import torch
+        import torch.nn as nn
+        import torch.nn.functional as F
+
+        class NeuMF(nn.Module):
+            def __init__(self, n_users=138493, n_items=26744, mf_dim=64, mlp_layers=(256, 256, 128, 64)):
+                super().__init__()
+                self.mf_user = nn.Embedding(n_users, mf_dim); self.mf_item = nn.Embedding(n_items, mf_dim)
+                self.mlp_user = nn.Embedding(n_users, mlp_layers[0] // 2); self.mlp_item = nn.Embedding(n_items, mlp_layers[0] // 2)
+                self.mlp = nn.ModuleList(nn.Linear(a, b) for a, b in zip(mlp_layers[:-1], mlp_layers[1:]))
+                self.out = nn.Linear(mf_dim + mlp_layers[-1], 1)
+                for e in (self.mf_user, self.mf_item, self.mlp_user, self.mlp_item):
+                    nn.init.normal_(e.weight, 0.0, 0.01)
+
+            def forward(self, user, item):
+                mf = self.mf_user(user) * self.mf_item(item)
+                x = torch.cat([self.mlp_user(user), self.mlp_item(item)], dim=1)
+                for l in self.mlp:
+                    x = F.relu(l(x))
+                return self.out(torch.cat([mf, x], dim=1)).squeeze(-1)
+        return NeuMF()
 
 
 def run_reference(args, rank, world, local):
     """UNMODIFIED reference pytorch/deepreduce.py through its documented API (README.md:36-48):
-    grace_from_params + IndexCompressor wrapper, grc.step(grad, name) per tensor after backward."""
+    grace_from_params + Value/Index/DeepReduce wrapper, grc.step(grad, name) per tensor after backward.  Same model
+    architecture, batch, dtype, optimizer, input pipeline (uint8 NHWC pinned -> H2D -> normalise -> bf16
+    channels_last, prefetched one step ahead) and step counts as the `ours` arm; nothing of deepreduce_b200 is
+    imported on this path."""
     import numpy as np
     import torch
     ref_file = os.path.join(ROOT, "baseline", "_ref", "deepreduce_ref", "deepreduce.py")
@@ -333,12 +443,24 @@ def run_reference(args, rank, world, local):
         np.RankWarning = np.exceptions.RankWarning        # numpy>=2 moved it; the reference reads np.RankWarning
     from deepreduce_ref import deepreduce as R
     from grace_dl.dist.helper import grace_from_params
-    import torchvision
 
     torch.manual_seed(1234)
     torch.backends.cudnn.benchmark = True
-    assert args.model == "resnet50"
-    model = torchvision.models.resnet50(weights=None).cuda().to(memory_format=torch.channels_last)
+    if args.model == "resnet50":
+        import torchvision
+        model, kind, default_b, unit = torchvision.models.resnet50(weights=None), "image224", 256, "images/s"
+    elif args.model == "bert_large":
+        from transformers import BertConfig, BertForMaskedLM
+        model = BertForMaskedLM(BertConfig(vocab_size=30522, hidden_size=1024, num_hidden_layers=24, num_attention_heads=16,
+                                           intermediate_size=4096, max_position_embeddings=max(args.seq, 128)))
+        kind, default_b, unit = "bert", 8, "sequences/s"
+    elif args.model == "ncf":
+        model, kind, default_b, unit = _RefNeuMF.build(), "ncf", 65536, "samples/s"
+    else:
+        return {"impl": "reference", "unavailable": f"no reference arm for model {args.model}"}
+    model = model.cuda()
+    if kind.startswith("image"):
+        model = model.to(memory_format=torch.channels_last)
     cfg = dict(CONFIGS[args.config])
     cfg["world_size"] = world
     grc = grace_from_params(cfg)
@@ -348,26 +470,36 @@ def run_reference(args, rank, world, local):
         cfg["hash_table"] = torch.randint(0, 2 ** 31 - 1, (d_max, 16), dtype=torch.int32, device="cuda", generator=g)
         wrapper = {'value': R.ValueCompressor, 'index': R.IndexCompressor, 'both': R.DeepReduce}[cfg["deepreduce"]]
         grc.compressor = wrapper(grc.compressor, cfg)
-    opt = torch.optim.SGD(model.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
-    B = args.batch or 256
+    opt = torch.optim.SGD(model.parameters(), lr=0.05 if kind != "bert" else 1e-4, momentum=0.9, weight_decay=1e-4, fused=True)
+    B = args.batch or default_b
     gen = torch.Generator().manual_seed(77 + rank)
-    host_x = [torch.randn(B, 3, 224, 224, generator=gen).pin_memory() for _ in range(2)]
-    host_y = [torch.randint(0, 1000, (B,), generator=gen).pin_memory() for _ in range(2)]
-    dev_x = [x.cuda().contiguous(memory_format=torch.channels_last) for x in host_x]
-    dev_y = [y.cuda() for y in host_y]
+    pool, tgt = synth_batches(kind, B, args.seq, gen)
     amp = args.dtype == "bf16"
     named = [(n, p) for n, p in model.named_parameters()]
+    loss_fn = loss_for(kind) or torch.nn.functional.cross_entropy
+    mean = torch.tensor(MEAN, device="cuda").view(1, 1, 1, 3)
+    inv_std = (1.0 / torch.tensor(STD, device="cuda")).view(1, 1, 1, 3)
 
-    def train(x, y):
+    def prep(xs):
+        if kind.startswith("image"):          # uint8 NHWC -> normalised bf16, NCHW view of the NHWC storage (= channels_last)
+            x = xs[0]
+            return (((x.float() * (1.0 / 255.0) - mean) * inv_std).to(torch.bfloat16).permute(0, 3, 1, 2),)
+        return xs
+
+    def train(xs, y):
         opt.zero_grad(set_to_none=True)
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
-            out = model(x)
-        loss = torch.nn.functional.cross_entropy(out.float(), y)
+            out = model(*prep(xs))
+        loss = loss_fn(out.float() if torch.is_tensor(out) else out, y)
         loss.backward()
         for n, p in named:
-            p.grad = grc.step(p.grad, n).view_as(p)
+            if p.grad is not None:
+                p.grad = grc.step(p.grad, n).view_as(p)
         opt.step()
         return loss
+
+    dev_x = [tuple(t.cuda() for t in p) for p in pool]
+    dev_y = [t.cuda() for t in tgt]
 
     def step(i):
         train(dev_x[i & 1], dev_y[i & 1])
@@ -382,23 +514,51 @@ def run_reference(args, rank, world, local):
     value = world * B * args.steps / (ms / 1e3)
     e2e = None
     if not args.no_e2e:
+        host_x = [tuple(t.pin_memory() for t in p) for p in pool]
+        host_y = [t.pin_memory() for t in tgt]
+        copy_stream = torch.cuda.Stream()
+        loss_host = torch.zeros(1).pin_memory()
+        staged = {}
+
+        def stage(i):
+            with torch.cuda.stream(copy_stream):
+                xs = tuple(t.cuda(non_blocking=True) for t in host_x[i & 1])
+                y = host_y[i & 1].cuda(non_blocking=True)
+                ev = torch.cuda.Event(); ev.record(copy_stream)
+            staged["cur"] = (xs, y, ev)
+
         def step_e2e(i):
-            x = host_x[i & 1].cuda(non_blocking=True).contiguous(memory_format=torch.channels_last)
-            y = host_y[i & 1].cuda(non_blocking=True)
-            float(train(x, y).item())
-        step_e2e(0)
-        n_e = max(2, min(args.steps, 5))
-        _, wall_e = timed(step_e2e, n_e, world)
-        e2e = {"value": world * B * n_e / (wall_e / 1e3), "unit": "images/s",
-               "h2d_bytes_per_step": int(host_x[0].numel() * 4 + host_y[0].numel() * 8), "d2h_bytes_per_step": 4}
+            if "cur" not in staged:
+                stage(i)
+            xs, y, ev = staged.pop("cur")
+            torch.cuda.current_stream().wait_event(ev)
+            stage(i + 1)                                   # prefetch the next batch while this step computes
+            loss = train(xs, y)
+            loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            for t in xs:
+                t.record_stream(torch.cuda.current_stream())
+            return float(loss_host[0])
+
+        for i in range(2):
+            step_e2e(i)
+        _, wall_e = timed(step_e2e, args.steps, world)
+        h2d = sum(t.numel() * t.element_size() for t in host_x[0]) + host_y[0].numel() * host_y[0].element_size()
+        e2e = {"value": world * B * args.steps / (wall_e / 1e3), "unit": unit,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4}
+    names = {"resnet50": "ResNet-50 images/sec (whole job, device-timed, max over ranks)",
+             "bert_large": "BERT-large sequences/sec (whole job, device-timed, max over ranks)",
+             "ncf": "NCF (MovieLens-20M shapes) samples/sec (whole job, device-timed, max over ranks)"}
+    pub_cfg = {k: v for k, v in CONFIGS[args.config].items()}
     return {
-        "metric": "ResNet-50 images/sec (whole job, device-timed, max over ranks)",
-        "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": names.get(args.model, f"{args.model} {unit}"),
+        "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": args.dtype, "data": "synthetic (fp32 224x224x3, random-init weights)", "impl": "reference",
-        "config": {"model": "resnet50 (torchvision)", "global_batch": B * world, "per_gpu_batch": B,
-                   "parallelism": f"dp{world}", "gradient_exchange": args.config, "params": {k: v for k, v in cfg.items() if isinstance(v, (str, int, float, bool, type(None)))},
-                   "harness": "unmodified reference pytorch/deepreduce.py + GRACE/cupy shims (baseline/), per-tensor grc.step after backward"},
+        "dtype": args.dtype, "data": "synthetic (shapes of the named benchmark, random-init weights)", "impl": "reference",
+        "config": bench_config(args, kind, B, world, pub_cfg),
+        "harness": {"model_impl": "torchvision / transformers / plain torch (bench.py)",
+                    "exchange": "unmodified reference pytorch/deepreduce.py + GRACE/cupy shims (baseline/), per-tensor grc.step after backward",
+                    "input_kernel": "torch ops"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": 0, "wall_ms_per_step": wall / args.steps,
     }
 
