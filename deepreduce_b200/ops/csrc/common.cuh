@@ -150,6 +150,19 @@ DR_D void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t* status = nullptr) 
   } while (!ok);
 }
 
+// ---- cp.async (LDGSTS): global -> shared copies tracked by commit groups, not by the register scoreboard.  A
+// software prefetch through registers dies at ~5 loads in flight per warp (6 scoreboard slots, counting semantics:
+// waiting for the oldest load also waits for every newer one sharing its slot — v12 profile of the candidate walks)
+DR_D void cp_async_8(void* dst_smem, const void* src_gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+DR_D void cp_async_4(void* dst_smem, const void* src_gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+DR_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+DR_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
 // NVLS: a store to a multicast address is replicated by the NVSwitch into every bound GPU's memory
 DR_D void multimem_st_v4(uint4* mc_addr, uint4 v) {
   asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1,%2,%3,%4};"

@@ -50,8 +50,9 @@ constexpr uint32_t kChunk = 256;                      // candidate capacity per 
 constexpr uint32_t kHalf = kTile / 2;                 // elements per ring stage (g half-tile | r half-tile)
 constexpr uint32_t kStageBytes = 2u * kHalf * 4u;     // 16 KB
 constexpr uint32_t kMaxStages = 6;
-constexpr int kPF = 6;                                // candidate-list walks: tiles of lookahead (register prefetch)
+constexpr int kPF = 8;                                // candidate-list walks: chunk heads in flight per warp (cp.async ring)
 constexpr uint32_t kUnsafeWord = 8;                   // P.barrier[8]: tensors whose history bound hid the threshold
+constexpr uint32_t kNeedHist2Word = 9;                // P.barrier[9]: tensors whose digit 2 could not be taken speculatively
 
 struct ScanSmem {
   uint32_t warp_tot[kWarps];
@@ -62,7 +63,7 @@ struct ScanSmem {
 
 struct Smem {
   union {
-    uint32_t hist[kHistBins];                 // radix-select digit histogram
+    uint32_t hist[2 * kHistBins];             // radix-select digit histogram | speculative digit-2 histogram (accumulate phase)
     float acc[kTile];                         // raw / rle decode accumulator
     uint32_t q[kWarps][64];                   // probe passes: per-warp survivor ring
     uint32_t excl[kTile];                     // emit: exclusive prefixes of a chunk of tiles
@@ -261,24 +262,78 @@ DR_D void write_final(const EngineParams& P, Smem& sm, uint32_t t, uint32_t bin1
   }
 }
 
+// Digit 1 AND (speculatively) digit 2 of a multi-tile tensor at the end of the accumulate phase.  Every CTA also
+// binned digit 2 of its candidates under the guess that the threshold bin is last step's (`guess`).  The CTA that
+// completes the tensor resolves digit 1; if the guess was right it resolves digit 2 on the spot and the tensor needs
+// no digit-2 phase at all (no pass over the candidates, no grid barrier) — otherwise it discards the speculative
+// counts and the tensor is counted in P.barrier[kNeedHist2Word], which switches the digit-2 phase on for this step.
+DR_D void finish_spec(const EngineParams& P, Smem& sm, uint32_t t, uint32_t n_mine, uint32_t n_tiles, uint32_t k,
+                      uint32_t guess) {
+  const uint32_t tid = threadIdx.x;
+  uint32_t* gh1 = hist_ptr(P, 0, t);
+  uint32_t* gh2 = hist_ptr(P, 2, t);
+  const bool whole = (n_mine == n_tiles);                 // this CTA saw every tile: resolve from shared memory
+  bool last = whole;
+  if (!whole) {
+    __syncthreads();
+    for (int j = tid; j < 2 * kHistBins; j += kThreads) {
+      const uint32_t v = sm.u.hist[j];
+      if (v) { atomicAdd((j < kHistBins ? gh1 : gh2 - kHistBins) + j, v); sm.u.hist[j] = 0; }
+    }
+    __threadfence();                                      // merged counts are visible before the ticket is taken
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      const uint32_t before = atomicAdd(P.hist_total + t, n_mine);
+      sm.s.lb = (before + n_mine == n_tiles) ? 1u : 0u;
+      __threadfence();
+    }
+    __syncthreads();
+    last = sm.s.lb != 0u;
+    __syncthreads();
+  }
+  if (!last) return;
+  if (whole) resolve_bins([&](int b) { return sm.u.hist[b]; }, kHistBins, k, sm.s);
+  else resolve_bins([&](int b) { return __ldcg(gh1 + b); }, kHistBins, k, sm.s);
+  const uint32_t bin1 = sm.s.res[0], krem1 = sm.s.res[1];
+  write_digit1(P, sm, t);
+  if (bin1 != kUnsafe && bin1 == guess) {
+    if (whole) resolve_bins([&](int b) { return sm.u.hist[kHistBins + b]; }, kHistBins, krem1, sm.s);
+    else resolve_bins([&](int b) { return __ldcg(gh2 + b); }, kHistBins, krem1, sm.s);
+    write_final(P, sm, t, bin1);
+    if (tid == 0) P.sel[t].done_epoch = P.epoch;
+  } else {
+    if (!whole) for (int j = tid; j < kHistBins; j += kThreads) gh2[j] = 0u;     // the digit-2 phase starts from zero
+    if (tid == 0) atomicAdd(P.barrier + kNeedHist2Word, 1u);
+  }
+  if (whole) {
+    __syncthreads();
+    for (int j = tid; j < 2 * kHistBins; j += kThreads) sm.u.hist[j] = 0;
+    __syncthreads();
+  }
+}
+
 // Append this thread's flagged elements (bit j of m: element e0 + j, key key[j]) to the warp's candidate chunk.
-// `cnt` (warp-uniform) is the number of entries already in the chunk.
+// `cnt` (warp-uniform) is the number of entries already in the chunk.  One ballot per element slot gives every
+// flagged lane its position (popcount of the lower lanes) — no shuffle scan, no per-element branches with their own
+// reconvergence points (v11/v12: 155 of the ~260 instructions of a half-tile iteration).
 DR_D void append_candidates(Smem& sm, uint32_t m, const uint32_t (&key)[4], uint32_t e0, uint2* chunk, uint32_t& cnt,
-                            bool do_hist, uint32_t lane) {
-  const uint32_t c = __popc(m);
-  const uint32_t incl = warp_incl_scan(c, lane);
-  const uint32_t tot = __shfl_sync(kFullMask, incl, 31);
-  if (tot == 0u) return;
-  uint2* dst = chunk + (cnt + incl - c);
+                            bool do_hist, uint32_t lane, uint32_t guess = 0xFFFFFFFFu) {
+  const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    if ((m >> j) & 1u) {
-      const uint32_t k = key[j];
-      if (do_hist) atomicAdd(&sm.u.hist[k >> 20], 1u);
-      *dst++ = make_uint2(k, e0 + (uint32_t)j);
+    const bool f = ((m >> j) & 1u) != 0u;
+    const uint32_t b = __ballot_sync(kFullMask, f);
+    if (f) {
+      chunk[cnt + (uint32_t)__popc(b & lt)] = make_uint2(key[j], e0 + (uint32_t)j);
+      if (do_hist) {
+        atomicAdd(&sm.u.hist[key[j] >> 20], 1u);
+        // speculative digit 2: last step's threshold bin is almost always this step's (see finish_spec)
+        if ((key[j] >> 20) == guess) atomicAdd(&sm.u.hist[kHistBins + ((key[j] >> 9) & 0x7FFu)], 1u);
+      }
     }
+    cnt += (uint32_t)__popc(b);
   }
-  cnt += tot;
 }
 
 DR_D uint32_t round16(uint32_t bytes) { return (bytes + 15u) & ~15u; }
@@ -294,7 +349,11 @@ DR_D void phase_accum(const EngineParams& P, Smem& sm) {
     for (uint32_t i = blockIdx.x * kThreads + tid; i < n4; i += gridDim.x * kThreads) p[i] = z;
   }
   if (sharded(P) && blockIdx.x == 0 && tid == 0) *s2_ptr(P.arena[P.rank], P, parity_slot, P.rank) = 0u;
-  clear_hist(sm);
+  // per-tile counts are accumulated by the insert (raw / rle) and query (bloom) phases of this step
+  for (uint32_t i = blockIdx.x * kThreads + tid; i < P.n_tiles; i += gridDim.x * kThreads) P.tile_count[i] = 0u;
+  __syncthreads();
+  for (int j = tid; j < 2 * kHistBins; j += kThreads) sm.u.hist[j] = 0;
+  __syncthreads();
   const bool has_resid = (P.beta != 0.0f);
   uint32_t t0, t_end;
   tile_range(P, t0, t_end);
@@ -355,11 +414,16 @@ DR_D void phase_accum(const EngineParams& P, Smem& sm) {
     }
     const bool do_hist = (fixed == 0u);
     const bool single = ti.single != 0u;
+    // last step's threshold bin: the guess under which digit 2 is binned speculatively (one-tile tensors finish both
+    // digits from registers below and need no guess)
+    const uint32_t guess = (do_hist && !single) ? __ldcg(&P.sel[cur].bin1) : 0xFFFFFFFFu;
     uint32_t n_mine = 0;
     uint32_t keys[8];
     while (true) {                                                         // tiles of this tensor inside my range
       uint32_t cnt = 0;
       uint2* chunk = P.cand + chunk_of(tile, warp);
+      float* r_t = P.resid + ti.base + tid * 4u;                           // this thread's 4 elements of half 0
+      float* g_t = P.grad + ti.base + tid * 4u;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const uint32_t off = (uint32_t)h * kHalf;
@@ -387,8 +451,8 @@ DR_D void phase_accum(const EngineParams& P, Smem& sm) {
             } else {
               a.x = gamma * g.x; a.y = gamma * g.y; a.z = gamma * g.z; a.w = gamma * g.w;
             }
-            *reinterpret_cast<float4*>(P.resid + ti.base + e0) = a;
-            *reinterpret_cast<float4*>(P.grad + ti.base + e0) = zero4;    // the dense output starts from zero
+            *reinterpret_cast<float4*>(r_t + off) = a;
+            *reinterpret_cast<float4*>(g_t + off) = zero4;                // the dense output starts from zero
             const uint32_t kv[4] = {__float_as_uint(a.x) & 0x7FFFFFFFu, __float_as_uint(a.y) & 0x7FFFFFFFu,
                                     __float_as_uint(a.z) & 0x7FFFFFFFu, __float_as_uint(a.w) & 0x7FFFFFFFu};
             if (whole) {
@@ -405,7 +469,7 @@ DR_D void phase_accum(const EngineParams& P, Smem& sm) {
           if (lane == 0) mbar_arrive(&empty[stage]);                       // this warp is done with the stage
           prev_stage = stage; prev_par = par; first_item = false;
           if (++stage == n_stages) { stage = 0; par ^= 1u; }
-          append_candidates(sm, m, key4, e0, chunk, cnt, do_hist, lane);
+          append_candidates(sm, m, key4, e0, chunk, cnt, do_hist, lane, guess);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) keys[h * 4 + j] = key4[j];
@@ -442,8 +506,7 @@ DR_D void phase_accum(const EngineParams& P, Smem& sm) {
         clear_hist(sm);
       }
     } else {
-      const uint32_t k = __ldg(&tdp->k), nt = __ldg(&tdp->n_tiles);
-      if (finish_digit(P, sm, 0, cur, n_mine, nt, k)) write_digit1(P, sm, cur);
+      finish_spec(P, sm, cur, n_mine, __ldg(&tdp->n_tiles), __ldg(&tdp->k), guess);
     }
   }
 }
@@ -533,16 +596,34 @@ DR_D uint32_t rle_get(const uint32_t* stream, uint32_t j) {
   return v & 0xFFFu;
 }
 
-// the emit phase ORs fields into the stream: clear it first (any phase before emit; runs with the digit-2 pass)
-DR_D void rle_zero_streams(const EngineParams& P) {
-  uint32_t* my_slot = slot_ptr(P.arena[P.rank], P, P.epoch & 1u, P.rank);
-  for (uint32_t t = 0; t < P.n_tensors; ++t) {
-    const TensorDesc* td = P.tensors + t;
-    if (__ldg(&td->mode) != (uint32_t)kModeRle) continue;
-    const uint32_t n = rle_stream_words(__ldg(&td->val_cap));
-    uint32_t* dst = my_slot + __ldg(&td->off_idx);
-    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) dst[i] = 0u;
+// ===========================================================================
+// Walk of a warp's candidate chunks (one per tile) with the heads of the next kPF chunks in flight: cp.async copies
+// the first 32 entries (256 B) and the count of chunk tile+kPF into a warp-private SMEM ring while chunk `tile` is
+// processed.  The lists were written a phase ago and sit in DRAM; every chunk head is a separate 256-byte request,
+// so the walk lives on memory-level parallelism.
+// ===========================================================================
+struct CandWalk {
+  uint2* ent;          // [kPF][32] this warp's ring
+  uint32_t* cnt;       // [kPF]
+  uint32_t lane, warp;
+};
+
+DR_D CandWalk cand_walk_init() {
+  CandWalk w;
+  w.lane = threadIdx.x & 31u; w.warp = threadIdx.x >> 5;
+  uint8_t* base = reinterpret_cast<uint8_t*>(g_filter_smem);
+  w.ent = reinterpret_cast<uint2*>(base) + (size_t)w.warp * kPF * 32;
+  w.cnt = reinterpret_cast<uint32_t*>(base + (size_t)kWarps * kPF * 32 * sizeof(uint2)) + w.warp * kPF;
+  return w;
+}
+
+// issue the copy of chunk `tile`'s head into ring slot `slot` (or an empty group past the end: group counting stays uniform)
+DR_D void cand_walk_issue(const EngineParams& P, const CandWalk& w, uint32_t tile, uint32_t t_end, uint32_t slot) {
+  if (tile < t_end) {
+    cp_async_8(w.ent + slot * 32u + w.lane, P.cand + chunk_of(tile, w.warp) + w.lane);
+    if (w.lane == 0) cp_async_4(w.cnt + slot, P.cand_cnt + tile * kWarps + w.warp);
   }
+  cp_async_commit();
 }
 
 // ===========================================================================
@@ -550,9 +631,8 @@ DR_D void rle_zero_streams(const EngineParams& P) {
 // ===========================================================================
 DR_D void phase_hist2(const EngineParams& P, Smem& sm) {
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  // per-tile counts are accumulated by the insert (raw / rle) and query (bloom) phases of this step
-  for (uint32_t i = blockIdx.x * kThreads + tid; i < P.n_tiles; i += gridDim.x * kThreads) P.tile_count[i] = 0u;
   clear_hist(sm);
+  const CandWalk cw = cand_walk_init();
   uint32_t tile, t_end;
   tile_range(P, tile, t_end);
   while (tile < t_end) {
@@ -564,38 +644,27 @@ DR_D void phase_hist2(const EngineParams& P, Smem& sm) {
     if (__ldcg(&P.sel[cur].done_epoch) == P.epoch) { tile = seg_end; continue; }     // one-tile / fixed-threshold tensors
     const uint32_t prefix = __ldcg(&P.sel[cur].bin1), k_cur = __ldcg(&P.sel[cur].krem1);
     if (prefix == kUnsafe && tid == 0) atomicExch(P.status, kErrResolve);
-    // software pipeline: count + first 32 entries of the next kPF tiles are in flight while a tile is binned (the
-    // lists were written a phase ago and come from DRAM: with one tile of lookahead the walk was one DRAM latency
-    // per tile, v11 profile)
-    uint2 en[kPF];
-    uint32_t cn[kPF];
+    __syncwarp();
 #pragma unroll
-    for (int p = 0; p < kPF; ++p) {
-      const uint32_t tl = tile + (uint32_t)p;
-      cn[p] = 0; en[p] = make_uint2(0, 0);
-      if (tl < seg_end) { cn[p] = __ldcg(P.cand_cnt + tl * kWarps + warp); en[p] = __ldcg(P.cand + chunk_of(tl, warp) + lane); }
-    }
-    for (uint32_t base = tile; base < seg_end; base += kPF) {
-#pragma unroll
-      for (int p = 0; p < kPF; ++p) {
-        const uint32_t tl = base + (uint32_t)p;
-        if (tl < seg_end) {
-          const uint32_t c = cn[p], ka = en[p].x;
-          if (tl + kPF < seg_end) {
-            cn[p] = __ldcg(P.cand_cnt + (tl + kPF) * kWarps + warp);
-            en[p] = __ldcg(P.cand + chunk_of(tl + kPF, warp) + lane);
-          }
-          if (lane < c && (ka >> 20) == prefix) atomicAdd(&sm.u.hist[(ka >> 9) & 0x7FFu], 1u);
-          if (c > 32u) {
-            const uint2* chunk = P.cand + chunk_of(tl, warp);
-            for (uint32_t j = 32u + lane; j < c; j += 32u) {
-              const uint32_t k = __ldcg(chunk + j).x;
-              if ((k >> 20) == prefix) atomicAdd(&sm.u.hist[(k >> 9) & 0x7FFu], 1u);
-            }
-          }
+    for (int p = 0; p < kPF; ++p) cand_walk_issue(P, cw, tile + (uint32_t)p, seg_end, (uint32_t)p);
+    for (uint32_t tl = tile, i = 0; tl < seg_end; ++tl, ++i) {
+      const uint32_t slot = i & (kPF - 1);
+      cp_async_wait<kPF - 1>();                                            // the oldest group (chunk tl) has landed
+      __syncwarp();
+      const uint32_t c = cw.cnt[slot];
+      const uint32_t ka = cw.ent[slot * 32u + lane].x;
+      __syncwarp();                                                        // everyone has read the slot: refill it
+      cand_walk_issue(P, cw, tl + kPF, seg_end, slot);
+      if (lane < c && (ka >> 20) == prefix) atomicAdd(&sm.u.hist[(ka >> 9) & 0x7FFu], 1u);
+      if (c > 32u) {
+        const uint2* chunk = P.cand + chunk_of(tl, warp);
+        for (uint32_t j = 32u + lane; j < c; j += 32u) {
+          const uint32_t k = __ldcg(chunk + j).x;
+          if ((k >> 20) == prefix) atomicAdd(&sm.u.hist[(k >> 9) & 0x7FFu], 1u);
         }
       }
     }
+    cp_async_wait<0>();
     if (finish_digit(P, sm, 2, cur, seg_end - tile, nt, k_cur)) write_final(P, sm, cur, prefix);
     tile = seg_end;
   }
@@ -655,43 +724,34 @@ DR_D void phase_insert(const EngineParams& P, Smem& sm) {
     recip = n_hash > 1u ? (0xFFFFFFFFu / n_hash) + 1u : 0u;
     thr = __ldcg(&P.sel[cur].thr);
   };
-  uint2 en[kPF];
-  uint32_t cn[kPF];
+  const CandWalk cw = cand_walk_init();
 #pragma unroll
-  for (int p = 0; p < kPF; ++p) {
-    const uint32_t tl = tile + (uint32_t)p;
-    cn[p] = 0; en[p] = make_uint2(0, 0);
-    if (tl < t_end) { cn[p] = __ldcg(P.cand_cnt + tl * kWarps + warp); en[p] = __ldcg(P.cand + chunk_of(tl, warp) + lane); }
-  }
-  for (uint32_t base = tile; base < t_end; base += kPF) {
-#pragma unroll
-    for (int p = 0; p < kPF; ++p) {
-      const uint32_t tl = base + (uint32_t)p;
-      if (tl < t_end) {
-        const Tile ti = load_tile(P, tl);
-        const uint32_t c = cn[p];
-        const uint2 ea = en[p];
-        if (tl + kPF < t_end) {
-          cn[p] = __ldcg(P.cand_cnt + (tl + kPF) * kWarps + warp);
-          en[p] = __ldcg(P.cand + chunk_of(tl + kPF, warp) + lane);
+  for (int p = 0; p < kPF; ++p) cand_walk_issue(P, cw, tile + (uint32_t)p, t_end, (uint32_t)p);
+  for (uint32_t tl = tile, i = 0; tl < t_end; ++tl, ++i) {
+    const uint32_t slot = i & (kPF - 1);
+    const Tile ti = load_tile(P, tl);
+    cp_async_wait<kPF - 1>();                                              // the oldest group (chunk tl) has landed
+    __syncwarp();
+    const uint32_t c = cw.cnt[slot];
+    const uint2 ea = cw.ent[slot * 32u + lane];
+    __syncwarp();                                                          // everyone has read the slot: refill it
+    cand_walk_issue(P, cw, tl + kPF, t_end, slot);
+    if (ti.tensor != cur) tensor_params(ti.tensor);
+    uint32_t n_sel_tile = 0;
+    if (c) {                                                               // warp-uniform
+      process(tl, ti.local0, lane < c, ea.x, ea.y, n_sel_tile);
+      if (c > 32u) {
+        const uint2* chunk = P.cand + chunk_of(tl, warp);
+        for (uint32_t j0 = 32u; j0 < c; j0 += 32u) {
+          const bool have = j0 + lane < c;
+          const uint2 eb = have ? __ldcg(chunk + j0 + lane) : make_uint2(0, 0);
+          process(tl, ti.local0, have, eb.x, eb.y, n_sel_tile);
         }
-        if (ti.tensor != cur) tensor_params(ti.tensor);
-        uint32_t n_sel_tile = 0;
-        if (c) {                                                           // warp-uniform
-          process(tl, ti.local0, lane < c, ea.x, ea.y, n_sel_tile);
-          if (c > 32u) {
-            const uint2* chunk = P.cand + chunk_of(tl, warp);
-            for (uint32_t j0 = 32u; j0 < c; j0 += 32u) {
-              const bool have = j0 + lane < c;
-              const uint2 eb = have ? __ldcg(chunk + j0 + lane) : make_uint2(0, 0);
-              process(tl, ti.local0, have, eb.x, eb.y, n_sel_tile);
-            }
-          }
-        }
-        if (mode != (uint32_t)kModeBloom && lane == 0 && n_sel_tile) atomicAdd(P.tile_count + tl, n_sel_tile);
       }
     }
+    if (mode != (uint32_t)kModeBloom && lane == 0 && n_sel_tile) atomicAdd(P.tile_count + tl, n_sel_tile);
   }
+  cp_async_wait<0>();
 }
 
 // ===========================================================================
@@ -813,7 +873,7 @@ DR_D void phase_query(const EngineParams& P, Smem& sm) {
     for (size_t i = (size_t)blockIdx.x * kThreads + tid; i < n4; i += (size_t)gridDim.x * kThreads) h[i] = z;
     for (uint32_t i = blockIdx.x * kThreads + tid; i < (uint32_t)kNumHist * P.n_tensors; i += gridDim.x * kThreads)
       P.hist_total[i] = 0u;
-    if (blockIdx.x == 0 && tid == 0) P.barrier[kUnsafeWord] = 0u;
+    if (blockIdx.x == 0 && tid == 0) { P.barrier[kUnsafeWord] = 0u; P.barrier[kNeedHist2Word] = 0u; }
   }
   const uint32_t parity = P.epoch & 1u;
   uint32_t* my_slot = slot_ptr(P.arena[P.rank], P, parity, P.rank);
@@ -1665,8 +1725,9 @@ DR_D void phase_scatter(const EngineParams& P) {
 template <bool kFull>
 DR_D bool phase_active(const EngineParams& P, int ph) {
   switch (ph) {
-    case kPhAccum: case kPhHist2: case kPhInsert: case kPhQuery: case kPhEmit: return true;
+    case kPhAccum: case kPhInsert: case kPhQuery: case kPhEmit: return true;
     case kPhFallback: return __ldcg(P.barrier + kUnsafeWord) != 0u;
+    case kPhHist2: return __ldcg(P.barrier + kNeedHist2Word) != 0u;
     case kPhRankHist: case kPhRankScan: case kPhRankScatter: case kPhRankExact: case kPhFit: case kPhExpand:
       return kFull && P.n_poly != 0u;
     case kPhFix: return kFull && P.n_poly_tasks != 0u;
@@ -1702,10 +1763,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) dr_engine_kernel(const _
     switch (ph) {
       case kPhAccum: phase_accum(P, sm); break;
       case kPhFallback: phase_fallback(P, sm); break;
-      case kPhHist2:
-        if (kFull && P.has_rle) rle_zero_streams(P);
-        phase_hist2(P, sm);
-        break;
+      case kPhHist2: phase_hist2(P, sm); break;
       case kPhInsert: phase_insert(P, sm); break;
       case kPhQuery: phase_query(P, sm); break;
       case kPhEmit: phase_emit<kFull>(P, sm); break;
@@ -1770,7 +1828,7 @@ int engine_max_grid(int blocks_per_sm, int dyn_smem_bytes) {
 
 cudaError_t engine_launch(const EngineParams& P, int grid, int blocks_per_sm, int dyn_smem_bytes, cudaStream_t stream) {
   ensure_attr();
-  if (dyn_smem_bytes < 2 * (int)kStageBytes) return cudaErrorInvalidValue;     // the TMA ring needs two stages
+  if (dyn_smem_bytes < 40 * 1024) return cudaErrorInvalidValue;     // TMA ring (>= 2 stages), candidate rings, emit lists
   cudaError_t e = cudaMemsetAsync(P.barrier, 0, 4 * sizeof(uint32_t), stream);  // grid barrier + the two tickets
   if (e != cudaSuccess) return e;
   void* args[] = {const_cast<EngineParams*>(&P)};

@@ -23,9 +23,14 @@ def main():
     hint = bool(int(sys.argv[5])) if len(sys.argv) > 5 else True
     value = (sys.argv[6] if len(sys.argv) > 6 else 'none')
     value = None if value == 'none' else value
-    m = resnet50()
-    named = list(reversed([(n, p) for n, p in m.named_parameters()]))
-    plan = BucketPlan([p.numel() for _, p in named], [n for n, _ in named], compress_ratio=0.01, hint=hint, value=value)
+    shape = sys.argv[7] if len(sys.argv) > 7 else 'resnet50'
+    if shape == 'resnet50':
+        m = resnet50()
+        named = list(reversed([(n, p) for n, p in m.named_parameters()]))
+        plan = BucketPlan([p.numel() for _, p in named], [n for n, _ in named], compress_ratio=0.01, hint=hint, value=value)
+    else:            # 'uniformN': N equal tensors with ResNet-50's total size (isolates the per-tensor overheads)
+        n = int(shape.replace('uniform', ''))
+        plan = BucketPlan([25557032 // n] * n, compress_ratio=0.01, hint=hint, value=value)
     eng = BucketEngine(plan, device="cuda:0", world=1, rank=0, blocks_per_sm=bps, use_tma=use_tma, hist_shift=hist_shift)
     gen = torch.Generator(device="cuda").manual_seed(0)
     grads = [torch.randn(plan.total_elems, device="cuda", generator=gen) * 0.01 for _ in range(4)]
@@ -72,7 +77,7 @@ def main():
     # algorithmic HBM bytes: read g + read r + write r (accum), write dense out (decode); other passes re-read r (L2/HBM)
     min_bytes = 4 * d
     med = fused[len(fused) // 2]
-    out = {"kernel": "dr_engine_kernel (fused, W=1)", "model": "resnet50 grads", "dense_bytes": d,
+    out = {"kernel": "dr_engine_kernel (fused, W=1)", "model": f"{shape} grads", "dense_bytes": d,
            "wire_bytes": plan.wire_bytes(), "grid": eng.grid(), "blocks_per_sm": bps, "use_tma": use_tma, "hist_shift": hist_shift, "hint": hint, "value": value,
            "fused_ms_median": med, "fused_ms_min": fused[0],
            "phase_ms_unfused": dict(zip(PHASES, [round(x, 4) for x in per])),

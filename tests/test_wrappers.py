@@ -217,13 +217,19 @@ def test_fused_path_gating():
            {**base, 'deepreduce': 'index', 'index': 'bloom', 'policy': 'p0'},
            {**base, 'deepreduce': 'index', 'index': 'rle'},
            {**base, 'deepreduce': 'both', 'index': 'bloom', 'value': 'polyfit'},
-           {**base, 'deepreduce': 'both', 'index': 'bloom', 'value': 'qsgd', 'quantum_num': 127, 'bucket_size': 512}]
-    no = [{**base, 'compressor': 'threshold'}, {**base, 'compressor': 'randomk'},
+           {**base, 'deepreduce': 'both', 'index': 'bloom', 'value': 'qsgd', 'quantum_num': 127, 'bucket_size': 512},
+           # the reference's NCF recipes (run_deepreduce.sh:66-74): threshold sparsifier, value-only mode, int16 QSGD
+           {'compressor': 'threshold', 'memory': 'none', 'communicator': 'allgather', 'threshold': 0.0},
+           {'compressor': 'threshold', 'memory': 'none', 'communicator': 'allgather', 'threshold': 0.0,
+            'deepreduce': 'index', 'index': 'bloom', 'policy': 'p0', 'fpr': 0.01},
+           {**base, 'deepreduce': 'value', 'value': 'polyfit'}, {**base, 'deepreduce': 'value', 'value': 'qsgd', 'quantum_num': 32},
+           {**base, 'deepreduce': 'both', 'index': 'bloom', 'value': 'qsgd', 'quantum_num': 255}]
+    no = [{**base, 'compressor': 'randomk'},
           {**base, 'deepreduce': 'index', 'index': 'bloom', 'policy': 'random'},
           {**base, 'deepreduce': 'index', 'index': 'bloom', 'policy': 'conflict_sets'},
           {**base, 'deepreduce': 'index', 'index': 'huffman'}, {**base, 'deepreduce': 'index', 'index': 'integer'},
-          {**base, 'deepreduce': 'value', 'value': 'polyfit'}, {**base, 'deepreduce': 'both', 'index': 'rle', 'value': 'polyfit'},
-          {**base, 'deepreduce': 'both', 'index': 'bloom', 'value': 'qsgd', 'quantum_num': 255},
+          {**base, 'deepreduce': 'both', 'index': 'rle', 'value': 'polyfit'},
+          {**base, 'deepreduce': 'both', 'index': 'bloom', 'value': 'qsgd', 'bucket_size': 256},
           {**base, 'deepreduce': 'both', 'index': 'bloom', 'value': 'gzip'},
           {'compressor': 'none', 'memory': 'none', 'communicator': 'allreduce'}]
     for p in yes:
