@@ -452,7 +452,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("arena_import", &arena_import);
   m.def("arena_close", [](int64_t p) { dr::arena_close((void*)p); });
   m.def("arena_as_tensor", &arena_as_tensor);
-  m.def("enable_peer_access", [](int n) { return dr::arena_enable_peer_access(n); });
+  m.def("enable_peer_access", [](std::vector<int> devices) { return dr::arena_enable_peer_access(devices.data(), (int)devices.size()); });
   m.attr("TILE") = dr::kTile;
   m.attr("ARENA_HDR_WORDS") = dr::kArenaHdrWords;
   m.attr("SLOT_HEADER_WORDS") = dr::kSlotHeaderWords;

@@ -159,6 +159,9 @@ DR_D void cp_async_8(void* dst_smem, const void* src_gmem) {
 DR_D void cp_async_4(void* dst_smem, const void* src_gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
 }
+DR_D void cp_async_16(void* dst_smem, const void* src_gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
 DR_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 DR_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }

@@ -47,7 +47,7 @@ void arena_free(void* p);
 ArenaHandle arena_export(void* p);
 void* arena_import(const ArenaHandle& h);              // cudaIpcOpenMemHandle
 void arena_close(void* p);
-int arena_enable_peer_access(int world_local);         // returns #peers enabled
+int arena_enable_peer_access(const int* devices, int n);   // peers = the listed devices only; returns #enabled
 void launch_u8_to_nhwc_norm(const uint8_t* in, void* out_bf16, int64_t n_pix, const float* mean, const float* inv_std,
                             cudaStream_t st);
 

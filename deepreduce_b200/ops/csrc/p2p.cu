@@ -51,11 +51,14 @@ void* arena_import(const ArenaHandle& h) {
 
 void arena_close(void* p) { if (p) cudaIpcCloseMemHandle(p); }
 
-int arena_enable_peer_access(int world_local) {
-  int dev = 0, n = 0, enabled = 0;
+// Enable peer access from the current device to exactly the listed devices (the GPUs of the ranks of this
+// communication group) — never to every GPU of the box: mapping devices outside the job showed up as activity on
+// GPUs the job does not own (round-1 SCALE records).
+int arena_enable_peer_access(const int* devices, int n) {
+  int dev = 0, enabled = 0;
   cudaGetDevice(&dev);
-  cudaGetDeviceCount(&n);
-  for (int p = 0; p < n && p < world_local; ++p) {
+  for (int i = 0; i < n; ++i) {
+    const int p = devices[i];
     if (p == dev) continue;
     int can = 0;
     cudaDeviceCanAccessPeer(&can, dev, p);

@@ -417,7 +417,10 @@ class BucketEngine:
             return
         if os.environ.get("DR_NVLS", "0") == "1" and self._setup_arena_nvls(words):
             return
-        self.mod.enable_peer_access(torch.cuda.device_count())
+        # peer-map only the GPUs of this group's ranks (never every device of the box)
+        devs = [None] * self.world
+        dist.all_gather_object(devs, int(self.device.index or 0), group=self.group)
+        self.mod.enable_peer_access([int(d) for d in devs])
         self._arena_ptr = self.mod.arena_alloc(words * 4)
         self.arena = self.mod.arena_as_tensor(self._arena_ptr, words, self.device.index or 0)
         handle = self.mod.arena_export(self._arena_ptr)

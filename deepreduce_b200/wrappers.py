@@ -88,6 +88,29 @@ class _Wrapper(Compressor):
         self.params = dict(params or {})
         self.min_numel = int(self.params.get('min_numel', spec.SMALL_TENSOR_NUMEL))
         self.bench = bool(self.params.get('micro-benchmark', False))
+        # seeded index-selection policies ('random' / 'conflict_sets'): the seed is a function of (step, tensor) — the
+        # C++ reference seeds with the training step (tensorflow/policies.hpp:171), the PyTorch one reseeds the GLOBAL
+        # torch RNG with 42 on every call (pytorch/deepreduce.py:487).  Every rank compresses the same tensor the same
+        # number of times, so the per-name step counters agree; decompress() runs right after compress() of the same
+        # tensor (GRACE Communicator.step), so it uses the seed of the latest compress.  An explicit
+        # params['policy_seed'] pins the seed instead.
+        self._steps: dict = {}
+        self._call_seed = int(self.params.get('policy_seed', 42))
+
+    def _begin_call(self, name) -> dict:
+        call = dict(self.params)
+        if 'policy_seed' not in self.params:
+            step = self._steps.get(name, 0)
+            self._steps[name] = step + 1
+            tid = sum(str(name).encode()) if name is not None else 0
+            self._call_seed = spec.policy_seed(step, tid)
+        call['policy_seed'] = self._call_seed
+        return call
+
+    def _decode_params(self) -> dict:
+        call = dict(self.params)
+        call['policy_seed'] = self._call_seed
+        return call
 
 
 class ValueCompressor(_Wrapper):
@@ -133,7 +156,7 @@ class IndexCompressor(_Wrapper):
         vals, idxs = tensors
         shape = ctx
         if shape.numel() > self.min_numel:
-            call = dict(self.params)
+            call = self._begin_call(name)
             call['dense_tensor'] = tensor     # FP-aware fill (reference :117) without mutating user params
             with _Timer(self.bench, 'idx_compression', tensor.device):
                 vals, idxs, shape = self.idx_compressor.compress((vals, idxs, tensor.size()), call)
@@ -147,7 +170,7 @@ class IndexCompressor(_Wrapper):
         vals, idxs = tensors
         if shape.numel() > self.min_numel:
             with _Timer(self.bench, 'idx_decompression', vals.device):
-                vals, idxs, shape = self.idx_compressor.decompress((vals, idxs, shape), self.params)
+                vals, idxs, shape = self.idx_compressor.decompress((vals, idxs, shape), self._decode_params())
             _report_volume(self.params, tensors, shape)
         else:
             idxs = _host_idx(idxs)
@@ -182,7 +205,7 @@ class DeepReduce(_Wrapper):
         shape = ctx
         with _Timer(self.bench, '_compression', tensor.device):
             if shape.numel() > self.min_numel:
-                call = dict(self.params)
+                call = self._begin_call(name)
                 call['dense_tensor'] = tensor
                 vals, idxs_c, _ = self.idx_compressor.compress((vals, idxs, tensor.size()), call)
                 head = None
@@ -233,7 +256,7 @@ class DeepReduce(_Wrapper):
                     vals, mapping, _ = self.val_compressor.decompress((vals_c, mapping, shape), self.params)
                 carrier = vals.new_zeros(mapping.numel()) if head is None else torch.cat(
                     [head.to(vals.dtype), vals.new_zeros(mapping.numel())])
-                _, idxs, _ = self.idx_compressor.decompress((carrier, idxs_c, shape), self.params)
+                _, idxs, _ = self.idx_compressor.decompress((carrier, idxs_c, shape), self._decode_params())
                 if self.val_compressor.order_preserving:
                     pass                               # i-th value belongs to the i-th decoded index
                 else:
