@@ -25,9 +25,18 @@ def _cumtrapz(y, dx):
     return torch.cat([y.new_zeros(1), torch.cumsum(inc, dim=0)])
 
 
+def double_exponential_fit_oracle(y: torch.Tensor):
+    """Plain-torch specification (always the library path; numerics reference of the kernel)."""
+    return double_exponential_fit(y.detach().cpu())
+
+
 def double_exponential_fit(y: torch.Tensor):
     """y: [K] (ascending |values|) -> (a, b, p, q) float64 on x_i = i/K."""
     K = y.numel()
+    if y.is_cuda and K > 0:                                # hand-written kernel (ops/csrc/ops.cu::dexp_fit_kernel)
+        from .. import ops
+        if ops.require():
+            return tuple(ops.dexp_fit(y.float()).unbind())
     y = y.double()
     if K == 0:                                             # empty selection: the zero curve
         z = torch.zeros((), dtype=torch.float64, device=y.device)

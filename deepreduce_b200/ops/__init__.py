@@ -170,6 +170,12 @@ def polyfit_eval(coeffs, segments, degree, total):
     return cuda_module().polyfit_eval(coeffs.float().contiguous(), offs, lens, int(degree), int(total))
 
 
+def dexp_fit(y_ascending):
+    """(a, b, p, q) float64[4] of the double-exponential fit of ascending |values| — one-CTA sm_100a kernel
+    (scans + moment sums + both small solves); torch oracle: codecs.dexp.double_exponential_fit."""
+    return cuda_module().dexp_fit(y_ascending.contiguous())
+
+
 def delta_bp128_encode(idxs):
     return cuda_module().delta_bp128_encode(idxs.long().contiguous())
 

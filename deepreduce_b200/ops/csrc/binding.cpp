@@ -135,6 +135,16 @@ static torch::Tensor polyfit_eval(torch::Tensor coeffs, torch::Tensor seg_off, t
   return out;
 }
 
+static torch::Tensor dexp_fit(torch::Tensor y) {
+  CHECK_CUDA_T(y);
+  c10::cuda::CUDAGuard g(y.device());
+  auto v = y.to(torch::kFloat32).contiguous();
+  auto out = torch::zeros({4}, v.options().dtype(torch::kFloat64));
+  dr::launch_dexp_fit(v.data_ptr<float>(), v.numel(), out.data_ptr<double>(), cur_stream());
+  check_last("dexp_fit");
+  return out;
+}
+
 static torch::Tensor delta_bp128_encode(torch::Tensor idx) {
   CHECK_CUDA_T(idx);
   c10::cuda::CUDAGuard g(idx.device());
@@ -250,7 +260,7 @@ struct Engine {
     P.filter_smem_words = (uint32_t)(dyn_smem / 4);
     P.use_tma = 1; P.hist_shift = 23;
     P.shard = 0; P.s2_words = 0; P.s2_cap = 0; P.has_rle = 0; P.mc_arena = nullptr;
-    P.peer_timeout_ms = 120000u; P.fault = 0;
+    P.peer_timeout_ms = 120000u; P.fault = 0; P.debug_times = nullptr; P.cost_prefix = nullptr;
     cudaGetDevice(&device);
   }
 
@@ -281,6 +291,8 @@ struct Engine {
   }
   void set_peer_timeout_ms(int64_t ms) { P.peer_timeout_ms = (uint32_t)ms; }
   void set_fault(int f) { P.fault = f; }
+  void set_cost_prefix(int64_t p) { P.cost_prefix = reinterpret_cast<const uint32_t*>(p); }
+  void set_debug_times(int64_t p) { P.debug_times = reinterpret_cast<unsigned long long*>(p); }
   void set_grid_cap(int cap) { grid_cap = cap; }
   void set_multicast(int64_t p) { P.mc_arena = reinterpret_cast<uint32_t*>(p); }
 
@@ -441,6 +453,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("unpack_bits", &unpack_bits);
   m.def("polyfit_fit", &polyfit_fit);
   m.def("polyfit_eval", &polyfit_eval);
+  m.def("dexp_fit", &dexp_fit);
   m.def("delta_bp128_encode", &delta_bp128_encode);
   m.def("delta_bp128_decode", &delta_bp128_decode);
   m.def("u8_to_nhwc_norm", &u8_to_nhwc_norm);
@@ -471,6 +484,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("set_scratch", &Engine::set_scratch)
       .def("set_peer_timeout_ms", &Engine::set_peer_timeout_ms)
       .def("set_fault", &Engine::set_fault)
+      .def("set_cost_prefix", &Engine::set_cost_prefix)
+      .def("set_debug_times", &Engine::set_debug_times)
       .def("set_grid_cap", &Engine::set_grid_cap)
       .def("set_multicast", &Engine::set_multicast)
       .def("grid", &Engine::get_grid)

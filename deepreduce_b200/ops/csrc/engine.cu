@@ -230,7 +230,26 @@ DR_D void stage_filter(const uint32_t* __restrict__ filter, uint32_t n_words) {
   __syncthreads();
 }
 
+// first tile index whose cumulative cost reaches `target` (cost_prefix is non-decreasing, [n_tiles + 1] entries)
+DR_D uint32_t cost_lower_bound(const uint32_t* __restrict__ cp, uint32_t n, uint32_t target) {
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(cp + mid) < target) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+
+// This CTA's contiguous tile range.  Ranges have equal COST, not equal length: a tile of a tensor that ends inside the
+// range costs a histogram merge + ticket + resolve on top of its elements, and with equal counts the ~20 CTAs that
+// own the many small tensors of a model set the duration of every streaming phase (v15 timeline: accumulate median
+// 79 us, max 124 us; query 42 / 68 us).
 DR_D void tile_range(const EngineParams& P, uint32_t& t_begin, uint32_t& t_end) {
+  if (P.cost_prefix) {
+    const uint32_t total = __ldg(P.cost_prefix + P.n_tiles);
+    const uint32_t lo = (uint32_t)(((uint64_t)total * blockIdx.x) / gridDim.x);
+    const uint32_t hi = (uint32_t)(((uint64_t)total * (blockIdx.x + 1)) / gridDim.x);
+    t_begin = blockIdx.x == 0 ? 0u : cost_lower_bound(P.cost_prefix, P.n_tiles, lo);
+    t_end = blockIdx.x + 1 == gridDim.x ? P.n_tiles : cost_lower_bound(P.cost_prefix, P.n_tiles, hi);
+    return;
+  }
   t_begin = (uint32_t)(((uint64_t)P.n_tiles * blockIdx.x) / gridDim.x);
   t_end = (uint32_t)(((uint64_t)P.n_tiles * (blockIdx.x + 1)) / gridDim.x);
 }
@@ -1790,6 +1809,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) dr_engine_kernel(const _
       grid_barrier(P.barrier, bar_epoch, P.status, P.spin_limit);
       pending = false;
     }
+    if (P.debug_times && threadIdx.x == 0) P.debug_times[((size_t)ph * gridDim.x + blockIdx.x) * 2] = globaltimer_ns();
     switch (ph) {
       case kPhAccum: if (P.use_tma) phase_accum<true>(P, sm); else phase_accum<false>(P, sm); break;
       case kPhFallback: phase_fallback(P, sm); break;
@@ -1811,6 +1831,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) dr_engine_kernel(const _
       case kPhSignal2: if (!wait_flags(P, kArenaFlagWords, 100u)) return; break;
       case kPhScatter: phase_scatter(P); break;
       default: break;
+    }
+    if (P.debug_times) {
+      __syncthreads();
+      if (threadIdx.x == 0) P.debug_times[((size_t)ph * gridDim.x + blockIdx.x) * 2 + 1] = globaltimer_ns();
     }
     prev_wait = is_wait;
     pending = true;

@@ -30,6 +30,7 @@ void launch_polyfit_fit(const float* y, const int* seg_off, const int* seg_len, 
                         cudaStream_t st);
 void launch_polyfit_eval(const float* coeffs, const int* seg_off, const int* seg_len, int n_seg, int degree,
                          int64_t total, float* out, cudaStream_t st);
+void launch_dexp_fit(const float* y, int64_t K, double* out_abpq, cudaStream_t st);
 void launch_bp128_widths(const int64_t* idx, int64_t n, uint32_t* widths, cudaStream_t st);
 void launch_bp128_pack(const int64_t* idx, int64_t n, const uint32_t* widths, const int64_t* word_off, uint32_t* out,
                        cudaStream_t st);

@@ -141,6 +141,8 @@ struct TileInfo { uint32_t tensor, base, n, local0; };
 struct EngineParams {
   const TensorDesc* tensors;
   const TileInfo* tiles;         // [n_tiles]
+  const uint32_t* cost_prefix;   // [n_tiles + 1] cumulative cost of the tiles (host plan: elements + per-tensor overheads); the
+                                 // streaming phases cut the tile sequence into equal-COST ranges (nullptr: equal counts)
   uint32_t n_tensors;
   uint32_t n_tiles;
   uint32_t slot_words;           // words reserved per slot
@@ -181,6 +183,7 @@ struct EngineParams {
   uint32_t* bucket_pos;          // [sum K] original position p of the grouped values
   float* expand_buf;             // [world][sum K] fitted curves of every rank
   uint32_t poly_total;           // sum K over the vmode==1 tensors
+  unsigned long long* debug_times;  // optional [kPhEnd][grid][2] globaltimer ns at phase entry / exit of every CTA (nullptr: off)
   uint32_t peer_timeout_ms;      // peer-flag waits give up after this long (status 2, output poisoned with NaN, CTA exits)
   int fault;                     // fault injection (tests): 1 = this rank never releases its stage-1 flags
   uint32_t* mc_arena;            // NVLS multicast mapping of the symmetric arena (nullptr: per-peer P2P stores)

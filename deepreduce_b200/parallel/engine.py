@@ -370,6 +370,12 @@ class BucketEngine:
                 self.grad.data_ptr(), self.resid.data_ptr(), self.hist.data_ptr(), self.hist_total.data_ptr(),
                 self.sel.data_ptr(), self.tile_count.data_ptr(),
                 self.barrier.data_ptr(), self.status.data_ptr(), self.arena_ptrs, self.rank, self.world)
+            # equal-COST tile ranges per CTA (DR_BALANCE=0: equal counts)
+            self.balanced = os.environ.get("DR_BALANCE", "1") != "0"
+            if self.balanced:
+                seg_c, single_c = (float(x) for x in os.environ.get("DR_SEG_COST", "3.0,1.0").split(","))
+                self.cost_prefix = plan.cost_prefix(seg_c, single_c).to(dev)
+                self.ctx.set_cost_prefix(self.cost_prefix.data_ptr())
             self.ctx.set_scratch(self.pos_mask.data_ptr(), self.dec_mask.data_ptr(), self.cand.data_ptr(),
                                  self.cand_cnt.data_ptr())
             # a peer that does not signal within this wall time is fatal (status 2, output poisoned, see wait_flags)

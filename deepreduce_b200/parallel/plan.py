@@ -276,6 +276,29 @@ class BucketPlan:
             rows[:, 3] = loc
         return torch.from_numpy(out.astype(np.uint32).view(np.int32).copy())
 
+    def cost_prefix(self, seg_cost: float = 2.0, single_cost: float = 1.0) -> torch.Tensor:
+        """[n_tiles + 1] int32 cumulative tile costs for the kernel's equal-cost partition (``tile_range``): a tile costs
+        its share of 4096 elements, plus ``seg_cost`` tiles' worth where a multi-tile tensor starts (histogram merge,
+        ticket, resolve, filter staging) and ``single_cost`` for a one-tile tensor.  Units: 1/16 tile."""
+        c = np.zeros(self.n_tiles, dtype=np.int64)
+        for t in self.tensors:
+            loc = np.arange(t.n_tiles, dtype=np.int64) * spec.TILE
+            n = np.minimum(spec.TILE, t.numel - loc)
+            c[t.tile_begin:t.tile_begin + t.n_tiles] = np.maximum(1, np.rint(16.0 * n / spec.TILE)).astype(np.int64)
+            c[t.tile_begin] += int(round(16 * (single_cost if t.n_tiles == 1 else seg_cost)))
+        pre = np.concatenate([[0], np.cumsum(c)])
+        assert pre[-1] < 2 ** 31
+        return torch.from_numpy(pre.astype(np.int32))
+
+    def cta_ranges(self, grid: int, balanced: bool = True):
+        """(begin, end) tile range of every CTA of a `grid`-CTA launch — mirrors ``tile_range`` in engine.cu."""
+        if not balanced:
+            return [(self.n_tiles * b // grid, self.n_tiles * (b + 1) // grid) for b in range(grid)]
+        pre = self.cost_prefix().numpy().astype(np.int64)
+        total = int(pre[-1])
+        cuts = [0] + [int(np.searchsorted(pre, total * b // grid, side="left")) for b in range(1, grid)] + [self.n_tiles]
+        return [(cuts[b], cuts[b + 1]) for b in range(grid)]
+
     def stage2_layout(self, world: int):
         """(entries, words) of a stage-2 slot of the sharded decode.  A rank's slice receives what all W senders
         selected inside it: about sum(K) entries when selections are spread evenly, but up to W * sum(K) (or every

@@ -100,7 +100,7 @@ class Values_Approximation_Helper(Compressor):
             seg = y[b:N]
             if seg.numel() < 3:
                 break
-            line = torch.linspace(float(seg[0]), float(seg[-1]), seg.numel(), dtype=torch.float64)
+            line = torch.linspace(float(seg[0]), float(seg[-1]), seg.numel(), dtype=torch.float64, device=seg.device)
             b = b + int(torch.argmax((line - seg).abs()))
             pts.append(b)
         pts.append(N)
@@ -141,11 +141,12 @@ class BloomFilterCompressor(Compressor):
         return torch.nonzero(flat.abs() >= thr).flatten()
 
     @staticmethod
-    def randomk_indices(tensor_name, N, K):
+    def randomk_indices(tensor_name, N, K, device=None):
         seed = spec.policy_seed(BloomFilterCompressor.global_step, sum(str(tensor_name).encode()))
         BloomFilterCompressor.global_step += 1
-        keys = spec.policy_hash(torch.arange(N), seed)
-        comp = (keys << 31) | torch.arange(N)
+        ar = torch.arange(N, device=device)
+        keys = spec.policy_hash(ar, seed)
+        comp = (keys << 31) | ar
         return torch.sort(torch.sort(comp).values[:K] & 0x7FFFFFFF).values
 
     @staticmethod
@@ -159,7 +160,7 @@ class BloomFilterCompressor(Compressor):
         if on == "topk":
             idx = BloomFilterCompressor.topk_indices(flat, k)
         elif on == "randomk":
-            idx = BloomFilterCompressor.randomk_indices(params.get('tensor_name', 't'), n, k)
+            idx = BloomFilterCompressor.randomk_indices(params.get('tensor_name', 't'), n, k, device=flat.device)
         else:
             idx = BloomFilterCompressor.threshold_indices(flat, params)
         step = int(params.get('step', 0))
@@ -175,16 +176,18 @@ class BloomFilterCompressor(Compressor):
                            bloom_bytes=int(blob[:4].view(torch.int32)), policy=params.get('bloom_policy', 'conflict_sets'),
                            verbosity=params.get('bloom_verbosity', 1))
         params['tensors_size_are_same'] = False
-        return blob, tensor.shape
+        # the op itself is a host op upstream too ("Bloom on CPU", tensorflow/deepreduce.py:256, DEVICE_CPU kernels); the
+        # blob is handed back on the gradient's device so that the collective and the caller never see a device change
+        return blob.to(tensor.device), tensor.shape
 
     @staticmethod
     def decompress(compressed_tensor, ctx, params):
         n = 1
         for s in ctx:
             n *= int(s)
-        out = bloom_decompress_blob(compressed_tensor, n, step=int(params.get('step', 0)),
+        out = bloom_decompress_blob(compressed_tensor.cpu(), n, step=int(params.get('step', 0)),
                                     policy=params.get('bloom_policy', 'conflict_sets'))
-        return out.view(tuple(ctx))
+        return out.view(tuple(ctx)).to(compressed_tensor.device)
 
 
 class DoubleExpCompressor(Compressor):
@@ -212,7 +215,7 @@ class DoubleExpCompressor(Compressor):
             vals, idx, _ = _dexp.DoubleExp.decompress((b.float(), a, torch.Size([n])), {})
         else:
             idx, vals = a.long(), b
-        out = torch.zeros(n, dtype=torch.float32)
+        out = torch.zeros(n, dtype=torch.float32, device=vals.device)      # stays on the gradient's device (GPU upstream, :422-442)
         out[idx] = vals.float()
         return out.view(tuple(shape))
 
@@ -257,11 +260,11 @@ class PolySegCompressor(Compressor):
         coefs = []
         for lo, hi in zip(pts[:-1], pts[1:]):
             n = hi - lo
-            P = gram_basis(n, deg - 1)                       # `polynomial_degree` counts columns in the reference (:490)
+            P = gram_basis(n, deg - 1, device=flat.device)   # `polynomial_degree` counts columns in the reference (:490)
             num = P.T @ values[lo:hi].double()
             den = (P * P).sum(0)
             coefs.append(torch.where(den > 0, num / den.clamp_min(1e-300), torch.zeros_like(num)))
-        wire = torch.cat([torch.tensor(sizes, dtype=torch.float64), torch.cat(coefs), signed.double()])
+        wire = torch.cat([torch.tensor(sizes, dtype=torch.float64, device=flat.device), torch.cat(coefs), signed.double()])
         params['tensors_size_are_same'] = True
         return wire, tensor.shape
 
@@ -275,9 +278,9 @@ class PolySegCompressor(Compressor):
         sizes, coefs, signed = torch.split(tensor_compressed, [nseg, deg * nseg, K])
         sizes = sizes.long().tolist()
         coefs = coefs.view(nseg, deg)
-        vals = torch.cat([gram_basis(n, deg - 1) @ coefs[i] for i, n in enumerate(sizes) if n > 0])
+        vals = torch.cat([gram_basis(n, deg - 1, device=coefs.device) @ coefs[i] for i, n in enumerate(sizes) if n > 0])
         signed = signed.long()
         idx = signed.abs() - 1
-        out = torch.zeros(N, dtype=torch.float32)
+        out = torch.zeros(N, dtype=torch.float32, device=tensor_compressed.device)
         out[idx] = (vals * torch.sign(signed).double()).float()
         return out.view(tuple(ctx))

@@ -1,0 +1,54 @@
+"""Per-CTA phase timeline of the fused exchange kernel (debug_times facility): for every phase the min / median / max
+CTA duration, the spread of the CTAs' start and end times, and the slowest CTAs with what their tile range contains.
+    python scripts/cta_timeline.py [hist_shift]"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from deepreduce_b200.models import resnet50  # noqa: E402
+from deepreduce_b200.parallel import BucketEngine, BucketPlan  # noqa: E402
+
+PH = ["accum", "fallback", "hist2", "insert", "query", "emit"]
+
+
+def main():
+    hs = int(sys.argv[1]) if len(sys.argv) > 1 else 22
+    m = resnet50()
+    named = list(reversed([(n, p) for n, p in m.named_parameters()]))
+    plan = BucketPlan([p.numel() for _, p in named], [n for n, _ in named], compress_ratio=0.01)
+    eng = BucketEngine(plan, device="cuda:0", world=1, rank=0, hist_shift=hs)
+    G = eng.grid()
+    dbg = torch.zeros(20 * G * 2, dtype=torch.int64, device="cuda")
+    eng.ctx.set_debug_times(dbg.data_ptr())
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    grads = [torch.randn(plan.total_elems, device="cuda", generator=gen) * 0.01 for _ in range(4)]
+    flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")
+    for i in range(8):
+        eng.grad.copy_(grads[i % 4]); flush.zero_(); dbg.zero_(); eng.step()
+    torch.cuda.synchronize()
+    t = dbg.cpu().numpy().reshape(20, G, 2).astype(np.int64)
+    t0 = t[0, :, 0].min()
+    tiles = plan.tile_table().numpy().reshape(-1, 4)
+    nt = plan.n_tiles
+    ranges = plan.cta_ranges(G, eng.balanced)   # NOTE: printed ranges use the default costs
+    print(f"grid {G}, tiles {nt}, balanced {eng.balanced}, kernel span {(t[:6, :, 1].max() - t0) / 1e3:.1f} us")
+    for ph, name in enumerate(PH):
+        s, e = t[ph, :, 0], t[ph, :, 1]
+        if s.max() == 0:
+            print(f"{name:9s} (inactive)"); continue
+        d = (e - s) / 1e3
+        print(f"{name:9s} start {(s.min() - t0) / 1e3:7.1f}..{(s.max() - t0) / 1e3:7.1f} us | end {(e.min() - t0) / 1e3:7.1f}..{(e.max() - t0) / 1e3:7.1f} us | "
+              f"dur min {d.min():6.1f} med {np.median(d):6.1f} max {d.max():6.1f}")
+        for b in np.argsort(-d)[:4]:
+            a, z = ranges[b]
+            tens = tiles[a:z, 0]
+            print(f"      slow CTA {b:3d}: {d[b]:6.1f} us  tiles [{a},{z})  tensors {len(set(tens.tolist()))}  one-tile tensors {int(((tiles[a:z, 2] >> 31) & 1).sum())}")
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()

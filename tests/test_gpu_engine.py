@@ -355,3 +355,29 @@ def test_engine_state_roundtrip_and_accumulation():
     tr.ddp.check()
     assert tr.ddp.step_count == 1 and any(not torch.equal(p, q) for p, q in zip(w0, tr.model.parameters()))
     tr.close()
+
+
+def test_tf_compat_on_device_and_dexp_kernel():
+    """The TF-side compressors keep CUDA gradients on the device (Fit-DExp / PolySeg are GPU ops upstream,
+    tensorflow/deepreduce.py:376-557) and the double-exponential fit runs in the hand-written one-CTA kernel."""
+    from deepreduce_b200 import ops, tf_compat as T
+    from deepreduce_b200.codecs import dexp
+    g = torch.Generator().manual_seed(0)
+    y = torch.sort(torch.randn(50000, generator=g).abs()).values
+    ref = torch.stack(dexp.double_exponential_fit_oracle(y))
+    got = ops.dexp_fit(y.cuda()).cpu()
+    curve_ref = dexp.double_exponential_eval(ref.float(), y.numel())
+    curve_got = dexp.double_exponential_eval(got.float(), y.numel())
+    assert torch.allclose(curve_got, curve_ref, rtol=1e-3, atol=1e-4 * float(y.max())), (got, ref)
+    assert ops.launch_count() > 0
+    x = torch.randn(20000, generator=g)
+    for cls, params in ((T.DoubleExpCompressor, {"compress_ratio": 0.05}),
+                        (T.PolySegCompressor, {"compress_ratio": 0.05, "polynomial_degree": 5}),
+                        (T.BloomFilterCompressor, {"compress_ratio": 0.01, "bloom_fpr": 0.01, "bloom_policy": "leftmostK"})):
+        pc, pg = dict(params), dict(params)
+        comp_c, ctx_c = cls.compress(x.clone(), pc)
+        comp_g, ctx_g = cls.compress(x.cuda(), pg)
+        out_c = cls.decompress(comp_c, ctx_c, pc)
+        out_g = cls.decompress(comp_g, ctx_g, pg)
+        assert out_g.is_cuda, cls.__name__
+        assert torch.allclose(out_g.cpu(), out_c, rtol=2e-3, atol=2e-3), cls.__name__
