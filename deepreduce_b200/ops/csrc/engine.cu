@@ -51,7 +51,9 @@ constexpr uint32_t kHalf = kTile / 2;                 // elements per ring stage
 constexpr uint32_t kStageBytes = 2u * kHalf * 4u;     // 16 KB
 constexpr uint32_t kMaxStages = 6;
 constexpr uint32_t kCpStages = 4;                     // cp.async variant of the accumulate ring: fixed depth (wait_group needs a constant)
-constexpr int kPF = 8;                                // candidate-list walks: chunk heads in flight per warp (cp.async ring)
+constexpr int kPF = 4;                                // candidate-list walks: chunk heads in flight per warp (cp.async ring)
+constexpr uint32_t kHead = 64;                        // entries of a chunk head (512 B): with ~20 % of the elements above the history bound a
+                                                      // chunk holds ~50, and entries past the head are fetched on demand (one exposed DRAM latency)
 constexpr uint32_t kUnsafeWord = 8;                   // P.barrier[8]: tensors whose history bound hid the threshold
 constexpr uint32_t kNeedHist2Word = 9;                // P.barrier[9]: tensors whose digit 2 could not be taken speculatively
 
@@ -652,7 +654,7 @@ DR_D uint32_t rle_get(const uint32_t* stream, uint32_t j) {
 // so the walk lives on memory-level parallelism.
 // ===========================================================================
 struct CandWalk {
-  uint2* ent;          // [kPF][32] this warp's ring
+  uint2* ent;          // [kPF][kHead] this warp's ring
   uint32_t* cnt;       // [kPF]
   uint32_t lane, warp;
 };
@@ -661,15 +663,16 @@ DR_D CandWalk cand_walk_init() {
   CandWalk w;
   w.lane = threadIdx.x & 31u; w.warp = threadIdx.x >> 5;
   uint8_t* base = reinterpret_cast<uint8_t*>(g_filter_smem);
-  w.ent = reinterpret_cast<uint2*>(base) + (size_t)w.warp * kPF * 32;
-  w.cnt = reinterpret_cast<uint32_t*>(base + (size_t)kWarps * kPF * 32 * sizeof(uint2)) + w.warp * kPF;
+  w.ent = reinterpret_cast<uint2*>(base) + (size_t)w.warp * kPF * kHead;
+  w.cnt = reinterpret_cast<uint32_t*>(base + (size_t)kWarps * kPF * kHead * sizeof(uint2)) + w.warp * kPF;
   return w;
 }
 
 // issue the copy of chunk `tile`'s head into ring slot `slot` (or an empty group past the end: group counting stays uniform)
 DR_D void cand_walk_issue(const EngineParams& P, const CandWalk& w, uint32_t tile, uint32_t t_end, uint32_t slot) {
   if (tile < t_end) {
-    cp_async_8(w.ent + slot * 32u + w.lane, P.cand + chunk_of(tile, w.warp) + w.lane);
+    const uint2* src = P.cand + chunk_of(tile, w.warp);
+    cp_async_16(w.ent + slot * kHead + 2u * w.lane, src + 2u * w.lane);       // 32 lanes x 16 B = the 64-entry head
     if (w.lane == 0) cp_async_4(w.cnt + slot, P.cand_cnt + tile * kWarps + w.warp);
   }
   cp_async_commit();
@@ -701,13 +704,14 @@ DR_D void phase_hist2(const EngineParams& P, Smem& sm) {
       cp_async_wait<kPF - 1>();                                            // the oldest group (chunk tl) has landed
       __syncwarp();
       const uint32_t c = cw.cnt[slot];
-      const uint32_t ka = cw.ent[slot * 32u + lane].x;
+      const uint32_t ka = cw.ent[slot * kHead + lane].x, kb = cw.ent[slot * kHead + 32u + lane].x;
       __syncwarp();                                                        // everyone has read the slot: refill it
       cand_walk_issue(P, cw, tl + kPF, seg_end, slot);
       if (lane < c && (ka >> 20) == prefix) atomicAdd(&sm.u.hist[(ka >> 9) & 0x7FFu], 1u);
-      if (c > 32u) {
+      if (lane + 32u < c && (kb >> 20) == prefix) atomicAdd(&sm.u.hist[(kb >> 9) & 0x7FFu], 1u);
+      if (c > kHead) {
         const uint2* chunk = P.cand + chunk_of(tl, warp);
-        for (uint32_t j = 32u + lane; j < c; j += 32u) {
+        for (uint32_t j = kHead + lane; j < c; j += 32u) {
           const uint32_t k = __ldcg(chunk + j).x;
           if ((k >> 20) == prefix) atomicAdd(&sm.u.hist[(k >> 9) & 0x7FFu], 1u);
         }
@@ -782,16 +786,17 @@ DR_D void phase_insert(const EngineParams& P, Smem& sm) {
     cp_async_wait<kPF - 1>();                                              // the oldest group (chunk tl) has landed
     __syncwarp();
     const uint32_t c = cw.cnt[slot];
-    const uint2 ea = cw.ent[slot * 32u + lane];
+    const uint2 ea = cw.ent[slot * kHead + lane], eb2 = cw.ent[slot * kHead + 32u + lane];
     __syncwarp();                                                          // everyone has read the slot: refill it
     cand_walk_issue(P, cw, tl + kPF, t_end, slot);
     if (ti.tensor != cur) tensor_params(ti.tensor);
     uint32_t n_sel_tile = 0;
     if (c) {                                                               // warp-uniform
       process(tl, ti.local0, lane < c, ea.x, ea.y, n_sel_tile);
-      if (c > 32u) {
+      if (c > 32u) process(tl, ti.local0, lane + 32u < c, eb2.x, eb2.y, n_sel_tile);
+      if (c > kHead) {
         const uint2* chunk = P.cand + chunk_of(tl, warp);
-        for (uint32_t j0 = 32u; j0 < c; j0 += 32u) {
+        for (uint32_t j0 = kHead; j0 < c; j0 += 32u) {
           const bool have = j0 + lane < c;
           const uint2 eb = have ? __ldcg(chunk + j0 + lane) : make_uint2(0, 0);
           process(tl, ti.local0, have, eb.x, eb.y, n_sel_tile);

@@ -373,7 +373,7 @@ class BucketEngine:
             # equal-COST tile ranges per CTA (DR_BALANCE=0: equal counts)
             self.balanced = os.environ.get("DR_BALANCE", "1") != "0"
             if self.balanced:
-                seg_c, single_c = (float(x) for x in os.environ.get("DR_SEG_COST", "3.0,1.0").split(","))
+                seg_c, single_c = (float(x) for x in os.environ.get("DR_SEG_COST", "6.0,2.0").split(","))
                 self.cost_prefix = plan.cost_prefix(seg_c, single_c).to(dev)
                 self.ctx.set_cost_prefix(self.cost_prefix.data_ptr())
             self.ctx.set_scratch(self.pos_mask.data_ptr(), self.dec_mask.data_ptr(), self.cand.data_ptr(),

@@ -276,7 +276,7 @@ class BucketPlan:
             rows[:, 3] = loc
         return torch.from_numpy(out.astype(np.uint32).view(np.int32).copy())
 
-    def cost_prefix(self, seg_cost: float = 2.0, single_cost: float = 1.0) -> torch.Tensor:
+    def cost_prefix(self, seg_cost: float = 6.0, single_cost: float = 2.0) -> torch.Tensor:
         """[n_tiles + 1] int32 cumulative tile costs for the kernel's equal-cost partition (``tile_range``): a tile costs
         its share of 4096 elements, plus ``seg_cost`` tiles' worth where a multi-tile tensor starts (histogram merge,
         ticket, resolve, filter staging) and ``single_cost`` for a one-tile tensor.  Units: 1/16 tile."""
