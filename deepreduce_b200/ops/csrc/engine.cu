@@ -1464,9 +1464,9 @@ DR_D void phase_push(const EngineParams& P, Smem& sm) {
       }
     }
   }
-  __threadfence_system();
-  __syncthreads();
+  __syncthreads();                                       // every thread's peer stores are issued ...
   if (threadIdx.x == 0) {
+    __threadfence_system();                              // ... and ordered (cumulatively) before the ticket
     const uint32_t t = atomicAdd(P.barrier + 1, 1u);
     sm.s.lb = (t == gridDim.x - 1u) ? 1u : 0u;
   }
@@ -1524,11 +1524,20 @@ DR_D float coded_value(const uint32_t* slot, const TensorDesc& td, const float* 
 }
 
 // ===========================================================================
-// phase 15: decode.  Contiguous tile range per CTA (of this rank's slice when sharded); rank-major.
-// bloom: per sender, (1) membership test of its hinted groups against its filter staged in SMEM -> dec_mask
-// (probe_segment; my own positives are already in pos_mask), (2) one warp per tile turns masks into ranks
-// (prefix table + popcounts), fetches the values and accumulates into the zero-filled dense output.  The same warp
-// and lane own an element for every sender, so the sum order is rank-major and deterministic.
+// phases 15 + 16: decode of this rank's slice (all tiles when unsharded) for all W senders.
+//
+// phase 15 (probe pass).  The work is the concatenation, over the senders r != me, of my slice's tiles; every CTA
+// takes one contiguous piece of that sequence.  A CTA therefore stages ONE sender's filter per tensor and probes a
+// long run of tiles with it (v11-v15 walked sender-major inside every small per-CTA tile range and staged W filters
+// per tensor for a handful of tiles: decode 35 us median / 67 us max at W = 2 — and it grows with W).  Positives go
+// to dec_mask, one slot per (sender, tile of my slice).  My own positives are already in pos_mask (query phase).
+//
+// phase 16 (apply + compact + push).  After a grid barrier, one WARP per tile of my slice: for the senders in rank
+// order, masks -> in-tile ranks (prefix table + popcounts) -> value gather -> accumulate into the zero-filled dense
+// output (same warp and lane own an element for every sender: the sum order is rank-major and deterministic).  When
+// sharded, the same warp then re-reads the finished tile (L2-hot), compacts its non-zeros into a small SMEM stage
+// and stores them straight into every peer's stage-2 slot (P2P or one multimem store); the last CTA (ticket) writes
+// the entry count and releases the second flag set.  No separate compaction pass over the slice, no second barrier.
 // ===========================================================================
 DR_D uint32_t lower_bound_u32(const uint32_t* a, uint32_t n, uint32_t x) {
   uint32_t lo = 0, hi = n;
@@ -1536,80 +1545,91 @@ DR_D uint32_t lower_bound_u32(const uint32_t* a, uint32_t n, uint32_t x) {
   return lo;
 }
 
+// dec_mask slot of (sender r, tile): senders are laid out back to back, each with `span` tiles of my slice
+DR_D uint32_t* dec_mask_base(const EngineParams& P, int r, uint32_t s_begin, uint32_t span) {
+  // probe_segment / load_masks index with the GLOBAL tile id: shift the base so that base + tile*128 is the slot
+  return P.dec_mask + ((size_t)r * span) * kGroupsPerTile - (size_t)s_begin * kGroupsPerTile;
+}
+
 template <bool kFull>
 DR_D void phase_decode(const EngineParams& P, Smem& sm) {
-  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t tid = threadIdx.x;
   const uint32_t parity = P.epoch & 1u;
   uint32_t* arena = P.arena[P.rank];
   if (kFull) {
     for (uint32_t i = blockIdx.x * kThreads + tid; i < P.n_poly * 2u * kRankBins; i += gridDim.x * kThreads)
       P.poly_bins[i] = 0u;
   }
-  uint32_t tile, t_end;
-  decode_range(P, tile, t_end);
-  while (tile < t_end) {
+  if (P.world == 1) return;
+  uint32_t s_begin, s_end;
+  decode_span(P, P.rank, s_begin, s_end);
+  const uint32_t span = s_end - s_begin;
+  const uint64_t total = (uint64_t)(P.world - 1) * span;                   // (sender != me, tile of my slice) pairs
+  uint64_t w0 = total * blockIdx.x / gridDim.x, w1 = total * (blockIdx.x + 1) / gridDim.x;
+  while (w0 < w1) {
+    const uint32_t k = (uint32_t)(w0 / span);                              // k-th sender other than me
+    const int r = (int)k + ((int)k >= P.rank ? 1 : 0);
+    const uint32_t tile = s_begin + (uint32_t)(w0 - (uint64_t)k * span);
+    const uint32_t piece_end = s_begin + (uint32_t)min((uint64_t)span, w1 - (uint64_t)k * span);
+    const Tile t0 = load_tile(P, tile);
+    load_tensor(P, t0.tensor, sm);
+    const uint32_t seg_end = min(piece_end, sm.td.tile_begin + sm.td.n_tiles);
+    if (sm.td.mode == (uint32_t)kModeBloom) {
+      const uint32_t* slot = slot_ptr(arena, P, parity, r);
+      const DynHeader* dyn = reinterpret_cast<const DynHeader*>(slot + kSlotHeaderWords) + t0.tensor;
+      const uint32_t n_sel = __ldcg(&dyn->n_sel), cutoff = __ldcg(&dyn->cutoff);
+      if (n_sel != 0u) {                                                   // CTA-uniform
+        const uint32_t* filter = slot + sm.td.off_filter;
+        const bool fits = sm.td.n_filter_words <= P.filter_smem_words;
+        if (fits) stage_filter(filter, sm.td.n_filter_words);
+        __syncthreads();
+        if (tid == 0) sm.s.lb = 0;
+        __syncthreads();
+        ProbeCtx c;
+        c.hint = sm.td.off_hint ? slot + sm.td.off_hint : nullptr;
+        c.prefix = slot + sm.td.off_prefix; c.n_sel = n_sel; c.cutoff = cutoff;
+        c.mask_out = dec_mask_base(P, r, s_begin, span); c.tile_count = nullptr;
+        c.tile_begin = sm.td.tile_begin; c.seg_a = tile; c.seg_b = seg_end;
+        c.n_hash = sm.td.n_hash; c.m_bits = sm.td.m_bits; c.seed = P.seed;
+        if (fits) probe_segment(P, sm, c, [&](uint32_t w) { return g_filter_smem[w]; });
+        else probe_segment(P, sm, c, [&](uint32_t w) { return __ldcg(filter + w); });
+        __syncthreads();
+      }
+    }
+    w0 += seg_end - tile;
+  }
+}
+
+constexpr uint32_t kS2Stage = 256;             // per-warp stage of the slice list: entries (index | value), flushed at > 128
+
+// debug timeline: sub-step stamps of the apply/compact phase go to the (otherwise unused at vmode 0) slots 6..9
+DR_D void dbg_stamp(const EngineParams& P, int slot, int which) {
+  if (P.debug_times && threadIdx.x == 0) P.debug_times[((size_t)slot * gridDim.x + blockIdx.x) * 2 + which] = globaltimer_ns();
+}
+
+template <bool kFull>
+DR_D void phase_compact(const EngineParams& P, Smem& sm, uint32_t& bar_epoch) {
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t parity = P.epoch & 1u;
+  uint32_t* arena = P.arena[P.rank];
+  const bool stage2 = sharded(P);
+  uint32_t s_begin, s_end;
+  decode_span(P, P.rank, s_begin, s_end);
+  const uint32_t span = s_end - s_begin;
+  uint32_t t_first, t_last;
+  decode_range(P, t_first, t_last);
+  // ---- (1) CTA-level: tensors without a filter (plain pairs, run-length) accumulate a tile in SMEM, rank-major
+  for (uint32_t tile = t_first; tile < t_last;) {
     const Tile t0 = load_tile(P, tile);
     const uint32_t t = t0.tensor;
+    {  // filter-coded tensors (and everything emit already scattered at W == 1) are skipped without a CTA barrier
+      const TensorDesc* tdp = P.tensors + t;
+      const uint32_t seg_end0 = min(t_last, __ldg(&tdp->tile_begin) + __ldg(&tdp->n_tiles));
+      if (__ldg(&tdp->mode) == (uint32_t)kModeBloom || (P.world == 1 && __ldg(&tdp->vmode) == 0u)) { tile = seg_end0; continue; }
+    }
     load_tensor(P, t, sm);
-    const uint32_t seg_end = min(t_end, sm.td.tile_begin + sm.td.n_tiles);
-    if (P.world == 1 && sm.td.vmode == 0u) { tile = seg_end; continue; }   // emit already scattered my own values
-    if (sm.td.mode == (uint32_t)kModeBloom) {
-      const uint32_t n_hash = sm.td.n_hash, m_bits = sm.td.m_bits;
-      const bool fits = sm.td.n_filter_words <= P.filter_smem_words;
-      for (int r = 0; r < P.world; ++r) {
-        const uint32_t* slot = slot_ptr(arena, P, parity, r);
-        const DynHeader* dyn = reinterpret_cast<const DynHeader*>(slot + kSlotHeaderWords) + t;
-        const uint32_t n_sel = __ldcg(&dyn->n_sel), cutoff = __ldcg(&dyn->cutoff);
-        if (n_sel == 0) continue;                                          // CTA-uniform
-        const uint32_t* filter = slot + sm.td.off_filter;
-        const uint32_t* hint = sm.td.off_hint ? slot + sm.td.off_hint : nullptr;
-        const uint32_t* prefix = slot + sm.td.off_prefix;
-        const float* vals = reinterpret_cast<const float*>(slot + sm.td.off_vals);
-        const float* fitted = P.expand_buf + (size_t)r * P.poly_total + sm.td.poly_off;   // 'both': rank r's curve
-        const bool own = (r == P.rank);
-        const uint32_t* masks = own ? P.pos_mask : P.dec_mask;
-        if (!own) {
-          if (fits) stage_filter(filter, sm.td.n_filter_words);
-          __syncthreads();
-          if (tid == 0) sm.s.lb = 0;
-          __syncthreads();
-          ProbeCtx c;
-          c.hint = hint; c.prefix = prefix; c.n_sel = n_sel; c.cutoff = cutoff;
-          c.mask_out = P.dec_mask; c.tile_count = nullptr;
-          c.tile_begin = sm.td.tile_begin; c.seg_a = tile; c.seg_b = seg_end;
-          c.n_hash = n_hash; c.m_bits = m_bits; c.seed = P.seed;
-          if (fits) probe_segment(P, sm, c, [&](uint32_t w) { return g_filter_smem[w]; });
-          else probe_segment(P, sm, c, [&](uint32_t w) { return __ldcg(filter + w); });
-          __syncthreads();                                                 // all masks of this sender are final
-        }
-        uint16_t* list = reinterpret_cast<uint16_t*>(g_filter_smem) + warp * kListCap;   // the staged filter is no longer needed
-        for (uint32_t tl = tile + warp; tl < seg_end; tl += kWarps) {
-          const Tile ti = load_tile(P, tl);
-          const uint32_t tile_local = tl - sm.td.tile_begin;
-          const uint32_t pre = __ldcg(prefix + tile_local);
-          if (!(pre < n_sel && ti.local0 <= cutoff)) continue;             // warp-uniform: nothing of rank r lands here
-          uint32_t mm[4];
-          load_masks(masks, tl, hint_nibble(hint, tile_local, lane), ti.n, lane, mm);
-          const uint32_t c = (uint32_t)(__popc(mm[0]) + __popc(mm[1]) + __popc(mm[2]) + __popc(mm[3]));
-          const uint32_t incl = warp_incl_scan(c, lane);
-          const uint32_t total = __shfl_sync(kFullMask, incl, 31);
-          const uint32_t n_take = min(total, n_sel - pre);                 // positives beyond the sender's n_sel were not shipped
-          for (uint32_t base = 0; base < n_take; base += kListCap) {
-            fill_list(list, mm, incl - c, base, lane);
-            __syncwarp();
-            const uint32_t n_here = min(kListCap, n_take - base);
-            for (uint32_t q = lane; q < n_here; q += 32u) {
-              const uint32_t e = list[q];
-              float* o = P.grad + ti.base + e;                             // the same warp handles this tile for every sender
-              *o = *o + coded_value<kFull>(slot, sm.td, vals, fitted, pre + base + q) * P.scale;
-            }
-            __syncwarp();
-          }
-        }
-        __syncthreads();                                                   // dec_mask / the filter buffer are reused by the next sender
-      }
-      tile = seg_end;
-    } else if (kFull && sm.td.mode == (uint32_t)kModeRle) {
+    const uint32_t seg_end = min(t_last, sm.td.tile_begin + sm.td.n_tiles);
+    if (kFull && sm.td.mode == (uint32_t)kModeRle) {
       // running entry prefix of every sender at my first tile of this tensor = sum of the earlier tiles' counts
       __syncthreads();
       if (tid < 16) sm.s.rle_pre[tid] = 0u;
@@ -1655,50 +1675,70 @@ DR_D void phase_decode(const EngineParams& P, Smem& sm) {
           const uint32_t* idxs = slot + sm.td.off_idx;
           const float* vals = reinterpret_cast<const float*>(slot + sm.td.off_vals);
           const float* fitted = P.expand_buf + (size_t)r * P.poly_total + sm.td.poly_off;
-          const uint32_t lo = lower_bound_u32(idxs, n_sel, ti.local0);
-          const uint32_t hi = lower_bound_u32(idxs, n_sel, ti.local0 + ti.n);
-          for (uint32_t j = lo + tid; j < hi; j += kThreads)
-            atomicAdd(&sm.u.acc[__ldcg(idxs + j) - ti.local0], coded_value<kFull>(slot, sm.td, vals, fitted, j) * P.scale);
+          if (n_sel <= 2048u) {
+            // short lists (the <= 1000-element bypass tensors ship <= 10 pairs): one pass over the list — two binary
+            // searches are ~20 dependent L2 round trips per sender and tile (W = 2 timeline: 3-12 us of this phase)
+            for (uint32_t j = tid; j < n_sel; j += kThreads) {
+              const uint32_t off = __ldcg(idxs + j) - ti.local0;
+              if (off < ti.n) atomicAdd(&sm.u.acc[off], coded_value<kFull>(slot, sm.td, vals, fitted, j) * P.scale);
+            }
+          } else {
+            const uint32_t lo = lower_bound_u32(idxs, n_sel, ti.local0);
+            const uint32_t hi = lower_bound_u32(idxs, n_sel, ti.local0 + ti.n);
+            for (uint32_t j = lo + tid; j < hi; j += kThreads)
+              atomicAdd(&sm.u.acc[__ldcg(idxs + j) - ti.local0], coded_value<kFull>(slot, sm.td, vals, fitted, j) * P.scale);
+          }
           __syncthreads();                                  // rank-major: one sender at a time
         }
         for (uint32_t e = tid; e < ti.n; e += kThreads) P.grad[ti.base + e] = sm.u.acc[e];
       }
     }
   }
-}
-
-// ===========================================================================
-// sharded decode, stage 2 (W > 1): my decoded slice -> exact (index, value) list -> straight into every peer's
-// stage-2 slot.  Same tile->CTA split as the decode phase (no grid barrier in between); entries are staged in the
-// dynamic SMEM buffer, a chunk of the list is reserved with one atomic per flush, and the peers' copies are written
-// with coalesced 4-byte P2P stores (or one multimem store).  Last CTA (ticket): entry count + second flag set.
-// ===========================================================================
-DR_D void phase_compact(const EngineParams& P, Smem& sm) {
-  const uint32_t tid = threadIdx.x, lane = tid & 31u;
-  const uint32_t parity = P.epoch & 1u;
-  uint32_t* s2 = s2_ptr(P.arena[P.rank], P, parity, P.rank);              // s2[0]: list cursor (zeroed in the accumulate phase)
-  const uint32_t cap = P.filter_smem_words / 2u;
-  uint32_t* st_idx = g_filter_smem;
-  float* st_val = reinterpret_cast<float*>(g_filter_smem + cap);
-  uint32_t tile, t_end;
-  decode_range(P, tile, t_end);
   __syncthreads();
-  if (tid == 0) sm.s.lb = 0;
-  __syncthreads();
-  auto flush = [&]() {                                                     // CTA-uniform
-    __syncthreads();
-    const uint32_t n = sm.s.lb;
-    if (tid == 0) sm.s.res[0] = n ? atomicAdd(s2, n) : 0u;
-    __syncthreads();
-    const uint32_t gbase = sm.s.res[0];
-    uint32_t n_ok = n;
-    if (gbase + n > P.s2_cap) {
-      if (tid == 0) atomicExch(P.status, kErrS2Overflow);                  // stage-2 capacity exceeded
+  dbg_stamp(P, 6, 0);
+  // ---- (2) one warp per tile: bloom apply (all senders, rank order), then the slice list of the finished tile
+  uint8_t* dyn_base = reinterpret_cast<uint8_t*>(g_filter_smem);
+  uint16_t* list = reinterpret_cast<uint16_t*>(dyn_base) + warp * kListCap;                         // 2 KB per warp
+  uint32_t* st_idx = reinterpret_cast<uint32_t*>(dyn_base + (size_t)kWarps * kListCap * 2u) + warp * 2u * kS2Stage;
+  float* st_val = reinterpret_cast<float*>(st_idx + kS2Stage);
+  uint32_t* s2 = s2_ptr(arena, P, parity, P.rank);                          // s2[0]: list cursor (zeroed in the accumulate phase)
+  uint32_t n_st = 0;                                                         // entries in my warp's stage (warp-uniform)
+  const uint32_t lt = (1u << lane) - 1u;
+  // fast mode: the warps' stages are gathered in a CTA-wide stage (the list region, free once the apply items are
+  // done) and the CTA reserves its part of the slice list with ONE global atomic — per-warp reservations were ~5 000
+  // same-address atomics in a few microseconds and cost more than the compaction itself (timeline: 17 us)
+  uint32_t* cta_idx = reinterpret_cast<uint32_t*>(dyn_base);
+  float* cta_val = reinterpret_cast<float*>(dyn_base + (size_t)kWarps * kListCap);
+  constexpr uint32_t kCtaCap = kWarps * kListCap / 4u;                       // 4096 entries (idx | val halves of the 32 KB list region)
+  const bool cta_stage = (!P.deterministic && P.world > 1);
+  auto flush = [&]() {                                                       // warp-uniform
+    if (n_st == 0u) return;
+    if (cta_stage) {
+      uint32_t pos = 0;
+      if (lane == 0) pos = atomicAdd(&sm.s.res[2], n_st);
+      pos = __shfl_sync(kFullMask, pos, 0);
+      if (pos + n_st <= kCtaCap) {
+        for (uint32_t j = lane; j < n_st; j += 32u) { cta_idx[pos + j] = st_idx[j]; cta_val[pos + j] = st_val[j]; }
+        __syncwarp();
+        n_st = 0;
+        return;
+      }
+      // does not fit (dense tiles): this and every later reservation go straight to the peers; the CTA stage ends
+      // at the first failed position (reservations are monotonic, so everything below it was written)
+      if (lane == 0) atomicMin(&sm.s.warp_tot[0], pos);
+    }
+    uint32_t gbase = 0;
+    if (lane == 0) gbase = atomicAdd(s2, n_st);
+    gbase = __shfl_sync(kFullMask, gbase, 0);
+    uint32_t n_ok = n_st;
+    if (gbase + n_st > P.s2_cap) {
+      if (lane == 0) atomicExch(P.status, kErrS2Overflow);                  // stage-2 capacity exceeded
       n_ok = gbase < P.s2_cap ? P.s2_cap - gbase : 0u;
     }
+    __syncwarp();
     if (P.mc_arena) {
       uint32_t* dst = s2_ptr(P.mc_arena, P, parity, P.rank);
-      for (uint32_t j = tid; j < n_ok; j += kThreads) {
+      for (uint32_t j = lane; j < n_ok; j += 32u) {
         multimem_st_b32(dst + 4 + gbase + j, st_idx[j]);
         multimem_st_b32(dst + 4 + P.s2_cap + gbase + j, __float_as_uint(st_val[j]));
       }
@@ -1706,59 +1746,193 @@ DR_D void phase_compact(const EngineParams& P, Smem& sm) {
       for (int h = 1; h < P.world; ++h) {
         const int peer = (P.rank + h) % P.world;
         uint32_t* dst = s2_ptr(P.arena[peer], P, parity, P.rank);
-        for (uint32_t j = tid; j < n_ok; j += kThreads) {
+        for (uint32_t j = lane; j < n_ok; j += 32u) {
           dst[4 + gbase + j] = st_idx[j];
           dst[4 + P.s2_cap + gbase + j] = __float_as_uint(st_val[j]);
         }
       }
     }
-    __syncthreads();
-    if (tid == 0) sm.s.lb = 0;
-    __syncthreads();
+    __syncwarp();
+    n_st = 0;
   };
-  for (; tile < t_end; ++tile) {
+  uint32_t cur = kNoTensor;
+  TensorDesc td;                                                             // this warp's current tensor (registers / local)
+  auto warp_tensor = [&](uint32_t t) {
+    cur = t;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(P.tensors + cur);
+    td.mode = __ldg(src + 5); td.n_hash = 0; td.tile_begin = __ldg(src + 3);
+    td.off_vals = __ldg(src + 8); td.off_prefix = __ldg(src + 10); td.off_hint = __ldg(src + 15);
+    td.vmode = __ldg(src + 16); td.off_coef = __ldg(src + 17); td.off_rankmap = __ldg(src + 18);
+    td.poly_degree = __ldg(src + 21); td.rank_u32 = __ldg(src + 22); td.poly_off = __ldg(src + 23);
+  };
+  const bool fast = !P.deterministic && P.world > 1;
+  if (fast) {
+    // ---- (2a) every (sender, tile of my slice) pair is an independent work item of one warp: masks -> ranks -> value
+    // gather -> RED.ADD into the zero-filled dense output.  No read-modify-write latency, W x more parallelism than
+    // walking the senders of a tile in turn (one tile per warp at W = 8 left 13 of 16 warps idle).
+    const uint64_t n_items = (uint64_t)P.world * span;
+    const uint64_t n_warps = (uint64_t)gridDim.x * kWarps;
+    for (uint64_t it = (uint64_t)blockIdx.x * kWarps + warp; it < n_items; it += n_warps) {
+      const int r = (int)(it / span);
+      const uint32_t tl = s_begin + (uint32_t)(it - (uint64_t)r * span);
+      const Tile ti = load_tile(P, tl);
+      if (ti.tensor != cur) warp_tensor(ti.tensor);
+      if (td.mode != (uint32_t)kModeBloom) continue;
+      const uint32_t tile_local = tl - td.tile_begin;
+      const uint32_t* slot = slot_ptr(arena, P, parity, r);
+      const DynHeader* dyn = reinterpret_cast<const DynHeader*>(slot + kSlotHeaderWords) + cur;
+      // one round trip: header words, prefix, hint and masks are independent loads
+      const uint32_t n_sel = __ldcg(&dyn->n_sel), cutoff = __ldcg(&dyn->cutoff);
+      const uint32_t pre = __ldcg(slot + td.off_prefix + tile_local);
+      const uint32_t* hint = td.off_hint ? slot + td.off_hint : nullptr;
+      const uint32_t* masks = (r == P.rank) ? P.pos_mask : dec_mask_base(P, r, s_begin, span);
+      uint32_t mm[4];
+      load_masks(masks, tl, hint_nibble(hint, tile_local, lane), ti.n, lane, mm);
+      if (n_sel == 0u || !(pre < n_sel && ti.local0 <= cutoff)) continue;   // warp-uniform
+      const float* vals = reinterpret_cast<const float*>(slot + td.off_vals);
+      const float* fitted = P.expand_buf + (size_t)r * P.poly_total + td.poly_off;
+      const uint32_t c = (uint32_t)(__popc(mm[0]) + __popc(mm[1]) + __popc(mm[2]) + __popc(mm[3]));
+      const uint32_t incl = warp_incl_scan(c, lane);
+      const uint32_t total = __shfl_sync(kFullMask, incl, 31);
+      const uint32_t n_take = min(total, n_sel - pre);
+      for (uint32_t base = 0; base < n_take; base += kListCap) {
+        fill_list(list, mm, incl - c, base, lane);
+        __syncwarp();
+        const uint32_t n_here = min(kListCap, n_take - base);
+        for (uint32_t q = lane; q < n_here; q += 32u)
+          atomicAdd(P.grad + ti.base + list[q], coded_value<kFull>(slot, td, vals, fitted, pre + base + q) * P.scale);
+        __syncwarp();
+      }
+    }
     __syncthreads();
-    if (sm.s.lb + (uint32_t)kTile > cap) flush();
-    const Tile ti = load_tile(P, tile);
-    float v[kPerThread];
-    uint32_t nz = 0;
+    dbg_stamp(P, 6, 1);
+    dbg_stamp(P, 7, 0);
+    grid_barrier(P.barrier, bar_epoch, P.status, P.spin_limit);            // every tile of my slice is final
+    dbg_stamp(P, 7, 1);
+    cur = kNoTensor;
+  }
+  if (tid == 0) { sm.s.res[2] = 0u; sm.s.warp_tot[0] = 0xFFFFFFFFu; }       // CTA stage cursor / first failed reservation
+  __syncthreads();
+  dbg_stamp(P, 8, 0);
+  for (uint32_t tl = t_first + warp; tl < t_last; tl += kWarps) {
+    const Tile ti = load_tile(P, tl);
+    if (ti.tensor != cur) warp_tensor(ti.tensor);
+    const bool apply = !fast && td.mode == (uint32_t)kModeBloom && !(P.world == 1 && td.vmode == 0u);
+    if (apply) {
+      const uint32_t tile_local = tl - td.tile_begin;
+      for (int r = 0; r < P.world; ++r) {
+        const uint32_t* slot = slot_ptr(arena, P, parity, r);
+        const DynHeader* dyn = reinterpret_cast<const DynHeader*>(slot + kSlotHeaderWords) + cur;
+        const uint32_t n_sel = __ldcg(&dyn->n_sel), cutoff = __ldcg(&dyn->cutoff);
+        if (n_sel == 0u) continue;
+        const uint32_t pre = __ldcg(slot + td.off_prefix + tile_local);
+        if (!(pre < n_sel && ti.local0 <= cutoff)) continue;               // warp-uniform: nothing of rank r lands here
+        const uint32_t* hint = td.off_hint ? slot + td.off_hint : nullptr;
+        const float* vals = reinterpret_cast<const float*>(slot + td.off_vals);
+        const float* fitted = P.expand_buf + (size_t)r * P.poly_total + td.poly_off;   // 'both': rank r's curve
+        const uint32_t* masks = (r == P.rank) ? P.pos_mask : dec_mask_base(P, r, s_begin, span);
+        uint32_t mm[4];
+        load_masks(masks, tl, hint_nibble(hint, tile_local, lane), ti.n, lane, mm);
+        const uint32_t c = (uint32_t)(__popc(mm[0]) + __popc(mm[1]) + __popc(mm[2]) + __popc(mm[3]));
+        const uint32_t incl = warp_incl_scan(c, lane);
+        const uint32_t total = __shfl_sync(kFullMask, incl, 31);
+        const uint32_t n_take = min(total, n_sel - pre);                   // positives beyond the sender's n_sel were not shipped
+        for (uint32_t base = 0; base < n_take; base += kListCap) {
+          fill_list(list, mm, incl - c, base, lane);
+          __syncwarp();
+          const uint32_t n_here = min(kListCap, n_take - base);
+          for (uint32_t q = lane; q < n_here; q += 32u) {
+            const uint32_t e = list[q];
+            float* o = P.grad + ti.base + e;
+            *o = *o + coded_value<kFull>(slot, td, vals, fitted, pre + base + q) * P.scale;
+          }
+          __syncwarp();
+        }
+      }
+    }
+    if (stage2) {
+      // the tile is final (every sender added, or written by part (1)): its non-zeros go to the peers
+      __syncwarp();
+      const float4* src4 = reinterpret_cast<const float4*>(P.grad + ti.base);
+      const uint32_t n4 = (ti.n + 3u) >> 2;                                  // tensors are padded to 32 floats
+      for (uint32_t i0 = 0; i0 < n4; i0 += 128u) {                           // four independent 512-byte loads in flight
+        float4 v4[4];
 #pragma unroll
-    for (int c = 0; c < kPerThread; ++c) {
-      const uint32_t e = c * kThreads + tid;
-      v[c] = e < ti.n ? __ldcg(P.grad + ti.base + e) : 0.f;
-      if (v[c] != 0.f) nz |= 1u << c;
-    }
-    const uint32_t cnt = __popc(nz);
-    const uint32_t incl = warp_incl_scan(cnt, lane);
-    uint32_t wbase = 0;
-    if (lane == 31 && incl) wbase = atomicAdd(&sm.s.lb, incl);
-    wbase = __shfl_sync(kFullMask, wbase, 31);
-    uint32_t pos = wbase + incl - cnt;
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t i = i0 + (uint32_t)u * 32u + lane;
+          v4[u] = i < n4 ? __ldcg(src4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
-    for (int c = 0; c < kPerThread; ++c) {
-      if ((nz >> c) & 1u) { st_idx[pos] = ti.base + c * kThreads + tid; st_val[pos] = v[c]; ++pos; }
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t i = i0 + (uint32_t)u * 32u + lane;
+          const float vv[4] = {v4[u].x, v4[u].y, v4[u].z, v4[u].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const bool nz = vv[j] != 0.f && (i * 4u + (uint32_t)j) < ti.n;
+            const uint32_t bal = __ballot_sync(kFullMask, nz);
+            if (nz) {
+              const uint32_t pos = n_st + (uint32_t)__popc(bal & lt);
+              st_idx[pos] = ti.base + i * 4u + (uint32_t)j;
+              st_val[pos] = vv[j];
+            }
+            n_st += (uint32_t)__popc(bal);
+          }
+          if (n_st > kS2Stage - 128u) flush();
+        }
+      }
     }
   }
-  flush();
-  __threadfence_system();
-  __syncthreads();
-  if (tid == 0) {
-    const uint32_t t = atomicAdd(P.barrier + 2, 1u);
-    sm.s.res[1] = (t == gridDim.x - 1u) ? 1u : 0u;
-  }
-  __syncthreads();
-  if (sm.s.res[1]) {                                                       // last CTA: every chunk is in the peers' memory
-    __threadfence_system();
-    const int p = tid;
-    if (p < P.world && p != P.rank) {
-      const uint32_t n = min(__ldcg(s2), P.s2_cap);
-      uint32_t* dst = s2_ptr(P.arena[p], P, parity, P.rank);
-      dst[0] = n; dst[1] = P.epoch;
-      __threadfence_system();
-      st_release_sys(P.arena[p] + kArenaFlagWords + P.rank, P.epoch);
+  if (stage2) {
+    flush();
+    __syncthreads();                                                         // every warp's entries are staged / stored
+    if (cta_stage) {
+      const uint32_t n = min(min(sm.s.res[2], kCtaCap), sm.s.warp_tot[0]);
+      if (tid == 0) sm.s.res[3] = n ? atomicAdd(s2, n) : 0u;
+      __syncthreads();
+      const uint32_t gbase = sm.s.res[3];
+      uint32_t n_ok = n;
+      if (gbase + n > P.s2_cap) {
+        if (tid == 0) atomicExch(P.status, kErrS2Overflow);
+        n_ok = gbase < P.s2_cap ? P.s2_cap - gbase : 0u;
+      }
+      if (P.mc_arena) {
+        uint32_t* dst = s2_ptr(P.mc_arena, P, parity, P.rank);
+        for (uint32_t j = tid; j < n_ok; j += kThreads) {
+          multimem_st_b32(dst + 4 + gbase + j, cta_idx[j]);
+          multimem_st_b32(dst + 4 + P.s2_cap + gbase + j, __float_as_uint(cta_val[j]));
+        }
+      } else {
+        for (int h = 1; h < P.world; ++h) {
+          const int peer = (P.rank + h) % P.world;
+          uint32_t* dst = s2_ptr(P.arena[peer], P, parity, P.rank);
+          for (uint32_t j = tid; j < n_ok; j += kThreads) {
+            dst[4 + gbase + j] = cta_idx[j];
+            dst[4 + P.s2_cap + gbase + j] = __float_as_uint(cta_val[j]);
+          }
+        }
+      }
+      __syncthreads();
     }
+    dbg_stamp(P, 8, 1);
+    if (tid == 0) {
+      __threadfence_system();                                                // ... and ordered before the ticket (cumulative)
+      const uint32_t t = atomicAdd(P.barrier + 2, 1u);
+      sm.s.res[1] = (t == gridDim.x - 1u) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (sm.s.res[1]) {                                                       // last CTA: every chunk is in the peers' memory
+      const int p = tid;
+      if (p < P.world && p != P.rank) {
+        __threadfence_system();
+        const uint32_t n = min(__ldcg(s2), P.s2_cap);
+        uint32_t* dst = s2_ptr(P.arena[p], P, parity, P.rank);
+        dst[0] = n; dst[1] = P.epoch;
+        __threadfence_system();
+        st_release_sys(P.arena[p] + kArenaFlagWords + P.rank, P.epoch);
+      }
+    }
+    __syncthreads();
   }
-  __syncthreads();
 }
 
 DR_D void phase_scatter(const EngineParams& P) {
@@ -1786,8 +1960,8 @@ DR_D bool phase_active(const EngineParams& P, int ph) {
       return kFull && P.n_poly != 0u;
     case kPhFix: return kFull && P.n_poly_tasks != 0u;
     case kPhPush: case kPhSignal: return P.world > 1;
-    case kPhDecode: return P.world > 1 || (kFull && P.n_poly_tasks != 0u);
-    case kPhCompact: case kPhSignal2: case kPhScatter: return sharded(P);
+    case kPhDecode: case kPhCompact: return P.world > 1 || (kFull && P.n_poly_tasks != 0u);
+    case kPhSignal2: case kPhScatter: return sharded(P);
     default: return false;
   }
 }
@@ -1809,8 +1983,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) dr_engine_kernel(const _
     if (ph == kPhFallback && pending) { grid_barrier(P.barrier, bar_epoch, P.status, P.spin_limit); pending = false; }
     if (!phase_active<kFull>(P, ph)) continue;
     const bool is_wait = (ph == kPhSignal || ph == kPhSignal2);
-    // no barrier: in front of a flag wait; after one (every CTA waited itself); compact reads only the tiles this CTA decoded
-    if (pending && !is_wait && !prev_wait && ph != kPhCompact) {
+    // no barrier: in front of a flag wait; after one (every CTA waited itself)
+    if (pending && !is_wait && !prev_wait) {
       grid_barrier(P.barrier, bar_epoch, P.status, P.spin_limit);
       pending = false;
     }
@@ -1832,7 +2006,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) dr_engine_kernel(const _
       case kPhPush: phase_push(P, sm); break;
       case kPhSignal: if (!wait_flags(P, 0u, 0u)) return; break;
       case kPhDecode: phase_decode<kFull>(P, sm); break;
-      case kPhCompact: phase_compact(P, sm); break;
+      case kPhCompact: phase_compact<kFull>(P, sm, bar_epoch); break;
       case kPhSignal2: if (!wait_flags(P, kArenaFlagWords, 100u)) return; break;
       case kPhScatter: phase_scatter(P); break;
       default: break;
@@ -1887,7 +2061,7 @@ int engine_max_grid(int blocks_per_sm, int dyn_smem_bytes) {
 
 cudaError_t engine_launch(const EngineParams& P, int grid, int blocks_per_sm, int dyn_smem_bytes, cudaStream_t stream) {
   ensure_attr();
-  if (dyn_smem_bytes < 40 * 1024) return cudaErrorInvalidValue;     // TMA ring (>= 2 stages), candidate rings, emit lists
+  if (dyn_smem_bytes < 64 * 1024) return cudaErrorInvalidValue;     // TMA ring, candidate rings, emit / decode lists + slice stage
   if (!P.use_tma && dyn_smem_bytes < (int)(kCpStages * kStageBytes)) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemsetAsync(P.barrier, 0, 4 * sizeof(uint32_t), stream);  // grid barrier + the two tickets
   if (e != cudaSuccess) return e;

@@ -184,6 +184,10 @@ struct EngineParams {
   float* expand_buf;             // [world][sum K] fitted curves of every rank
   uint32_t poly_total;           // sum K over the vmode==1 tensors
   unsigned long long* debug_times;  // optional [kPhEnd][grid][2] globaltimer ns at phase entry / exit of every CTA (nullptr: off)
+  int deterministic;             // 1: decode adds the senders of a tile in rank order by one warp (bit-reproducible sums);
+                                 // 0 (default): every (sender, tile) pair is an independent work item that adds with RED.ADD.F32 —
+                                 // identical on all ranks (owner computes), order-dependent in the last ulp only where >= 3
+                                 // senders hit the same element
   uint32_t peer_timeout_ms;      // peer-flag waits give up after this long (status 2, output poisoned with NaN, CTA exits)
   int fault;                     // fault injection (tests): 1 = this rank never releases its stage-1 flags
   uint32_t* mc_arena;            // NVLS multicast mapping of the symmetric arena (nullptr: per-peer P2P stores)

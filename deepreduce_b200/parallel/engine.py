@@ -359,7 +359,9 @@ class BucketEngine:
             # (own positives, decode scratch) and the candidate lists — (key, in-tile offset) of every element above
             # the history bound, 256 slots per (tile, warp) at a fixed place (8 B per element, touched sparsely)
             self.pos_mask = torch.zeros(nt * 128, dtype=torch.int32, device=dev)
-            self.dec_mask = torch.zeros(nt * 128, dtype=torch.int32, device=dev)
+            # decode scratch: one mask slot per (sender, tile of the slice this rank decodes)
+            span_max = (nt // self.world + 1) if (self.shard and self.world > 1) else nt
+            self.dec_mask = torch.zeros(self.world * span_max * 128, dtype=torch.int32, device=dev)
             self.cand = torch.empty(nt * 4096 * 2, dtype=torch.int32, device=dev)
             self.cand_cnt = torch.zeros(nt * 16, dtype=torch.int32, device=dev)
             self.barrier = torch.zeros(16, dtype=torch.int32, device=dev)
@@ -383,6 +385,10 @@ class BucketEngine:
                 peer_timeout_ms = int(os.environ.get("DR_PEER_TIMEOUT_MS", "120000"))
             self.ctx.set_peer_timeout_ms(int(peer_timeout_ms))
             self.ctx.set_fault(int(fault))
+            # DR_DETERMINISTIC=1: rank-ordered decode sums (bit-reproducible run to run); default: independent
+            # (sender, tile) work items with RED.ADD.F32 (every rank still ends with identical bits: owner computes)
+            self.deterministic = os.environ.get("DR_DETERMINISTIC", "0") == "1"
+            self.ctx.set_deterministic(int(self.deterministic))
             scale = (1.0 / self.world) if average else 1.0
             if filter_smem_bytes is None:      # <1>: 128 regs, 1 CTA/SM; <2>: 64 regs, 2 CTAs/SM
                 filter_smem_bytes = 160 * 1024 if blocks_per_sm < 2 else 80 * 1024
@@ -522,7 +528,7 @@ class BucketEngine:
         base = ARENA_HDR_WORDS + (self.epoch & 1) * W * sw
         out = self.arena[base:base + W * sw]
         dist.all_gather_into_tensor(out, out[self.rank * sw:(self.rank + 1) * sw], group=self.group)
-        self.ctx.run(self.epoch, PH_EXPAND, PH_COMPACT)
+        self.ctx.run(self.epoch, PH_EXPAND, PH_PUSH2)      # expand, probe pass, apply pass (unsharded: no stage 2)
 
     def run_phases(self, begin: int, end: int, epoch: Optional[int] = None):
         """Debug / unfused chain: run a sub-range of phases (one launch)."""

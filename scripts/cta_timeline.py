@@ -12,34 +12,45 @@ sys.path.insert(0, ROOT)
 from deepreduce_b200.models import resnet50  # noqa: E402
 from deepreduce_b200.parallel import BucketEngine, BucketPlan  # noqa: E402
 
-PH = ["accum", "fallback", "hist2", "insert", "query", "emit"]
+PH = ["accum", "fallback", "hist2", "insert", "query", "emit", "apply-items", "apply-barrier", "compact-loop", "rank_exact", "fit", "fix",
+      "push", "signal", "expand", "decode", "compact", "push2", "signal2", "scatter"]
 
 
 def main():
     hs = int(sys.argv[1]) if len(sys.argv) > 1 else 22
+    world = int(os.environ.get("WORLD_SIZE", 1)); rank = int(os.environ.get("RANK", 0)); local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     m = resnet50()
     named = list(reversed([(n, p) for n, p in m.named_parameters()]))
     plan = BucketPlan([p.numel() for _, p in named], [n for n, _ in named], compress_ratio=0.01)
-    eng = BucketEngine(plan, device="cuda:0", world=1, rank=0, hist_shift=hs)
+    eng = BucketEngine(plan, device=f"cuda:{local}", hist_shift=hs) if world > 1 else BucketEngine(plan, device="cuda:0", world=1, rank=0, hist_shift=hs)
     G = eng.grid()
     dbg = torch.zeros(20 * G * 2, dtype=torch.int64, device="cuda")
     eng.ctx.set_debug_times(dbg.data_ptr())
-    gen = torch.Generator(device="cuda").manual_seed(0)
+    gen = torch.Generator(device="cuda").manual_seed(rank)
     grads = [torch.randn(plan.total_elems, device="cuda", generator=gen) * 0.01 for _ in range(4)]
     flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")
     for i in range(8):
-        eng.grad.copy_(grads[i % 4]); flush.zero_(); dbg.zero_(); eng.step()
+        eng.grad.copy_(grads[i % 4]); flush.zero_(); dbg.zero_()
+        if world > 1:
+            dist.barrier()
+        eng.step()
     torch.cuda.synchronize()
+    if rank != 0:
+        eng.close(); dist.destroy_process_group(); return
     t = dbg.cpu().numpy().reshape(20, G, 2).astype(np.int64)
     t0 = t[0, :, 0].min()
     tiles = plan.tile_table().numpy().reshape(-1, 4)
     nt = plan.n_tiles
     ranges = plan.cta_ranges(G, eng.balanced)   # NOTE: printed ranges use the default costs
-    print(f"grid {G}, tiles {nt}, balanced {eng.balanced}, kernel span {(t[:6, :, 1].max() - t0) / 1e3:.1f} us")
+    print(f"world {world} grid {G}, tiles {nt}, balanced {eng.balanced}, kernel span {(t[:, :, 1].max() - t0) / 1e3:.1f} us")
     for ph, name in enumerate(PH):
         s, e = t[ph, :, 0], t[ph, :, 1]
         if s.max() == 0:
-            print(f"{name:9s} (inactive)"); continue
+            continue
         d = (e - s) / 1e3
         print(f"{name:9s} start {(s.min() - t0) / 1e3:7.1f}..{(s.max() - t0) / 1e3:7.1f} us | end {(e.min() - t0) / 1e3:7.1f}..{(e.max() - t0) / 1e3:7.1f} us | "
               f"dur min {d.min():6.1f} med {np.median(d):6.1f} max {d.max():6.1f}")
@@ -48,6 +59,8 @@ def main():
             tens = tiles[a:z, 0]
             print(f"      slow CTA {b:3d}: {d[b]:6.1f} us  tiles [{a},{z})  tensors {len(set(tens.tolist()))}  one-tile tensors {int(((tiles[a:z, 2] >> 31) & 1).sum())}")
     eng.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
