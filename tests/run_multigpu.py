@@ -16,7 +16,10 @@ def main():
     from deepreduce_b200.parallel import BucketEngine, BucketPlan, engine_oracle
     sizes = [64, 1001, 4097, 36864, 147456, 10, 589824, 2359296]
     ok = True
-    for index, policy, value, shard in (("bloom", "leftmost", None, True), ("bloom", "leftmost", None, False),
+    subset = os.environ.get("DR_TEST_SUBSET", "0") == "1"      # W = 8 runs are charged 8x: the representative configurations only
+    for index, policy, value, shard in ((("bloom", "leftmost", None, True), ("rle", "leftmost", None, True),
+                                          ("bloom", "leftmost", "polyfit", True), ("bloom", "thr", None, True),
+                                          ("bloom", "leftmost", None, "nccl")) if subset else ()) or (("bloom", "leftmost", None, True), ("bloom", "leftmost", None, False),
                                         ("bloom", "p0", None, True), (None, "leftmost", None, True),
                                         ("rle", "leftmost", None, True), ("rle", "leftmost", None, False),
                                         ("bloom", "leftmost", "polyfit", True), ("bloom", "leftmost", "polyfit", False),
