@@ -173,6 +173,10 @@ DR_D void multimem_st_v4(uint4* mc_addr, uint4 v) {
                   "f"(__uint_as_float(v.w)) : "memory");
 }
 
+DR_D void multimem_st_v2(uint2* mc_addr, uint2 v) {
+  asm volatile("multimem.st.weak.global.v2.f32 [%0], {%1,%2};"
+               :: "l"(mc_addr), "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)) : "memory");
+}
 DR_D void multimem_st_b32(uint32_t* mc_addr, uint32_t v) {
   asm volatile("multimem.st.weak.global.f32 [%0], %1;" :: "l"(mc_addr), "f"(__uint_as_float(v)) : "memory");
 }

@@ -1736,20 +1736,15 @@ DR_D void phase_compact(const EngineParams& P, Smem& sm, uint32_t& bar_epoch) {
       n_ok = gbase < P.s2_cap ? P.s2_cap - gbase : 0u;
     }
     __syncwarp();
+    // entries travel as interleaved (index, value) pairs: one 8-byte store per entry and peer (256 B per warp store)
     if (P.mc_arena) {
-      uint32_t* dst = s2_ptr(P.mc_arena, P, parity, P.rank);
-      for (uint32_t j = lane; j < n_ok; j += 32u) {
-        multimem_st_b32(dst + 4 + gbase + j, st_idx[j]);
-        multimem_st_b32(dst + 4 + P.s2_cap + gbase + j, __float_as_uint(st_val[j]));
-      }
+      uint2* dst = reinterpret_cast<uint2*>(s2_ptr(P.mc_arena, P, parity, P.rank) + 4) + gbase;
+      for (uint32_t j = lane; j < n_ok; j += 32u) multimem_st_v2(dst + j, make_uint2(st_idx[j], __float_as_uint(st_val[j])));
     } else {
       for (int h = 1; h < P.world; ++h) {
         const int peer = (P.rank + h) % P.world;
-        uint32_t* dst = s2_ptr(P.arena[peer], P, parity, P.rank);
-        for (uint32_t j = lane; j < n_ok; j += 32u) {
-          dst[4 + gbase + j] = st_idx[j];
-          dst[4 + P.s2_cap + gbase + j] = __float_as_uint(st_val[j]);
-        }
+        uint2* dst = reinterpret_cast<uint2*>(s2_ptr(P.arena[peer], P, parity, P.rank) + 4) + gbase;
+        for (uint32_t j = lane; j < n_ok; j += 32u) dst[j] = make_uint2(st_idx[j], __float_as_uint(st_val[j]));
       }
     }
     __syncwarp();
@@ -1896,19 +1891,13 @@ DR_D void phase_compact(const EngineParams& P, Smem& sm, uint32_t& bar_epoch) {
         n_ok = gbase < P.s2_cap ? P.s2_cap - gbase : 0u;
       }
       if (P.mc_arena) {
-        uint32_t* dst = s2_ptr(P.mc_arena, P, parity, P.rank);
-        for (uint32_t j = tid; j < n_ok; j += kThreads) {
-          multimem_st_b32(dst + 4 + gbase + j, cta_idx[j]);
-          multimem_st_b32(dst + 4 + P.s2_cap + gbase + j, __float_as_uint(cta_val[j]));
-        }
+        uint2* dst = reinterpret_cast<uint2*>(s2_ptr(P.mc_arena, P, parity, P.rank) + 4) + gbase;
+        for (uint32_t j = tid; j < n_ok; j += kThreads) multimem_st_v2(dst + j, make_uint2(cta_idx[j], __float_as_uint(cta_val[j])));
       } else {
         for (int h = 1; h < P.world; ++h) {
           const int peer = (P.rank + h) % P.world;
-          uint32_t* dst = s2_ptr(P.arena[peer], P, parity, P.rank);
-          for (uint32_t j = tid; j < n_ok; j += kThreads) {
-            dst[4 + gbase + j] = cta_idx[j];
-            dst[4 + P.s2_cap + gbase + j] = __float_as_uint(cta_val[j]);
-          }
+          uint2* dst = reinterpret_cast<uint2*>(s2_ptr(P.arena[peer], P, parity, P.rank) + 4) + gbase;
+          for (uint32_t j = tid; j < n_ok; j += kThreads) dst[j] = make_uint2(cta_idx[j], __float_as_uint(cta_val[j]));
         }
       }
       __syncthreads();
@@ -1942,9 +1931,8 @@ DR_D void phase_scatter(const EngineParams& P) {
     const int r = (P.rank + h) % P.world;
     const uint32_t* s2 = s2_ptr(P.arena[P.rank], P, parity, r);
     const uint32_t n = min(__ldcg(s2), P.s2_cap);
-    const uint32_t* idx = s2 + 4;
-    const float* val = reinterpret_cast<const float*>(s2 + 4 + P.s2_cap);
-    for (uint32_t i = gtid; i < n; i += gsz) P.grad[__ldcg(idx + i)] = __ldcg(val + i);
+    const uint2* pairs = reinterpret_cast<const uint2*>(s2 + 4);             // interleaved (index, value)
+    for (uint32_t i = gtid; i < n; i += gsz) { const uint2 e = __ldcg(pairs + i); P.grad[e.x] = __uint_as_float(e.y); }
   }
 }
 
