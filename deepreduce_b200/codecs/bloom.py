@@ -74,6 +74,38 @@ def bloom_query_oracle(words: torch.Tensor, d: int, k: int, m_bits: int,
     return torch.cat(out) if out else torch.empty(0, dtype=torch.int64, device=words.device)
 
 
+def conflict_sets_cuda(positives: torch.Tensor, K: int, k: int, m_bits: int, seed: int, pseed: int):
+    """P2 on the device.  The conflict sets (positives grouped by filter bit) are built with a sort of the
+    (bit position, rank) pairs and ordered by (size, bit position); the draw itself — sequential by definition —
+    runs in the one-warp kernel ``conflict_sets_pick_kernel`` (ops/csrc/ops.cu).  Same result as the host routine
+    (``native_cpu.cpp::conflict_sets_impl`` / the reference's policies.hpp:43-146), no device->host bounce of the
+    positives.  Returns None when the positives do not fit the kernel's shared-memory bitmap (> 1.6 M)."""
+    from .. import ops
+    P = int(positives.numel())
+    if P == 0 or P > 1_600_000:
+        return None if P else positives
+    dev = positives.device
+    pos = spec.bloom_positions(positives, k, m_bits, seed)                    # [P, k] filter bits of every positive
+    rank = torch.arange(P, device=dev, dtype=torch.int64)[:, None].expand(P, k)
+    key = torch.unique((pos << 32 | rank).flatten())                          # sorted; a positive enters a set once
+    bit, member = key >> 32, (key & 0xFFFFFFFF).to(torch.int32)
+    start = torch.ones(key.numel(), dtype=torch.bool, device=dev)
+    start[1:] = bit[1:] != bit[:-1]
+    first = torch.nonzero(start).flatten()                                    # first entry of every set (sets in bit order)
+    size = torch.diff(first, append=torch.tensor([key.numel()], device=dev))
+    order = torch.argsort(size << 32 | bit[first])                            # visit order: (size, bit position)
+    size_v = size[order]
+    off_v = torch.zeros(order.numel() + 1, dtype=torch.int64, device=dev)
+    off_v[1:] = torch.cumsum(size_v, 0)
+    # gather the members set by set in visit order
+    idx = torch.repeat_interleave(first[order] - off_v[:-1], size_v) + torch.arange(key.numel(), device=dev)
+    members_v = member[idx].contiguous()
+    chosen = ops.cuda_module().conflict_sets_pick(off_v.to(torch.int32).contiguous(), members_v,
+                                                  size_v.to(torch.int32).contiguous(), P, int(K), int(pseed) & spec.MASK32)
+    bits = ((chosen.to(torch.int64)[:, None] >> torch.arange(32, device=dev)) & 1).flatten()[:P].bool()
+    return positives[bits]
+
+
 def conflict_sets_oracle(positives: torch.Tensor, K: int, k: int, m_bits: int, seed: int, pseed: int):
     """P2 (reference policies.hpp:43-146, paper Alg. 1).  Sequential by nature;
     runs in the native C++ op when built, else in Python (small inputs only).
@@ -83,6 +115,10 @@ def conflict_sets_oracle(positives: torch.Tensor, K: int, k: int, m_bits: int, s
     falls back to leftmost among the unchosen (the reference spins forever,
     SURVEY §3.7)."""
     from .. import ops
+    if positives.is_cuda and ops.has_cuda_native():
+        sel = conflict_sets_cuda(positives, K, k, m_bits, seed, pseed)
+        if sel is not None:
+            return sel
     if ops.has_cpu_native():
         return ops.cpu.conflict_sets(positives.cpu().to(torch.int64), int(K), int(k), int(m_bits),
                                      int(seed), int(pseed)).to(positives.device)
@@ -150,9 +186,12 @@ def bloom_insert(idxs, k, m_bits, seed=spec.DEFAULT_SEED):
 def bloom_select(words, d, K, k, m_bits, policy, pseed=42, seed=spec.DEFAULT_SEED):
     """Universe query + policy -> ascending int64 indices."""
     policy = canonical_policy(policy)
-    if use_cuda(words) and policy != "conflict_sets":
+    if use_cuda(words):
         from .. import ops
-        return ops.bloom_select(words, d, K, k, m_bits, policy, pseed, seed)
+        if policy != "conflict_sets":
+            return ops.bloom_select(words, d, K, k, m_bits, policy, pseed, seed)
+        pos = ops.bloom_select(words, d, K, k, m_bits, "p0", pseed, seed)     # all positives (query kernel), then P2 on the device
+        return conflict_sets_oracle(pos, K, k, m_bits, seed, pseed)
     pos = bloom_query_oracle(words, d, k, m_bits, seed)
     return apply_policy_oracle(pos, K, policy, pseed, k, m_bits, seed)
 

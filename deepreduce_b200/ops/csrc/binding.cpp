@@ -135,6 +135,19 @@ static torch::Tensor polyfit_eval(torch::Tensor coeffs, torch::Tensor seg_off, t
   return out;
 }
 
+// sets in visit order (CSR over member RANKS); returns the chosen flags of the positives, bit-packed
+static torch::Tensor conflict_sets_pick(torch::Tensor set_off, torch::Tensor members, torch::Tensor last, int64_t n_pos, int64_t K,
+                                        int64_t pseed) {
+  CHECK_CUDA_T(set_off); CHECK_CUDA_T(members); CHECK_CUDA_T(last);
+  c10::cuda::CUDAGuard g(set_off.device());
+  auto out = torch::zeros({(n_pos + 31) / 32}, set_off.options().dtype(torch::kInt32));
+  cudaError_t e = dr::launch_conflict_sets_pick((const uint32_t*)set_off.data_ptr<int32_t>(), (const uint32_t*)members.data_ptr<int32_t>(),
+                                                (uint32_t*)last.data_ptr<int32_t>(), (uint32_t)(set_off.numel() - 1), (uint32_t)n_pos,
+                                                (uint32_t)K, (uint32_t)pseed, (uint32_t*)out.data_ptr<int32_t>(), cur_stream());
+  TORCH_CHECK(e == cudaSuccess, "conflict_sets_pick: ", cudaGetErrorString(e));
+  return out;
+}
+
 static torch::Tensor dexp_fit(torch::Tensor y) {
   CHECK_CUDA_T(y);
   c10::cuda::CUDAGuard g(y.device());
@@ -455,6 +468,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("polyfit_fit", &polyfit_fit);
   m.def("polyfit_eval", &polyfit_eval);
   m.def("dexp_fit", &dexp_fit);
+  m.def("conflict_sets_pick", &conflict_sets_pick);
   m.def("delta_bp128_encode", &delta_bp128_encode);
   m.def("delta_bp128_decode", &delta_bp128_decode);
   m.def("u8_to_nhwc_norm", &u8_to_nhwc_norm);

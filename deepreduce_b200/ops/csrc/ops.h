@@ -30,6 +30,8 @@ void launch_polyfit_fit(const float* y, const int* seg_off, const int* seg_len, 
                         cudaStream_t st);
 void launch_polyfit_eval(const float* coeffs, const int* seg_off, const int* seg_len, int n_seg, int degree,
                          int64_t total, float* out, cudaStream_t st);
+cudaError_t launch_conflict_sets_pick(const uint32_t* set_off, const uint32_t* members, uint32_t* last, uint32_t n_sets, uint32_t n_pos,
+                                      uint32_t K, uint32_t pseed, uint32_t* chosen_out, cudaStream_t st);
 void launch_dexp_fit(const float* y, int64_t K, double* out_abpq, cudaStream_t st);
 void launch_bp128_widths(const int64_t* idx, int64_t n, uint32_t* widths, cudaStream_t st);
 void launch_bp128_pack(const int64_t* idx, int64_t n, const uint32_t* widths, const int64_t* word_off, uint32_t* out,

@@ -148,9 +148,19 @@ class DeepReduceDDP:
             names = [n for n, _ in items]
             shapes = [tuple(p.shape) for _, p in items]
             owner = list(range(len(items)))
-            if self.fused and self.params.get('split_numel'):      # opt-in: huge tensors enter the plan as tile-aligned chunks
-                from .plan import split_large
-                numels, names, shapes, owner = split_large(numels, names, shapes, int(self.params['split_numel']))
+            if self.fused:
+                # tensors whose bloom filter would not fit the kernel's SMEM staging buffer enter the plan as tile-aligned
+                # chunks with their own top-k / filter ('split_numel': 'auto', the default; an int pins the chunk size,
+                # 0 / None keeps every tensor whole and lets oversize filters be probed from L2)
+                sn = self.params.get('split_numel', 'auto')
+                if sn == 'auto':
+                    uses_bloom = self.params.get('deepreduce') in ('index', 'both') and self.params.get('index', 'bloom') == 'bloom'
+                    from .plan import auto_split_numel
+                    sn = auto_split_numel(self.params.get('compress_ratio', 0.01), self.params.get('fpr', None),
+                                          (160 if blocks_per_sm < 2 else 80) * 1024) if uses_bloom and self.params.get('compressor') == 'topk' else 0
+                if sn:
+                    from .plan import split_large
+                    numels, names, shapes, owner = split_large(numels, names, shapes, int(sn))
             if self.fused:
                 plan = BucketPlan(numels, names, shapes, **plan_kwargs_from_params(self.params))
                 residual = self.params.get('memory', 'none') == 'residual'

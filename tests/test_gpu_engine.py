@@ -381,3 +381,22 @@ def test_tf_compat_on_device_and_dexp_kernel():
         out_g = cls.decompress(comp_g, ctx_g, pg)
         assert out_g.is_cuda, cls.__name__
         assert torch.allclose(out_g.cpu(), out_c, rtol=2e-3, atol=2e-3), cls.__name__
+
+
+def test_conflict_sets_p2_on_device_matches_host():
+    """P2 (conflict sets) runs on the GPU — set construction by sort, the sequential draw in a one-warp kernel — and
+    returns exactly what the host C++ routine (the reference's policies.hpp semantics) returns."""
+    from deepreduce_b200 import ops
+    from deepreduce_b200.codecs import bloom as B
+    torch.manual_seed(0)
+    for d, K in ((36864, 368), (589824, 5898), (20000, 2000)):
+        idx = torch.randperm(d)[:K].sort().values
+        k, m_bits, _ = spec.bloom_layout(K, d)
+        words = B.bloom_insert_oracle(idx, k, m_bits)
+        pos = B.bloom_query_oracle(words, d, k, m_bits)
+        for pseed in (7, 12345):
+            ref = ops.cpu.conflict_sets(pos, K, k, m_bits, spec.DEFAULT_SEED, pseed)
+            got = B.conflict_sets_cuda(pos.cuda(), K, k, m_bits, spec.DEFAULT_SEED, pseed)
+            assert got is not None and torch.equal(got.cpu(), ref), (d, K, pseed)
+            sel = B.bloom_select(words.cuda(), d, K, k, m_bits, "conflict_sets", pseed)
+            assert torch.equal(sel.cpu(), ref)
