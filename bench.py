@@ -494,7 +494,10 @@ def run_reference(args, rank, world, local):
         loss.backward()
         for n, p in named:
             if p.grad is not None:
-                p.grad = grc.step(p.grad, n).view_as(p)
+                g = grc.step(p.grad, n).view(p.shape).to(p.dtype)
+                if g.stride() != p.stride():           # channels_last conv weights: the fused optimizer wants matching layouts
+                    g = torch.empty_like(p).copy_(g)
+                p.grad = g
         opt.step()
         return loss
 

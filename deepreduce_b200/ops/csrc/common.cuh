@@ -50,6 +50,11 @@ DR_HD uint32_t policy_hash(uint32_t x, uint32_t seed) {
   return fmix32((x * kGolden + seed) ^ 0x5BD1E995u);
 }
 
+// per-(step, tensor) seed of the 'random' policy (spec.py::policy_seed): sender, residual update and receivers agree
+DR_HD uint32_t policy_seed(uint32_t step, uint32_t tensor_id) {
+  return fmix32((step * 0x01000193u) ^ ((tensor_id + 1u) * kGolden));
+}
+
 // Membership test with early exit, two probes per iteration (both loads in flight).
 // `filter` is a bit-packed uint32 array.
 template <typename LoadFn>

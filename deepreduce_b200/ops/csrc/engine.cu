@@ -378,7 +378,8 @@ DR_D void phase_accum(const EngineParams& P, Smem& sm) {
   }
   if (sharded(P) && blockIdx.x == 0 && tid == 0) *s2_ptr(P.arena[P.rank], P, parity_slot, P.rank) = 0u;
   // per-tile counts are accumulated by the insert (raw / rle) and query (bloom) phases of this step
-  for (uint32_t i = blockIdx.x * kThreads + tid; i < P.n_tiles; i += gridDim.x * kThreads) P.tile_count[i] = 0u;
+  // (+ two per-tensor counters behind the tiles: filter positives and inserted elements — 'random' policy)
+  for (uint32_t i = blockIdx.x * kThreads + tid; i < P.n_tiles + 2u * P.n_tensors; i += gridDim.x * kThreads) P.tile_count[i] = 0u;
   __syncthreads();
   for (int j = tid; j < 2 * kHistBins; j += kThreads) sm.u.hist[j] = 0;
   __syncthreads();
@@ -730,6 +731,10 @@ DR_D void phase_hist2(const EngineParams& P, Smem& sm) {
 // Warp-private: a warp walks its own candidate chunks; the selected elements of one iteration are compacted into a
 // 32-entry SMEM row so that every lane sets one (element, hash) bit — no divergent per-element hash loops.
 // ===========================================================================
+// 'random' policy: per-tensor counters behind the per-tile counts (zeroed with them in phase 0)
+DR_D uint32_t* n_pos_of(const EngineParams& P, uint32_t t) { return P.tile_count + P.n_tiles + t; }
+DR_D uint32_t* n_ins_of(const EngineParams& P, uint32_t t) { return P.tile_count + P.n_tiles + P.n_tensors + t; }
+
 DR_D void phase_insert(const EngineParams& P, Smem& sm) {
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t parity = P.epoch & 1u;
@@ -746,9 +751,9 @@ DR_D void phase_insert(const EngineParams& P, Smem& sm) {
     const bool sel = have && k >= thr;
     const uint32_t b = __ballot_sync(kFullMask, sel);
     if (b == 0u) return;
+    n_sel_tile += __popc(b);
     if (mode != (uint32_t)kModeBloom) {
       if (sel) atomicOr(P.pos_mask + (size_t)tl * kGroupsPerTile + (e >> 5), 1u << (e & 31u));
-      n_sel_tile += __popc(b);
       return;
     }
     if (sel) {
@@ -803,7 +808,10 @@ DR_D void phase_insert(const EngineParams& P, Smem& sm) {
         }
       }
     }
-    if (mode != (uint32_t)kModeBloom && lane == 0 && n_sel_tile) atomicAdd(P.tile_count + tl, n_sel_tile);
+    if (lane == 0 && n_sel_tile) {
+      if (mode != (uint32_t)kModeBloom) atomicAdd(P.tile_count + tl, n_sel_tile);
+      else if (P.policy == kPolicyRandom) atomicAdd(n_ins_of(P, cur), n_sel_tile);   // the policy's target count
+    }
   }
   cp_async_wait<0>();
 }
@@ -828,6 +836,8 @@ struct ProbeCtx {
   uint32_t tile_begin;      // first global tile of the tensor
   uint32_t seg_a, seg_b;    // global tile range handled by this CTA
   uint32_t n_hash, m_bits, seed;
+  uint32_t pol_T, pol_seed; // 'random' policy on the receiving side: a positive x survives iff policy_hash(x, pol_seed) <= pol_T
+                            // (0xFFFFFFFF: no filter — the sender's own query, every other policy)
 };
 
 // caller: sm.s.lb = 0 and __syncthreads() before; __syncthreads() after
@@ -859,6 +869,7 @@ DR_D void probe_segment(const EngineParams& P, Smem& sm, const ProbeCtx& c, Load
         const uint32_t p0 = mulhi32(v, m_bits);
         pass = ((ld(p0 >> 5) >> (p0 & 31u)) & 1u) != 0u;
       }
+      if (pass && c.pol_T != 0xFFFFFFFFu) pass = policy_hash(x, c.pol_seed) <= c.pol_T;
       if (pass) {
         atomicOr(c.mask_out + (size_t)tile * kGroupsPerTile + (e >> 5), 1u << (e & 31u));
         if (c.tile_count) atomicAdd(c.tile_count + tile, 1u);
@@ -896,7 +907,8 @@ DR_D void probe_segment(const EngineParams& P, Smem& sm, const ProbeCtx& c, Load
         const uint32_t p1 = mulhi32(h.a + h.b, m_bits);
         ok &= ld(p1 >> 5) >> (p1 & 31u);
       }
-      const bool pass = valid && (ok & 1u);
+      bool pass = valid && (ok & 1u);
+      if (c.n_hash <= 2u && c.pol_T != 0xFFFFFFFFu) pass = pass && policy_hash(x, c.pol_seed) <= c.pol_T;
       const uint32_t b = __ballot_sync(kFullMask, pass);
       const size_t gi = (size_t)tile * kGroupsPerTile + g;
       if (c.n_hash <= 2u) {
@@ -949,9 +961,17 @@ DR_D void phase_query(const EngineParams& P, Smem& sm) {
       c.mask_out = P.pos_mask; c.tile_count = P.tile_count;
       c.tile_begin = sm.td.tile_begin; c.seg_a = tile; c.seg_b = seg_end;
       c.n_hash = sm.td.n_hash; c.m_bits = sm.td.m_bits; c.seed = P.seed;
+      c.pol_T = 0xFFFFFFFFu; c.pol_seed = 0u;
       if (fits) probe_segment(P, sm, c, [&](uint32_t w) { return g_filter_smem[w]; });
       else probe_segment(P, sm, c, [&](uint32_t w) { return __ldcg(filter + w); });
       __syncthreads();
+      if (P.policy == kPolicyRandom) {                                     // raw positives of the tensor (emit derives the acceptance rate)
+        uint32_t part = 0;
+        for (uint32_t j = tile + tid; j < seg_end; j += kThreads) part += __ldcg(P.tile_count + j);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(kFullMask, part, o);
+        if ((tid & 31u) == 0u && part) atomicAdd(n_pos_of(P, t0.tensor), part);
+      }
     }
     tile = seg_end;
   }
@@ -1001,11 +1021,74 @@ DR_D void fill_list(uint16_t* list, const uint32_t (&mm)[4], uint32_t rank0, uin
   }
 }
 
+// 'random' policy (P1; reference pytorch/deepreduce.py:484-490 draws K of the positives with torch.randperm under a fixed
+// global seed).  Here every positive x of a bloom tensor survives iff policy_hash(x, seed(step, tensor)) <= T with
+// T = 2^32 * target / n_pos, target = the number of inserted elements (capped by the capacity): a seeded Bernoulli
+// draw of rate target/n_pos — the expected count is the reference's K, false positives and true elements are
+// dropped alike, and sender and receivers agree because T travels in the tensor's header word `thr_bits` (the
+// receiver applies the same test inside its membership probe).  Runs at the head of the emit phase over this CTA's
+// tiles: rewrites the positive masks and the per-tile counts in place; a grid barrier separates it from the
+// compaction, which then is the leftmost policy on the surviving set.
+DR_D void policy_filter(const EngineParams& P, Smem& sm) {
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  uint32_t* my_slot = slot_ptr(P.arena[P.rank], P, P.epoch & 1u, P.rank);
+  uint32_t tile, t_end;
+  tile_range(P, tile, t_end);
+  while (tile < t_end) {
+    const Tile t0 = load_tile(P, tile);
+    const TensorDesc* tdp = P.tensors + t0.tensor;
+    const uint32_t tile_begin = __ldg(&tdp->tile_begin), n_tiles = __ldg(&tdp->n_tiles);
+    const uint32_t seg_end = min(t_end, tile_begin + n_tiles);
+    if (__ldg(&tdp->mode) == (uint32_t)kModeBloom) {
+      const uint32_t n_pos = __ldcg(n_pos_of(P, t0.tensor)), n_ins = __ldcg(n_ins_of(P, t0.tensor));
+      const uint32_t target = min(n_ins, min(__ldg(&tdp->k), __ldg(&tdp->val_cap)));
+      const uint32_t T = (n_pos <= target) ? 0xFFFFFFFFu : (uint32_t)(((uint64_t)target << 32) / n_pos);
+      const uint32_t pseed = policy_seed(P.epoch, __ldg(&tdp->salt));
+      const uint32_t oh = __ldg(&tdp->off_hint);
+      const uint32_t* hint = oh ? my_slot + oh : nullptr;
+      if (tile == tile_begin && tid == 0) {                                // the CTA that owns the tensor's first tile
+        DynHeader* dyn = reinterpret_cast<DynHeader*>(my_slot + kSlotHeaderWords) + t0.tensor;
+        dyn->thr_bits = T;
+        dyn->n_pos = n_pos;
+      }
+      if (T != 0xFFFFFFFFu) {
+        for (uint32_t tl = tile + warp; tl < seg_end; tl += (uint32_t)kWarps) {
+          const Tile ti = load_tile(P, tl);
+          uint32_t mm[4];
+          load_masks(P.pos_mask, tl, hint_nibble(hint, tl - tile_begin, lane), ti.n, lane, mm);
+          uint32_t cnt = 0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t w = mm[j], keep = 0u;
+            while (w) {
+              const uint32_t b = (uint32_t)__ffs((int)w) - 1u;
+              w &= w - 1u;
+              const uint32_t x = ti.local0 + (4u * lane + (uint32_t)j) * 32u + b;
+              if (policy_hash(x, pseed) <= T) keep |= 1u << b;
+            }
+            mm[j] = keep;
+            cnt += (uint32_t)__popc(keep);
+          }
+          reinterpret_cast<uint4*>(P.pos_mask + (size_t)tl * kGroupsPerTile)[lane] = make_uint4(mm[0], mm[1], mm[2], mm[3]);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(kFullMask, cnt, o);
+          if (lane == 0) P.tile_count[tl] = cnt;
+        }
+      }
+    }
+    tile = seg_end;
+  }
+}
+
 template <bool kFull>
-DR_D void phase_emit(const EngineParams& P, Smem& sm) {
+DR_D void phase_emit(const EngineParams& P, Smem& sm, uint32_t& bar_epoch) {
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t parity = P.epoch & 1u;
   uint32_t* my_slot = slot_ptr(P.arena[P.rank], P, parity, P.rank);
+  if (P.policy == kPolicyRandom) {                                         // grid-uniform
+    policy_filter(P, sm);
+    grid_barrier(P.barrier, bar_epoch, P.status, P.spin_limit);
+  }
   if (blockIdx.x == 0 && tid == 0) {
     my_slot[0] = kMagic; my_slot[1] = P.epoch; my_slot[2] = P.n_tensors; my_slot[3] = P.payload_words;
     my_slot[4] = (uint32_t)P.rank;
@@ -1126,8 +1209,10 @@ DR_D void phase_emit(const EngineParams& P, Smem& sm) {
         if (tile_local + 1u == n_tiles) {
           const uint32_t all = excl + total;
           dyn->n_sel = min(all, limit);
-          dyn->n_pos = all;
-          dyn->thr_bits = thr;
+          if (!(P.policy == kPolicyRandom && mode == (uint32_t)kModeBloom)) {   // else: written by policy_filter
+            dyn->n_pos = all;
+            dyn->thr_bits = thr;
+          }
           if (all < limit) dyn->cutoff = 0xFFFFFFFFu;
           P.sel[cur].prev_thr = thr;
         }
@@ -1591,6 +1676,11 @@ DR_D void phase_decode(const EngineParams& P, Smem& sm) {
         c.mask_out = dec_mask_base(P, r, s_begin, span); c.tile_count = nullptr;
         c.tile_begin = sm.td.tile_begin; c.seg_a = tile; c.seg_b = seg_end;
         c.n_hash = sm.td.n_hash; c.m_bits = sm.td.m_bits; c.seed = P.seed;
+        c.pol_T = 0xFFFFFFFFu; c.pol_seed = 0u;
+        if (P.policy == kPolicyRandom) {                                   // the sender's acceptance threshold rides in its header
+          c.pol_T = __ldcg(&dyn->thr_bits);
+          c.pol_seed = policy_seed(P.epoch, sm.td.salt);
+        }
         if (fits) probe_segment(P, sm, c, [&](uint32_t w) { return g_filter_smem[w]; });
         else probe_segment(P, sm, c, [&](uint32_t w) { return __ldcg(filter + w); });
         __syncthreads();
@@ -1983,7 +2073,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) dr_engine_kernel(const _
       case kPhHist2: phase_hist2(P, sm); break;
       case kPhInsert: phase_insert(P, sm); break;
       case kPhQuery: phase_query(P, sm); break;
-      case kPhEmit: phase_emit<kFull>(P, sm); break;
+      case kPhEmit: phase_emit<kFull>(P, sm, bar_epoch); break;
       case kPhRankHist: if constexpr (kFull) phase_rank_hist(P, sm); break;
       case kPhRankScan: if constexpr (kFull) phase_rank_scan(P, sm); break;
       case kPhRankScatter: if constexpr (kFull) phase_rank_scatter(P, sm); break;

@@ -42,16 +42,16 @@ def _is_dense(p: torch.Tensor) -> bool:
 def _fused_supported(params: dict) -> bool:
     """Which ``params`` dicts the fused bucket engine serves (everything else takes the GRACE-compatible per-tensor
     path).  Covers every recipe of the reference's launch script (run_deepreduce.sh:35-107): top-k or threshold
-    sparsifier x {no codec, index (bloom leftmost / p0, run-length), value (polyfit, QSGD int8/int16), both}.
-    Not fused: bloom policies 'random' / 'conflict_sets' (per-tensor kernels), host codecs (Huffman, Deflate, dexp,
-    the integer family), 'randomk', non-512 QSGD buckets."""
+    sparsifier x {no codec, index (bloom leftmost / random / p0, run-length), value (polyfit, QSGD int8/int16), both}.
+    Not fused: bloom policy 'conflict_sets' (per-tensor GPU kernel), host codecs (Huffman, Deflate, dexp, the integer
+    family), 'randomk', non-512 QSGD buckets."""
     if params.get('compressor') not in ('topk', 'threshold') or params.get('communicator', 'allgather') != 'allgather':
         return False
     dr = params.get('deepreduce', None)
     if dr is None:
         return True
     from ..codecs.bloom import canonical_policy
-    pol_ok = canonical_policy(params.get('policy', 'leftmost')) in ('leftmost', 'p0')
+    pol_ok = canonical_policy(params.get('policy', 'leftmost')) in ('leftmost', 'random', 'p0')
     value_ok = (params.get('value', 'polyfit') == 'polyfit'
                 or (params.get('value') == 'qsgd' and 1 <= int(params.get('quantum_num', 127)) <= 32767
                     and int(params.get('bucket_size', 512)) == 512))

@@ -88,6 +88,18 @@ def select_threshold_oracle(acc: torch.Tensor, fixed_thr: int):
     return torch.nonzero(_abs_keys(acc) >= fixed_thr).flatten(), int(fixed_thr)
 
 
+def random_policy_filter(pos: torch.Tensor, n_ins: int, limit: int, epoch: int, salt: int, T: Optional[int] = None):
+    """'random' policy of the fused engine: keep the positives x with policy_hash(x, policy_seed(step, tensor)) <= T,
+    T = floor(2^32 * min(n_ins, limit) / n_pos) (0xFFFFFFFF = keep all when nothing has to go).  Sender: T from the
+    counts; receiver: T from the header (pass it in).  Returns (surviving positives, T)."""
+    if T is None:
+        n_pos, target = int(pos.numel()), min(int(n_ins), int(limit))
+        T = 0xFFFFFFFF if n_pos <= target else (target << 32) // n_pos
+    if T != 0xFFFFFFFF:
+        pos = pos[spec.policy_hash(pos, spec.policy_seed(epoch, salt)) <= T]
+    return pos, T
+
+
 def encode_tensor_oracle(tp, acc: torch.Tensor, slot: np.ndarray, t_index: int, policy: str, seed: int, epoch: int = 1):
     """Encode one tensor into `slot` (uint32 numpy view); returns new residual."""
     sel_topk, T = (select_threshold_oracle(acc, tp.fixed_thr) if getattr(tp, "fixed_thr", 0)
@@ -111,12 +123,17 @@ def encode_tensor_oracle(tp, acc: torch.Tensor, slot: np.ndarray, t_index: int, 
             np.bitwise_or.at(hint, tile * 4 + gi // 32, (np.uint32(1) << (gi % 32).astype(np.uint32)))
             slot[tp.off_hint:tp.off_hint + 4 * tp.n_tiles] = hint
         limit = tp.val_cap if policy == "p0" else min(tp.k, tp.val_cap)
-        sel = pos[:limit]
         n_pos = int(pos.numel())
+        if policy == "random":
+            # P1: seeded Bernoulli draw of rate target/n_pos over the positives (ops/csrc/engine.cu::policy_filter); the
+            # acceptance threshold travels in header word 2, the receiver repeats the test on its own positives
+            # (T now names the acceptance threshold: that is what header word 2 carries for this policy)
+            pos, T = random_policy_filter(pos, int(sel_topk.numel()), limit, epoch, tp.salt)
+        sel = pos[:limit]
         slot[tp.off_filter:tp.off_filter + tp.n_filter_words] = words.cpu().numpy().view(np.uint32)
         starts = torch.arange(tp.n_tiles, dtype=torch.int64) * spec.TILE
         slot[tp.off_prefix:tp.off_prefix + tp.n_tiles] = torch.searchsorted(sel.cpu(), starts).numpy().astype(np.uint32)
-        cutoff = int(sel[-1].item()) if n_pos >= limit and limit > 0 else 0xFFFFFFFF
+        cutoff = int(sel[-1].item()) if int(pos.numel()) >= limit and limit > 0 else 0xFFFFFFFF
     elif tp.mode == MODE_RLE:
         n_pos = int(sel_topk.numel())
         limit = tp.val_cap
@@ -234,6 +251,8 @@ def decode_slot_oracle(plan: BucketPlan, slot, *, seed=spec.DEFAULT_SEED) -> tor
                 tile, gi = grp // 128, grp % 128
                 bit = (torch.from_numpy(hint.astype(np.int64))[tile * 4 + gi // 32] >> (gi % 32)) & 1
                 pos = pos[bit.bool()]
+            if plan.policy == "random":
+                pos, _ = random_policy_filter(pos, 0, 0, int(a[1]), t.salt, T=int(a[d0 + 2]))
             if cutoff != 0xFFFFFFFF:
                 pos = pos[pos <= cutoff]
             idx = pos[:n_sel]
@@ -305,6 +324,9 @@ def stats_from_slot(plan: BucketPlan, slot) -> dict:
         row = {"name": t.name, "numel": t.numel, "k": t.k, "n_sel": n_sel, "n_pos": n_pos, "false_pos": false_pos,
                "threshold": thr, "cutoff": None if cutoff == 0xFFFFFFFF else cutoff,
                "value_bytes": vbytes, "index_bytes": ibytes}
+        if plan.policy == "random" and t.mode == MODE_BLOOM:   # header word 2 is the policy's acceptance threshold here
+            row["threshold"] = None
+            row["accept_rate"] = 1.0 if thr_bits == 0xFFFFFFFF else thr_bits / 2.0 ** 32
         per.append(row)
         for key in tot:
             tot[key] += row[key]
@@ -354,7 +376,8 @@ class BucketEngine:
             self.hist = torch.zeros(NUM_HIST * nT * HIST_BINS, dtype=torch.int32, device=dev)
             self.hist_total = torch.zeros(NUM_HIST * nT, dtype=torch.int32, device=dev)
             self.sel = torch.zeros(nT * 8, dtype=torch.int32, device=dev)
-            self.tile_count = torch.zeros(nt, dtype=torch.int32, device=dev)
+            # per-tile positive counts + two per-tensor counters (positives, inserted) used by the random policy
+            self.tile_count = torch.zeros(nt + 2 * len(plan.tensors), dtype=torch.int32, device=dev)
             # scratch of the candidate / bitmask pipeline (ops/csrc/engine.cu): one mask word per 32-element group
             # (own positives, decode scratch) and the candidate lists — (key, in-tile offset) of every element above
             # the history bound, 256 slots per (tile, warp) at a fixed place (8 B per element, touched sparsely)

@@ -164,8 +164,6 @@ class BucketPlan:
             fixed_thr = int(np.array([thr], dtype=np.float32).view(np.uint32)[0]) + 1
         if self.policy not in POLICY_ID:
             raise ValueError(f"fused engine supports policies {list(POLICY_ID)}; got {self.policy!r}")
-        if self.policy == "random":
-            raise NotImplementedError("policy 'random' is served by the per-tensor path, not the fused engine yet")
         names = list(self.names) if self.names is not None else [f"t{i}" for i in range(len(self.numels))]
         shapes = list(self.shapes) if self.shapes is not None else [(int(n),) for n in self.numels]
         elem = 0

@@ -45,6 +45,10 @@ def decode_slot_torch(plan, slot: torch.Tensor, seed: int = spec.DEFAULT_SEED):
                 hint = slot[t.off_hint:t.off_hint + 4 * t.n_tiles].to(torch.int64) & 0xFFFFFFFF
                 grp = pos // 32
                 pos = pos[((hint[grp // 32] >> (grp % 32)) & 1).bool()]
+            if plan.policy == "random":                    # header word 2 = acceptance threshold, word 1 of the slot = step
+                T = int(hdr[d0 + 2])
+                if T != 0xFFFFFFFF:
+                    pos = pos[(spec.policy_hash(pos, spec.policy_seed(int(hdr[1]), t.salt)) <= T).to(pos.device)]
             if cutoff != 0xFFFFFFFF:
                 pos = pos[pos <= cutoff]
             idx = pos[:n_sel]

@@ -19,18 +19,21 @@ def main():
     subset = os.environ.get("DR_TEST_SUBSET", "0") == "1"      # W = 8 runs are charged 8x: the representative configurations only
     for index, policy, value, shard in ((("bloom", "leftmost", None, True), ("rle", "leftmost", None, True),
                                           ("bloom", "leftmost", "polyfit", True), ("bloom", "thr", None, True),
-                                          ("bloom", "leftmost", None, "nccl")) if subset else ()) or (("bloom", "leftmost", None, True), ("bloom", "leftmost", None, False),
+                                          ("bloom", "rnd", None, True), ("bloom", "leftmost", None, "nccl")) if subset else ()) or (("bloom", "leftmost", None, True), ("bloom", "leftmost", None, False),
                                         ("bloom", "p0", None, True), (None, "leftmost", None, True),
                                         ("rle", "leftmost", None, True), ("rle", "leftmost", None, False),
                                         ("bloom", "leftmost", "polyfit", True), ("bloom", "leftmost", "polyfit", False),
                                         ("bloom", "leftmost", "qsgd", True), (None, "leftmost", "polyfit", True),
-                                        ("bloom", "thr", None, True), (None, "thr", "qsgd", False)) + (
+                                        ("bloom", "thr", None, True), (None, "thr", "qsgd", False),
+                                        ("bloom", "rnd", None, True), ("bloom", "rnd", "qsgd", True), ("bloom", "rnd", None, False)) + (
             # multi-host transport (encode -> one NCCL all_gather of the slots -> decode); DR_TEST_NCCL_TRANSPORT=0 skips
             (("bloom", "leftmost", None, "nccl"), ("rle", "leftmost", None, "nccl"), ("bloom", "leftmost", "polyfit", "nccl"))
             if os.environ.get("DR_TEST_NCCL_TRANSPORT", "1") == "1" else ()):
         extra = {}
         if policy == "thr":                      # 'threshold' sparsifier (variable K)
             policy, extra = "leftmost", dict(sparsifier="threshold", threshold=1.8, capacity_ratio=0.2)
+        if policy == "rnd":                      # 'random' policy (P1): a generous fpr so that the draw has something to drop
+            policy, extra = "random", dict(fpr=0.02)
         plan = BucketPlan(sizes, compress_ratio=0.01, index=index, policy=policy, value=value, **extra)
         eng = BucketEngine(plan, device=f"cuda:{local}", spin_limit=4_000_000, shard=shard,
                            transport="nccl" if shard == "nccl" else None)

@@ -239,7 +239,9 @@ def test_wire_format_is_self_sufficient(seed):
                  for _ in range(rnd.randint(1, 5))]
         mode = rnd.choice([dict(index='bloom'), dict(index='bloom', policy='p0'), dict(index='bloom', hint=False),
                            dict(index='rle'), dict(index=None), dict(index='bloom', value='polyfit', poly_min_k=32),
-                           dict(index='bloom', value='qsgd')])
+                           dict(index='bloom', value='qsgd'), dict(index='bloom', policy='random', fpr=0.05),
+                           dict(index='bloom', policy='random', value='qsgd', sparsifier='threshold', threshold=1.0,
+                                capacity_ratio=0.5, fpr=0.01)])
         W = rnd.choice([1, 2, 3])
         plan = BucketPlan(sizes, compress_ratio=rnd.choice([0.001, 0.01, 0.1, 0.5]), min_numel=rnd.choice([0, 1000]), **mode)
         kind = rnd.choice(['randn', 'ties', 'sparse'])
@@ -288,7 +290,8 @@ def test_selfcheck_torch_decoder_matches_numpy_oracle():
     sizes = [64, 1001, 4097, 36864, 147456]
     gen = torch.Generator().manual_seed(3)
     for kw in (dict(index="bloom"), dict(index="bloom", hint=False), dict(index="bloom", policy="p0"), dict(index=None),
-               dict(index="bloom", sparsifier="threshold", threshold=1.0, capacity_ratio=0.5)):
+               dict(index="bloom", sparsifier="threshold", threshold=1.0, capacity_ratio=0.5),
+               dict(index="bloom", policy="random", fpr=0.05), dict(index="bloom", policy="random", fpr=0.05, hint=False)):
         plan = BucketPlan(sizes, compress_ratio=0.01, **kw)
         g = torch.zeros(plan.total_elems)
         for v in plan.views(g):
@@ -302,3 +305,31 @@ def test_selfcheck_torch_decoder_matches_numpy_oracle():
     g = torch.randn(plan.total_elems)
     _, _, slots = engine_oracle(plan, [g], [torch.zeros_like(g)])
     assert decode_slot_torch(plan, torch.from_numpy(slots[0].view("int32").copy())) is None
+
+
+def test_random_policy_is_a_seeded_draw_of_the_right_size():
+    """Fused 'random' policy (P1, reference pytorch/deepreduce.py:484-490): the shipped set is a seeded Bernoulli draw
+    of rate inserted/positives — about K coordinates, all of them filter positives, a different draw every step and
+    every tensor, reproduced by the receiver from the header's acceptance threshold alone."""
+    import numpy as np
+    from deepreduce_b200.parallel import BucketPlan, decode_slot_oracle, engine_oracle
+    from deepreduce_b200.parallel.plan import DYN_WORDS, SLOT_HEADER_WORDS
+    d = 200000
+    plan = BucketPlan([d, d], compress_ratio=0.01, index="bloom", policy="random", fpr=0.02, hint=False)
+    g = torch.randn(plan.total_elems, generator=torch.Generator().manual_seed(0))
+    sets = []
+    for step in (1, 2):
+        out, res, slots = engine_oracle(plan, [g], [torch.zeros_like(g)], epoch=step)
+        assert torch.equal(decode_slot_oracle(plan, slots[0]), out)
+        assert torch.equal(res[0] + out, g)                      # error feedback keeps what was not shipped
+        for ti, t in enumerate(plan.tensors):
+            n_sel, _, T, n_pos = (int(x) for x in slots[0][SLOT_HEADER_WORDS + DYN_WORDS * ti:][:4])
+            assert n_pos > t.k * 1.5                               # fpr 2 % of the universe on top of K = 1 %
+            assert T == (t.k << 32) // n_pos                       # the top-k select ships exactly K here (no 22-bit ties in randn)
+            assert abs(n_sel - t.k) < 6 * np.sqrt(t.k) and n_sel <= t.k
+            seg = out[t.elem_off:t.elem_off + t.numel]
+            sets.append(set(torch.nonzero(seg).flatten().tolist()))
+    assert sets[0] != sets[2] and sets[1] != sets[3]               # step 1 vs step 2: another draw
+    top = set(torch.topk(g[:d].abs(), plan.tensors[0].k).indices.tolist())
+    frac_true = len(sets[0] & top) / len(sets[0])
+    assert 0.25 < frac_true < 0.55                                 # true elements and false positives are dropped alike (K / n_pos ~ 1/3)

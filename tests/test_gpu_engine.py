@@ -165,12 +165,18 @@ def _run_vs_oracle(kind, index, policy, hint, tma, value, hist_shift=22, bps=2, 
     ("bloom", "p0", None, dict(sparsifier="threshold", threshold=0.0, fpr=0.01, capacity_ratio=0.3)),
     ("rle", "leftmost", None, dict(sparsifier="threshold", threshold=2.0, capacity_ratio=0.1)),
     ("bloom", "leftmost", "qsgd", dict(sparsifier="threshold", threshold=1.0, capacity_ratio=0.5)),
+    ("bloom", "random", None, dict(fpr=0.02)),                                 # P1: seeded draw among the positives
+    ("bloom", "random", None, dict(fpr=0.05, hint=False)),
+    ("bloom", "random", "qsgd", dict(sparsifier="threshold", threshold=1.0, capacity_ratio=0.5, fpr=0.01)),   # run_deepreduce.sh:73
+    ("bloom", "random", "polyfit", dict(fpr=0.02)),
 ])
 def test_engine_fused_recipe_modes(index, policy, value, kw):
     """The reference's launch recipes beyond top-k + bloom (run_deepreduce.sh:66-74): threshold sparsifier (variable K),
-    value-only mode, QSGD with >= 128 levels — all inside the fused kernel, bit-exact against the oracle."""
+    value-only mode, QSGD with >= 128 levels, policy 'random' (P1, :73-74) — all inside the fused kernel, bit-exact against the oracle."""
+    kw = dict(kw)
+    hint = kw.pop("hint", True)
     for kind in ("randn", "sparse"):
-        _run_vs_oracle(kind, index, policy, True, True, value, **kw)
+        _run_vs_oracle(kind, index, policy, hint, True, value, **kw)
 
 
 def test_topk_select_exact_with_ties_and_sparse():
@@ -189,6 +195,42 @@ def test_topk_select_exact_with_ties_and_sparse():
     assert v.numel() == 100 and set(i.cpu().tolist()) == {0, 5, 77, 1999} and float(v.abs().sum()) == 6.0
     from deepreduce_b200.grace.sparsifiers import _desparsify
     assert torch.equal(_desparsify((v, i), torch.Size([200000])).cpu(), z)
+
+
+@pytest.mark.timeout(300)
+def test_both_adversarial_ties_is_bounded():
+    """Worst case of the exact in-bin rank of the 'both' mode (ops/csrc/engine.cu::phase_rank_exact is all-pairs
+    inside a counting-sort bin): every shipped value has the same magnitude, so the K = 131072 values (the largest K
+    that takes the polynomial fit, plan.MAX_POLY_K) fall into two bins.  The step must finish without tripping a
+    watchdog, agree with the oracle, and its time is reported (profiles/README.md quotes it)."""
+    import json
+    import time
+    from deepreduce_b200.parallel import BucketEngine, BucketPlan, engine_oracle
+    d = 1310720
+    plan = BucketPlan([d], compress_ratio=0.1, index="bloom", value="polyfit")
+    assert plan.tensors[0].vmode == 1 and plan.tensors[0].k == 131072
+    eng = BucketEngine(plan, device="cuda:0", world=1, rank=0)
+    gen = torch.Generator().manual_seed(0)
+    g = torch.where(torch.rand(plan.total_elems, generator=gen) < 0.5, -1.0, 1.0)
+    g[d:] = 0
+    times = []
+    for step in range(3):
+        eng.resid.zero_()
+        eng.grad.copy_(g.cuda())
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        eng.step()
+        torch.cuda.synchronize()
+        times.append((time.perf_counter() - t0) * 1e3)
+        eng.check_status()
+    out_ref, new_res, slots = engine_oracle(plan, [g], [torch.zeros_like(g)], epoch=eng.epoch)
+    assert not _compare_slot(plan, eng.slot(), slots[0], "ties131072")
+    assert torch.allclose(eng.grad.cpu(), out_ref, atol=2e-3, rtol=1e-2)
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, "adversarial_ties.json"), "w") as f:
+        json.dump({"K": 131072, "d": d, "values": "all +-1 (two rank bins of ~65536)", "step_ms": times}, f)
+    assert min(times) < 2000.0, times
+    eng.close()
 
 
 def test_engine_resnet50_shapes_and_volume():

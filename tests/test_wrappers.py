@@ -223,9 +223,12 @@ def test_fused_path_gating():
            {'compressor': 'threshold', 'memory': 'none', 'communicator': 'allgather', 'threshold': 0.0,
             'deepreduce': 'index', 'index': 'bloom', 'policy': 'p0', 'fpr': 0.01},
            {**base, 'deepreduce': 'value', 'value': 'polyfit'}, {**base, 'deepreduce': 'value', 'value': 'qsgd', 'quantum_num': 32},
-           {**base, 'deepreduce': 'both', 'index': 'bloom', 'value': 'qsgd', 'quantum_num': 255}]
+           {**base, 'deepreduce': 'both', 'index': 'bloom', 'value': 'qsgd', 'quantum_num': 255},
+           # ... and its last two (run_deepreduce.sh:73-74): policy 'random' (P1) with QSGD values
+           {**base, 'deepreduce': 'index', 'index': 'bloom', 'policy': 'random'},
+           {'compressor': 'threshold', 'memory': 'none', 'communicator': 'allgather', 'threshold': 0.0,
+            'deepreduce': 'both', 'index': 'bloom', 'policy': 'random', 'fpr': 0.01, 'value': 'qsgd'}]
     no = [{**base, 'compressor': 'randomk'},
-          {**base, 'deepreduce': 'index', 'index': 'bloom', 'policy': 'random'},
           {**base, 'deepreduce': 'index', 'index': 'bloom', 'policy': 'conflict_sets'},
           {**base, 'deepreduce': 'index', 'index': 'huffman'}, {**base, 'deepreduce': 'index', 'index': 'integer'},
           {**base, 'deepreduce': 'both', 'index': 'rle', 'value': 'polyfit'},
