@@ -58,6 +58,19 @@ def main():
             a, z = ranges[b]
             tens = tiles[a:z, 0]
             print(f"      slow CTA {b:3d}: {d[b]:6.1f} us  tiles [{a},{z})  tensors {len(set(tens.tolist()))}  one-tile tensors {int(((tiles[a:z, 2] >> 31) & 1).sum())}")
+    if os.environ.get("DR_TIMELINE_JSON"):          # per-CTA table for fitting the partition's cost model
+        import json
+        single = (tiles[:, 2] >> 31) & 1
+        rows = []
+        for b, (a, z) in enumerate(ranges):
+            tens = tiles[a:z, 0]
+            segs = len(set(tens.tolist()))
+            n_single = int(single[a:z].sum())
+            rows.append({"cta": b, "tiles": int(z - a), "segments": segs, "single": n_single,
+                         "elems": int((tiles[a:z, 2] & 0x7FFFFFFF).sum()),
+                         "dur_us": {name: float((t[ph, b, 1] - t[ph, b, 0]) / 1e3) for ph, name in enumerate(PH) if t[ph, :, 0].max() != 0}})
+        with open(os.environ["DR_TIMELINE_JSON"], "w") as f:
+            json.dump({"world": world, "grid": G, "rows": rows}, f)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
