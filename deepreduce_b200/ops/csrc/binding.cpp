@@ -273,7 +273,7 @@ struct Engine {
     P.filter_smem_words = (uint32_t)(dyn_smem / 4);
     P.use_tma = 1; P.hist_shift = 23;
     P.shard = 0; P.s2_words = 0; P.s2_cap = 0; P.has_rle = 0; P.mc_arena = nullptr;
-    P.peer_timeout_ms = 120000u; P.fault = 0; P.debug_times = nullptr; P.cost_prefix = nullptr; P.deterministic = 0;
+    P.peer_timeout_ms = 120000u; P.fault = 0; P.debug_times = nullptr; P.cost_prefix = nullptr; P.deterministic = 0; P.cuts = nullptr; P.cuts_grid = 0;
     cudaGetDevice(&device);
   }
 
@@ -307,6 +307,7 @@ struct Engine {
   void set_deterministic(int d) { P.deterministic = d; }
   void set_cost_prefix(int64_t p) { P.cost_prefix = reinterpret_cast<const uint32_t*>(p); }
   void set_debug_times(int64_t p) { P.debug_times = reinterpret_cast<unsigned long long*>(p); }
+  void set_cuts(int64_t p, int64_t grid) { P.cuts = reinterpret_cast<const uint32_t*>(p); P.cuts_grid = (uint32_t)grid; }
   void set_grid_cap(int cap) { grid_cap = cap; }
   void set_multicast(int64_t p) { P.mc_arena = reinterpret_cast<uint32_t*>(p); }
 
@@ -502,6 +503,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("set_deterministic", &Engine::set_deterministic)
       .def("set_cost_prefix", &Engine::set_cost_prefix)
       .def("set_debug_times", &Engine::set_debug_times)
+      .def("set_cuts", &Engine::set_cuts)
       .def("set_grid_cap", &Engine::set_grid_cap)
       .def("set_multicast", &Engine::set_multicast)
       .def("grid", &Engine::get_grid)

@@ -243,7 +243,12 @@ DR_D uint32_t cost_lower_bound(const uint32_t* __restrict__ cp, uint32_t n, uint
 // range costs a histogram merge + ticket + resolve on top of its elements, and with equal counts the ~20 CTAs that
 // own the many small tensors of a model set the duration of every streaming phase (v15 timeline: accumulate median
 // 79 us, max 124 us; query 42 / 68 us).
-DR_D void tile_range(const EngineParams& P, uint32_t& t_begin, uint32_t& t_end) {
+DR_D void tile_range(const EngineParams& P, int part, uint32_t& t_begin, uint32_t& t_end) {
+  if (P.cuts && gridDim.x == P.cuts_grid) {      // host-computed partition of this phase class (calibrated per CTA)
+    const uint32_t* c = P.cuts + (size_t)part * (P.cuts_grid + 1u) + blockIdx.x;
+    t_begin = __ldg(c); t_end = __ldg(c + 1);
+    return;
+  }
   if (P.cost_prefix) {
     const uint32_t total = __ldg(P.cost_prefix + P.n_tiles);
     const uint32_t lo = (uint32_t)(((uint64_t)total * blockIdx.x) / gridDim.x);
@@ -385,7 +390,7 @@ DR_D void phase_accum(const EngineParams& P, Smem& sm) {
   __syncthreads();
   const bool has_resid = (P.beta != 0.0f);
   uint32_t t0, t_end;
-  tile_range(P, t0, t_end);
+  tile_range(P, kPartAccum, t0, t_end);
   if (t0 >= t_end) return;
   uint8_t* ring = reinterpret_cast<uint8_t*>(g_filter_smem);
   const uint32_t n_stages = kTma ? min(kMaxStages, (P.filter_smem_words * 4u) / kStageBytes)   // host guarantees >= 2
@@ -571,7 +576,7 @@ DR_D void phase_fallback(const EngineParams& P, Smem& sm) {
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   clear_hist(sm);
   uint32_t tile, t_end;
-  tile_range(P, tile, t_end);
+  tile_range(P, kPartAccum, tile, t_end);
   while (tile < t_end) {
     const Tile t0 = load_tile(P, tile);
     const uint32_t cur = t0.tensor;
@@ -687,7 +692,7 @@ DR_D void phase_hist2(const EngineParams& P, Smem& sm) {
   clear_hist(sm);
   const CandWalk cw = cand_walk_init();
   uint32_t tile, t_end;
-  tile_range(P, tile, t_end);
+  tile_range(P, kPartAccum, tile, t_end);
   while (tile < t_end) {
     const Tile t0 = load_tile(P, tile);
     const uint32_t cur = t0.tensor;
@@ -742,7 +747,7 @@ DR_D void phase_insert(const EngineParams& P, Smem& sm) {
   uint32_t* row = sm.u.sel[warp];
   const uint32_t lt = (1u << lane) - 1u;
   uint32_t tile, t_end;
-  tile_range(P, tile, t_end);
+  tile_range(P, kPartInsert, tile, t_end);
   if (tile >= t_end) return;
   uint32_t cur = kNoTensor, thr = 0xFFFFFFFFu, mode = 0, n_hash = 0, m_bits = 0, recip = 0, tile_begin = 0;
   uint32_t* filter = nullptr;
@@ -944,7 +949,7 @@ DR_D void phase_query(const EngineParams& P, Smem& sm) {
   const uint32_t parity = P.epoch & 1u;
   uint32_t* my_slot = slot_ptr(P.arena[P.rank], P, parity, P.rank);
   uint32_t tile, t_end;
-  tile_range(P, tile, t_end);
+  tile_range(P, kPartQuery, tile, t_end);
   while (tile < t_end) {
     const Tile t0 = load_tile(P, tile);
     load_tensor(P, t0.tensor, sm);
@@ -1033,7 +1038,7 @@ DR_D void policy_filter(const EngineParams& P, Smem& sm) {
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   uint32_t* my_slot = slot_ptr(P.arena[P.rank], P, P.epoch & 1u, P.rank);
   uint32_t tile, t_end;
-  tile_range(P, tile, t_end);
+  tile_range(P, kPartEmit, tile, t_end);
   while (tile < t_end) {
     const Tile t0 = load_tile(P, tile);
     const TensorDesc* tdp = P.tensors + t0.tensor;
@@ -1094,7 +1099,7 @@ DR_D void phase_emit(const EngineParams& P, Smem& sm, uint32_t& bar_epoch) {
     my_slot[4] = (uint32_t)P.rank;
   }
   uint32_t t0, t_end;
-  tile_range(P, t0, t_end);
+  tile_range(P, kPartEmit, t0, t_end);
   for (uint32_t c0 = t0; c0 < t_end; c0 += (uint32_t)kTile) {
     const uint32_t n_chunk = min((uint32_t)kTile, t_end - c0);
     // ---- exclusive prefix of every tile of the chunk inside its tensor
@@ -2066,7 +2071,14 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) dr_engine_kernel(const _
       grid_barrier(P.barrier, bar_epoch, P.status, P.spin_limit);
       pending = false;
     }
-    if (P.debug_times && threadIdx.x == 0) P.debug_times[((size_t)ph * gridDim.x + blockIdx.x) * 2] = globaltimer_ns();
+    if (P.debug_times && threadIdx.x == 0) {
+      P.debug_times[((size_t)ph * gridDim.x + blockIdx.x) * 2] = globaltimer_ns();
+      if (ph == P.phase_begin) {
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        P.debug_times[((size_t)kPhEnd * gridDim.x + blockIdx.x) * 2] = smid;
+      }
+    }
     switch (ph) {
       case kPhAccum: if (P.use_tma) phase_accum<true>(P, sm); else phase_accum<false>(P, sm); break;
       case kPhFallback: phase_fallback(P, sm); break;

@@ -135,6 +135,10 @@ enum Phase : int {
   kPhEnd = 20
 };
 
+// phase classes with their own tile -> CTA partition (the phases have different cost profiles, and the SMs of the two dies
+// run the memory-heavy phases at different speeds): accumulate / fallback / hist2, insert, query, emit
+enum Part : int { kPartAccum = 0, kPartInsert = 1, kPartQuery = 2, kPartEmit = 3, kNumParts = 4 };
+
 // per-tile table (uint4): {tensor id, element offset of the tile in the flat buffers, valid count, offset inside tensor}
 struct TileInfo { uint32_t tensor, base, n, local0; };
 
@@ -183,7 +187,10 @@ struct EngineParams {
   uint32_t* bucket_pos;          // [sum K] original position p of the grouped values
   float* expand_buf;             // [world][sum K] fitted curves of every rank
   uint32_t poly_total;           // sum K over the vmode==1 tensors
-  unsigned long long* debug_times;  // optional [kPhEnd][grid][2] globaltimer ns at phase entry / exit of every CTA (nullptr: off)
+  unsigned long long* debug_times;  // optional [kPhEnd + 1][grid][2] globaltimer ns at phase entry / exit of every CTA (nullptr: off);
+                                    // row kPhEnd: {%smid of the CTA, 0}
+  const uint32_t* cuts;          // optional per-phase-class tile partitions [kNumParts][cuts_grid + 1] (first tile of every CTA,
+  uint32_t cuts_grid;            // host-computed: per-phase cost weights x per-CTA speeds); used when gridDim.x == cuts_grid
   int deterministic;             // 1: decode adds the senders of a tile in rank order by one warp (bit-reproducible sums);
                                  // 0 (default): every (sender, tile) pair is an independent work item that adds with RED.ADD.F32 —
                                  // identical on all ranks (owner computes), order-dependent in the last ulp only where >= 3

@@ -169,6 +169,10 @@ class DeepReduceDDP:
                                    gamma=float(self.params.get('gamma', 1.0)), average=self.params.get('average', True),
                                    use_history=use_history, blocks_per_sm=blocks_per_sm)
                 self.engines.append(eng)
+                # re-cut the kernel's tile partitions from measured per-CTA phase times (collective; ~12 exchange steps
+                # on synthetic gradients, state reset afterwards) — 'calibrate_partition': False keeps the static cut
+                if self.params.get('calibrate_partition', True) and eng.cuts is not None:
+                    eng.calibrate_partition()
                 flat, views = eng.grad, eng.grad_views
             else:
                 plan = BucketPlan(numels, names, shapes, index=None)

@@ -401,6 +401,8 @@ class BucketEngine:
                 seg_c, single_c = (float(x) for x in os.environ.get("DR_SEG_COST", "6.0,2.0").split(","))
                 self.cost_prefix = plan.cost_prefix(seg_c, single_c).to(dev)
                 self.ctx.set_cost_prefix(self.cost_prefix.data_ptr())
+            self.cta_speeds = None          # [4, grid] relative CTA speeds per phase class (calibrate_partition)
+            self.cuts = None
             self.ctx.set_scratch(self.pos_mask.data_ptr(), self.dec_mask.data_ptr(), self.cand.data_ptr(),
                                  self.cand_cnt.data_ptr())
             # a peer that does not signal within this wall time is fatal (status 2, output poisoned, see wait_flags)
@@ -434,7 +436,62 @@ class BucketEngine:
                               self.expand_buf.data_ptr(), int(plan.poly_total))
             self.ctx.configure(self.beta, self.gamma, scale, int(seed), POLICY_ID[plan.policy], int(use_history),
                                int(spin_limit), int(blocks_per_sm), int(filter_smem_bytes), int(use_tma), int(hist_shift))
+            # per-phase-class partitions (own cost weights per class; per-CTA speeds once calibrated); DR_CUTS=0: the
+            # single cost prefix above for every phase
+            if self.balanced and os.environ.get("DR_CUTS", "1") != "0":
+                self._set_cuts()
         self.grad_views = plan.views(self.grad)
+
+    def _set_cuts(self):
+        g = self.grid()
+        self.cuts = self.plan.phase_cuts(g, self.cta_speeds).contiguous().to(self.device)
+        self.ctx.set_cuts(self.cuts.data_ptr(), g)
+
+    @torch.no_grad()
+    def calibrate_partition(self, steps: int = 3, rounds: int = 2, gain: float = 0.8, verbose: bool = False):
+        """Measure how fast every CTA of the persistent kernel gets through its share of the accumulate / insert / query /
+        emit phases (``%globaltimer`` stamps, ``set_debug_times``) on synthetic gradients and re-cut the four tile
+        partitions so that slow CTAs get less work.  Why: the SMs of a B200 do not run the memory-heavy phases at the
+        same speed (the L2 is split over two dies; the per-CTA timeline shows ~75 of the 148 SMs 12 % slower in
+        accumulate and 20 % in query), and every phase ends at a grid barrier, i.e. lasts as long as its slowest CTA.
+        Collective at W > 1 (runs ``rounds * (steps + 1)`` exchange steps).  Resets residual / select history / gradient
+        afterwards; the step counter keeps running (flags are epoch-valued).  Returns the per-round phase maxima."""
+        G = self.grid()
+        dbg = torch.zeros((PH_END + 1) * G * 2, dtype=torch.int64, device=self.device)
+        self.ctx.set_debug_times(dbg.data_ptr())
+        gen = torch.Generator(device=self.device).manual_seed(977 + self.rank)
+        speeds = np.ones((4, G)) if self.cta_speeds is None else np.asarray(self.cta_speeds, dtype=np.float64).copy()
+        phases = (PH_ACCUM, PH_INSERT, PH_QUERY, PH_EMIT)
+        log = []
+        try:
+            for rnd in range(rounds + 1):                  # the last round only measures the result
+                dur = np.zeros((4, G))
+                for i in range(steps + 1):
+                    self.grad.normal_(generator=gen).mul_(1e-2)
+                    dbg.zero_()
+                    self.step()
+                    torch.cuda.synchronize(self.device)
+                    self.check_status()
+                    if i == 0:
+                        continue                           # first step of a round: no select history for the new cut
+                    t = dbg.cpu().numpy().reshape(PH_END + 1, G, 2)
+                    for c, ph in enumerate(phases):
+                        dur[c] += (t[ph, :, 1] - t[ph, :, 0]) / 1e3 / steps
+                log.append({"max_us": dur.max(axis=1).round(1).tolist(), "median_us": np.median(dur, axis=1).round(1).tolist()})
+                if verbose and self.rank == 0:
+                    print(f"[calibrate] round {rnd}: max {log[-1]['max_us']} median {log[-1]['median_us']}", flush=True)
+                if rnd == rounds:
+                    break
+                for c in range(4):
+                    rel = np.median(dur[c]) / np.maximum(dur[c], 1e-3)      # > 1: this CTA finished early -> give it more
+                    speeds[c] = np.clip(speeds[c] * rel ** gain, 0.5, 2.0)
+                    speeds[c] /= speeds[c].mean()
+                self.cta_speeds = speeds
+                self._set_cuts()
+        finally:
+            self.ctx.set_debug_times(0)
+        self.resid.zero_(); self.sel.zero_(); self.grad.zero_()
+        return log
 
     # ---- arena -------------------------------------------------------------
     def _setup_arena(self):

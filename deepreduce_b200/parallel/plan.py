@@ -27,6 +27,10 @@ HIST_BINS = 2048
 NUM_HIST = 3
 ALIGN_ELEMS = 32
 MAX_SEGMENTS = 22
+# (segment start, one-tile tensor) cost in tiles' worth for the four phase classes of the kernel's tile -> CTA partition
+# (accumulate, insert, query, emit): least-squares fit of the per-CTA phase durations of a ResNet-50 bucket
+# (profiles/round2/cta_timeline_v21.txt; scripts/cta_timeline.py)
+PART_WEIGHTS = ((5.0, 1.0), (2.0, 0.0), (5.5, 1.5), (3.0, 0.0))
 MAX_POLY_K = 1 << 17      # the all-pairs rank pass is O(K^2): larger tensors keep fp32 values
 DESC_WORDS = 32
 RANK_BINS = 8192
@@ -304,6 +308,22 @@ class BucketPlan:
         pre = np.concatenate([[0], np.cumsum(c)])
         assert pre[-1] < 2 ** 31
         return torch.from_numpy(pre.astype(np.int32))
+
+    def phase_cuts(self, grid: int, speeds=None, weights=None) -> torch.Tensor:
+        """[4, grid + 1] int32: first tile of every CTA for the kernel's four phase classes (accumulate / insert / query /
+        emit, ``Part`` in ops/csrc/plan.h).  Class c cuts the tiles where the cumulative cost (``cost_prefix`` with the
+        class's own segment / one-tile weights, ``PART_WEIGHTS``) reaches the cumulative share of the CTAs' relative
+        ``speeds[c]`` ([4, grid], default all ones): a CTA on a slower SM gets proportionally less work."""
+        weights = PART_WEIGHTS if weights is None else weights
+        out = np.zeros((len(weights), grid + 1), dtype=np.int64)
+        for c, (seg_c, single_c) in enumerate(weights):
+            pre = self.cost_prefix(seg_c, single_c).numpy().astype(np.float64)
+            sp = np.ones(grid) if speeds is None else np.maximum(np.asarray(speeds[c], dtype=np.float64), 1e-3)
+            share = np.concatenate([[0.0], np.cumsum(sp)]) / sp.sum()
+            cuts = np.searchsorted(pre, pre[-1] * share[1:-1], side="left")
+            out[c, 1:-1] = np.minimum(np.maximum.accumulate(cuts), self.n_tiles)
+            out[c, -1] = self.n_tiles
+        return torch.from_numpy(out.astype(np.int32))
 
     def cta_ranges(self, grid: int, balanced: bool = True):
         """(begin, end) tile range of every CTA of a `grid`-CTA launch — mirrors ``tile_range`` in engine.cu."""

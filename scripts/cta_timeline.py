@@ -28,7 +28,7 @@ def main():
     plan = BucketPlan([p.numel() for _, p in named], [n for n, _ in named], compress_ratio=0.01)
     eng = BucketEngine(plan, device=f"cuda:{local}", hist_shift=hs) if world > 1 else BucketEngine(plan, device="cuda:0", world=1, rank=0, hist_shift=hs)
     G = eng.grid()
-    dbg = torch.zeros(20 * G * 2, dtype=torch.int64, device="cuda")
+    dbg = torch.zeros(21 * G * 2, dtype=torch.int64, device="cuda")   # 20 phases + the %smid row
     eng.ctx.set_debug_times(dbg.data_ptr())
     gen = torch.Generator(device="cuda").manual_seed(rank)
     grads = [torch.randn(plan.total_elems, device="cuda", generator=gen) * 0.01 for _ in range(4)]
@@ -41,11 +41,14 @@ def main():
     torch.cuda.synchronize()
     if rank != 0:
         eng.close(); dist.destroy_process_group(); return
-    t = dbg.cpu().numpy().reshape(20, G, 2).astype(np.int64)
+    t = dbg.cpu().numpy().reshape(21, G, 2).astype(np.int64)
     t0 = t[0, :, 0].min()
     tiles = plan.tile_table().numpy().reshape(-1, 4)
     nt = plan.n_tiles
-    ranges = plan.cta_ranges(G, eng.balanced)   # NOTE: printed ranges use the default costs
+    ranges = plan.cta_ranges(G, eng.balanced)   # accumulate-class ranges (the other phase classes cut slightly differently)
+    if getattr(eng, "cuts", None) is not None:
+        c0 = eng.cuts.cpu().numpy()[0]
+        ranges = [(int(c0[b]), int(c0[b + 1])) for b in range(G)]
     print(f"world {world} grid {G}, tiles {nt}, balanced {eng.balanced}, kernel span {(t[:, :, 1].max() - t0) / 1e3:.1f} us")
     for ph, name in enumerate(PH):
         s, e = t[ph, :, 0], t[ph, :, 1]

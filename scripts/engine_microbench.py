@@ -32,6 +32,9 @@ def main():
         n = int(shape.replace('uniform', ''))
         plan = BucketPlan([25557032 // n] * n, compress_ratio=0.01, hint=hint, value=value)
     eng = BucketEngine(plan, device="cuda:0", world=1, rank=0, blocks_per_sm=bps, use_tma=use_tma, hist_shift=hist_shift)
+    calibrate = bool(int(sys.argv[8])) if len(sys.argv) > 8 else True
+    if calibrate and eng.cuts is not None:
+        eng.calibrate_partition()
     gen = torch.Generator(device="cuda").manual_seed(0)
     grads = [torch.randn(plan.total_elems, device="cuda", generator=gen) * 0.01 for _ in range(4)]
     flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")
@@ -78,7 +81,7 @@ def main():
     min_bytes = 4 * d
     med = fused[len(fused) // 2]
     out = {"kernel": "dr_engine_kernel (fused, W=1)", "model": f"{shape} grads", "dense_bytes": d,
-           "wire_bytes": plan.wire_bytes(), "grid": eng.grid(), "blocks_per_sm": bps, "use_tma": use_tma, "hist_shift": hist_shift, "hint": hint, "value": value,
+           "wire_bytes": plan.wire_bytes(), "grid": eng.grid(), "blocks_per_sm": bps, "use_tma": use_tma, "hist_shift": hist_shift, "calibrated_partition": calibrate, "hint": hint, "value": value,
            "fused_ms_median": med, "fused_ms_min": fused[0],
            "phase_ms_unfused": dict(zip(PHASES, [round(x, 4) for x in per])),
            "algorithmic_min_bytes": min_bytes, "achieved_gbs_vs_min_bytes": min_bytes / med / 1e6,

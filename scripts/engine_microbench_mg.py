@@ -26,6 +26,8 @@ def main():
     named = list(reversed([(n, p) for n, p in m.named_parameters()]))
     plan = BucketPlan([p.numel() for _, p in named], [n for n, _ in named], compress_ratio=0.01, index=index, value=value)
     eng = BucketEngine(plan, device=f"cuda:{local}")
+    if os.environ.get("DR_CALIBRATE", "1") != "0" and eng.cuts is not None:
+        eng.calibrate_partition()
     gen = torch.Generator(device="cuda").manual_seed(rank)
     grads = [torch.randn(plan.total_elems, device="cuda", generator=gen) * 0.01 for _ in range(4)]
     flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")

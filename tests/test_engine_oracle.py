@@ -333,3 +333,22 @@ def test_random_policy_is_a_seeded_draw_of_the_right_size():
     top = set(torch.topk(g[:d].abs(), plan.tensors[0].k).indices.tolist())
     frac_true = len(sets[0] & top) / len(sets[0])
     assert 0.25 < frac_true < 0.55                                 # true elements and false positives are dropped alike (K / n_pos ~ 1/3)
+
+
+def test_phase_cuts_cover_all_tiles_and_follow_speeds():
+    """BucketPlan.phase_cuts: four monotone partitions of the tiles (one per phase class of the kernel); a CTA with
+    relative speed s gets about s times the average cost."""
+    import numpy as np
+    from deepreduce_b200.parallel import BucketPlan
+    plan = BucketPlan([100, 5000, 300000, 4097, 2000000, 64, 1200000], compress_ratio=0.01)
+    G = 64
+    c = plan.phase_cuts(G).numpy()
+    assert c.shape == (4, G + 1) and (c[:, 0] == 0).all() and (c[:, -1] == plan.n_tiles).all() and (np.diff(c, axis=1) >= 0).all()
+    assert not np.array_equal(c[0], c[1])                      # accumulate and insert weigh segment starts differently
+    sp = np.ones((4, G)); sp[:, G // 2:] = 0.5
+    c2 = plan.phase_cuts(G, sp).numpy()
+    n_fast, n_slow = np.diff(c2[1])[:G // 2].sum(), np.diff(c2[1])[G // 2:].sum()
+    assert 1.7 < n_fast / n_slow < 2.3
+    tiny = BucketPlan([100, 200], compress_ratio=0.1)          # fewer tiles than CTAs: empty ranges are legal
+    c3 = tiny.phase_cuts(296).numpy()
+    assert (c3[:, -1] == tiny.n_tiles).all() and (np.diff(c3, axis=1) >= 0).all()

@@ -197,6 +197,34 @@ def test_topk_select_exact_with_ties_and_sparse():
     assert torch.equal(_desparsify((v, i), torch.Size([200000])).cpu(), z)
 
 
+def test_calibrated_partition_is_bit_exact():
+    """Per-phase tile partitions re-cut from measured per-CTA speeds (BucketEngine.calibrate_partition) change which CTA
+    handles which tile in every phase, never a bit of the slot, the output or the residual; and the state is fresh
+    afterwards.  Also with deliberately skewed speeds (some CTAs get almost nothing)."""
+    from deepreduce_b200.parallel import BucketEngine, BucketPlan, engine_oracle
+    plan = BucketPlan(SIZES + [2359296, 1048576], compress_ratio=0.01, index="bloom")
+    eng = BucketEngine(plan, device="cuda:0", world=1, rank=0)
+    assert eng.cuts is not None
+    log = eng.calibrate_partition(steps=2, rounds=1)
+    assert len(log) == 2 and float(eng.resid.abs().max()) == 0.0 and int(eng.sel.abs().max()) == 0
+    gen = torch.Generator().manual_seed(3)
+    resid_ref = torch.zeros(plan.total_elems)
+    for step in range(3):
+        if step == 2:                                    # skewed cut: a few CTAs own most of the tiles
+            sp = np.ones((4, eng.grid())); sp[:, ::3] = 0.05; sp[:, 7] = 30.0
+            eng.cta_speeds = sp; eng._set_cuts()
+        g = _fill(plan, gen, "randn")
+        eng.grad.copy_(g.cuda())
+        eng.step()
+        torch.cuda.synchronize()
+        eng.check_status()
+        out_ref, new_res, slots = engine_oracle(plan, [g], [resid_ref], epoch=eng.epoch)
+        assert not _compare_slot(plan, eng.slot(), slots[0], f"calib_s{step}")
+        assert torch.equal(eng.grad.cpu(), out_ref) and torch.equal(eng.resid.cpu(), new_res[0])
+        resid_ref = new_res[0]
+    eng.close()
+
+
 @pytest.mark.timeout(300)
 def test_both_adversarial_ties_is_bounded():
     """Worst case of the exact in-bin rank of the 'both' mode (ops/csrc/engine.cu::phase_rank_exact is all-pairs
