@@ -104,3 +104,38 @@ def test_fuzz_allgather_variable_sizes_world2():
     ret = mgr.dict()
     mp.spawn(_fuzz_worker, args=(2, _free_port(), 60, 0, ret), nprocs=2, join=True)
     assert ret["done"] == 60
+
+
+def _randomk_allreduce_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import deepreduce_b200 as dr
+    d, ratio = 5000, 0.05
+    grc = dr.deepreduce_from_params({'compressor': 'randomk', 'memory': 'none', 'communicator': 'allreduce', 'compress_ratio': ratio})
+    ok = True
+    for step in range(3):
+        g = torch.randn(d, generator=torch.Generator().manual_seed(10 * step + rank))
+        out = grc.step(g.clone(), 'w')
+        gs = [torch.empty_like(g) for _ in range(world)]
+        dist.all_gather(gs, g)
+        mean = sum(gs) / world
+        nz = torch.nonzero(out).flatten()
+        # shared random indices (same seed on every rank): the aggregate is the mean of the ranks' values THERE — an
+        # all-reduce that also summed the index tensors would scatter to W * idx (out of range / wrong places)
+        ok = ok and 0 < nz.numel() <= int(d * ratio) and torch.allclose(out[nz], mean[nz], atol=1e-6)
+        outs = [torch.empty_like(out) for _ in range(world)]
+        dist.all_gather(outs, out)
+        ok = ok and all(torch.equal(outs[0], o) for o in outs)
+    if rank == 0:
+        ret["ok"] = bool(ok)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_randomk_with_allreduce_world2():
+    """GRACE's randomk + allreduce pairing (config.py allows it): only the value component may be all-reduced."""
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_randomk_allreduce_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    assert ret["ok"]
