@@ -580,10 +580,18 @@ def main():
     rank, world, local = init_dist(args)
     if world != args.gpus and rank == 0:
         print(f"[bench] warning: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
-    try:
-        out = run_ours(args, rank, world, local) if args.impl == "ours" else run_reference(args, rank, world, local)
-    finally:
-        pass
+    if args.impl == "ours":
+        out = run_ours(args, rank, world, local)
+    else:
+        try:
+            out = run_reference(args, rank, world, local)
+        except Exception as e:      # the unmodified reference can fail on its own (e.g. its CPU 6x6 inverse on a singular segment)
+            import traceback
+            traceback.print_exc()
+            last = (traceback.extract_tb(e.__traceback__) or [None])[-1]
+            where = f"{os.path.basename(last.filename)}:{last.lineno}" if last else "?"
+            out = {"impl": "reference", "unavailable": f"reference raised {type(e).__name__} at {where}: {str(e).splitlines()[0][:160]}",
+                   "config": {"model": args.model, "gradient_exchange": args.config}}
     if rank == 0:
         print(json.dumps(out), file=result_out, flush=True)
     import torch.distributed as dist
