@@ -108,7 +108,8 @@ def main(argv=None):
     from .trainer import Trainer
     from .utils.checkpoint import load_checkpoint, save_checkpoint
     tr = Trainer(model, params, lr=args.lr, amp_dtype=torch.bfloat16 if use_cuda else None,
-                 channels_last=meta["kind"] == "image", loss_fn=loss_for(meta), bucket_cap_mb=32.0,
+                 channels_last=meta["kind"] == "image", loss_fn=loss_for(meta),
+                 bucket_cap_mb=32.0 if world == 1 else 1e9,      # N > 1: one bucket after backward (bench.py --bucket-mb)
                  accum_steps=args.grads_accumulated)
     if args.load_checkpoint_path:
         load_checkpoint(args.load_checkpoint_path, tr)

@@ -236,6 +236,12 @@ class DeepReduceDDP:
                 # kernel starts is exposed — launch inline on the current stream with the whole GPU instead of paying
                 # the thread hand-off + event round trip (measured: 54.30 -> 54.00 ms/step, profiles/overlap_sweep.md)
                 eng.ctx.set_grid_cap(0)
+                if self.sched is not None and len(self.buckets) > 1 and self.world > 1:
+                    # cross-rank ordering: every rank must run its bucket kernels in the same order — a full-grid
+                    # kernel that spins on peer flags would otherwise keep this rank's earlier (side-stream) buckets
+                    # from starting while the peers wait for exactly those (deadlock until the peer watchdog fires).
+                    # Make this stream wait for everything handed to the launch thread first.
+                    self.sched.wait_all()
                 eng.step(eng.epoch)
         else:
             if self.world > 1:
