@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--bucket-mb", type=float, default=None,
                     help="flat bucket size; default 128 MB on 1 GPU (ResNet-50 = one bucket; BERT-large = 11, overlapped with "
                          "backward) and ONE bucket launched after backward on N > 1 GPUs (a persistent exchange kernel that "
-                         "waits for its peers must not sit on SMs backward needs: BERT-large, 4 GPUs, 39.7 -> 33.1 ms/step)")
+                         "waits for its peers must not sit on SMs backward needs: BERT-large, 4 GPUs, 39.7 -> 33.1 ms/step, profiles/README.md)")
     ap.add_argument("--blocks-per-sm", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="(kept for compatibility: the exchange-kernel timing is always reported)")

@@ -221,7 +221,10 @@ class DeepReduceDDP:
         self._launched[b] = True
         if self.fused:
             eng = self.engines[b]
-            eng.epoch = self.step_count + 1
+            # the engine's own step counter, never reset: peer flags carry the epoch, so an epoch that was already used
+            # (e.g. by calibrate_partition's synthetic steps, or by a self-check step between training steps) would
+            # let the flag waits pass before the peers have written their slots
+            eng.epoch = eng.epoch + 1
             # buckets that become ready while backward is still running are launched with a capped grid so that the
             # persistent exchange kernel does not take every SM from cuDNN / cuBLAS; the bucket launched from
             # finish() (nothing left to overlap with) gets the whole GPU

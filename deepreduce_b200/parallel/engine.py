@@ -659,7 +659,9 @@ class BucketEngine:
     def load_state_dict(self, state):
         self.resid.copy_(state["resid"].to(self.device))
         self.sel.copy_(state["sel"].to(self.device))
-        self.epoch = int(state["epoch"])
+        # never move the step counter backwards inside a live process group: the peers' flags in the arena carry
+        # epochs this engine has already used (e.g. during calibrate_partition)
+        self.epoch = max(self.epoch, int(state["epoch"]))
 
 
 # ---------------------------------------------------------------------------

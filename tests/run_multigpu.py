@@ -37,6 +37,11 @@ def main():
         plan = BucketPlan(sizes, compress_ratio=0.01, index=index, policy=policy, value=value, **extra)
         eng = BucketEngine(plan, device=f"cuda:{local}", spin_limit=4_000_000, shard=shard,
                            transport="nccl" if shard == "nccl" else None)
+        if index == "bloom" and value is None and shard is True and policy == "leftmost" and not extra:
+            # the collective partition calibration (synthetic steps with their own epochs) must leave a fresh state and a
+            # step counter that only moves forward — the oracle steps below then still match bit for bit
+            eng.calibrate_partition(steps=1, rounds=1)
+            assert eng.epoch > 0 and float(eng.resid.abs().max()) == 0.0
         if rank == 0:
             print(f"engine index={index} value={value} shard={shard} nvls={bool(getattr(eng, 'multicast_ptr', 0))} "
                   f"{getattr(eng, '_nvls_error', '')}", flush=True)
