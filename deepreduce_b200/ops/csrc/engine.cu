@@ -1,4 +1,4 @@
-// DeepReduce-B200 fused bucket engine (sm_100a), v11.
+// DeepReduce-B200 fused bucket engine (sm_100a), v22.
 //
 // One persistent, cooperatively-launched kernel runs the whole per-bucket
 // gradient exchange:
@@ -19,8 +19,9 @@
 // one at a time (phase_begin/phase_end) — the "unfused chain" debug mode.
 //
 // Work decomposition: the bucket is cut into 4096-element tiles that never cross a
-// tensor; every streaming phase gives CTA b the same contiguous tile range.  The
-// universe is read exactly once (accumulate): everything after it works on
+// tensor; every streaming phase gives CTA b one contiguous tile range, cut on the host
+// per phase class from per-tile costs and measured per-CTA speeds (tile_range, P.cuts).
+// The universe is read exactly once (accumulate): everything after it works on
 //   * the candidate list  — the (key, offset) pairs with |x| above a fraction of last
 //     step's threshold, written per (tile, warp) at a fixed location (no allocation,
 //     no overflow); digit 2 of the select and the bloom insert walk it instead of d;
