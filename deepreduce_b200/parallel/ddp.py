@@ -172,7 +172,14 @@ class DeepReduceDDP:
                 # re-cut the kernel's tile partitions from measured per-CTA phase times (collective; ~12 exchange steps
                 # on synthetic gradients, state reset afterwards) — 'calibrate_partition': False keeps the static cut
                 if self.params.get('calibrate_partition', True) and eng.cuts is not None:
-                    eng.calibrate_partition()
+                    try:
+                        eng.calibrate_partition()
+                    except (ValueError, ArithmeticError, IndexError) as e:      # host-side arithmetic only: the static
+                        import warnings                                      # per-phase cut is a complete fallback
+                        warnings.warn(f"deepreduce_b200: partition calibration skipped ({e!r}); using the static cut")
+                        eng.cta_speeds = None
+                        eng._set_cuts()
+                        eng.resid.zero_(); eng.sel.zero_(); eng.grad.zero_()
                 flat, views = eng.grad, eng.grad_views
             else:
                 plan = BucketPlan(numels, names, shapes, index=None)
