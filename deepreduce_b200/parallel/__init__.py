@@ -1,4 +1,5 @@
 from .plan import BucketPlan, TensorPlan
 from .engine import BucketEngine, decode_slot_oracle, engine_oracle, stats_from_slot
+from .ddp import DeepReduceDDP
 
-__all__ = ["BucketPlan", "TensorPlan", "BucketEngine", "decode_slot_oracle", "engine_oracle", "stats_from_slot"]
+__all__ = ["BucketPlan", "TensorPlan", "BucketEngine", "DeepReduceDDP", "decode_slot_oracle", "engine_oracle", "stats_from_slot"]
