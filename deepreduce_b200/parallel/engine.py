@@ -32,6 +32,7 @@ import torch.distributed as dist
 
 from .. import spec
 from ..codecs.bloom import bloom_insert_oracle, bloom_query_oracle
+from .plan import update_cta_speeds
 from .plan import (ARENA_HDR_WORDS, DYN_WORDS, HIST_BINS, MODE_BLOOM, MODE_RLE, NUM_HIST, POLICY_ID,
                    SLOT_HEADER_WORDS, BucketPlan, rle_stream_words)
 
@@ -483,9 +484,7 @@ class BucketEngine:
                 if rnd == rounds:
                     break
                 for c in range(4):
-                    rel = np.median(dur[c]) / np.maximum(dur[c], 1e-3)      # > 1: this CTA finished early -> give it more
-                    speeds[c] = np.clip(speeds[c] * rel ** gain, 0.5, 2.0)
-                    speeds[c] /= speeds[c].mean()
+                    speeds[c] = update_cta_speeds(speeds[c], dur[c], gain)   # finished early -> more work next cut
                 self.cta_speeds = speeds
                 self._set_cuts()
         finally:

@@ -31,6 +31,18 @@ MAX_SEGMENTS = 22
 # (accumulate, insert, query, emit): least-squares fit of the per-CTA phase durations of a ResNet-50 bucket
 # (profiles/round2/cta_timeline_v21.txt; scripts/cta_timeline.py)
 PART_WEIGHTS = ((5.0, 1.0), (2.0, 0.0), (5.5, 1.5), (3.0, 0.0))
+
+
+def update_cta_speeds(speeds, dur, gain: float = 0.8):
+    """One calibration step of the per-CTA relative speeds of a phase class: a CTA that took ``dur[b]`` for its current
+    share when the median CTA took ``median(dur)`` gets its speed (= its share of the next cut) scaled by
+    ``(median / dur[b]) ** gain``; clipped to [0.5, 2] and renormalised to mean 1.  ``gain`` < 1 damps the measurement
+    noise of a single round (BucketEngine.calibrate_partition)."""
+    speeds = np.asarray(speeds, dtype=np.float64)
+    dur = np.asarray(dur, dtype=np.float64)
+    rel = np.median(dur) / np.maximum(dur, 1e-3)
+    out = np.clip(speeds * rel ** gain, 0.5, 2.0)
+    return out / out.mean()
 MAX_POLY_K = 1 << 17      # the all-pairs rank pass is O(K^2): larger tensors keep fp32 values
 DESC_WORDS = 32
 RANK_BINS = 8192
