@@ -19,6 +19,7 @@ CASES = [
     ("bloom", None, dict(sparsifier="threshold", threshold=1.0, capacity_ratio=0.5), True),
     (None, "polyfit", {}, True),
     ("bloom", "qsgd", dict(quantum_num=1000), True),
+    ("bloom", None, dict(policy="random", fpr=0.02), True),          # added after the last sanitizer run of round 2
 ]
 CASES = CASES[:int(os.environ.get("SAN_CASES", len(CASES)))]
 for index, value, kw, tma in CASES:
