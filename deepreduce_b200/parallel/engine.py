@@ -452,11 +452,12 @@ class BucketEngine:
     def calibrate_partition(self, steps: int = 3, rounds: int = 2, gain: float = 0.8, verbose: bool = False):
         """Measure how fast every CTA of the persistent kernel gets through its share of the accumulate / insert / query /
         emit phases (``%globaltimer`` stamps, ``set_debug_times``) on synthetic gradients and re-cut the four tile
-        partitions so that slow CTAs get less work.  Why: the SMs of a B200 do not run the memory-heavy phases at the
-        same speed (the L2 is split over two dies; the per-CTA timeline shows ~75 of the 148 SMs 12 % slower in
-        accumulate and 20 % in query), and every phase ends at a grid barrier, i.e. lasts as long as its slowest CTA.
-        Collective at W > 1 (runs ``rounds * (steps + 1)`` exchange steps).  Resets residual / select history / gradient
-        afterwards; the step counter keeps running (flags are epoch-valued).  Returns the per-round phase maxima."""
+        partitions so that slow CTAs get less work.  Why: the two co-resident CTAs of an SM do not run the issue-bound
+        phases at the same speed (the per-CTA timeline shows the second-launched CTA of almost every SM 12 % slower in
+        accumulate and 20 % in query; profiles/README.md section 2), and every phase ends at a grid barrier, i.e. lasts
+        as long as its slowest CTA.  Collective at W > 1 (runs ``(rounds + 1) * (steps + 1)`` exchange steps).  Resets
+        residual / select history / gradient afterwards; the step counter keeps running (flags are epoch-valued).
+        Returns the per-round phase maxima / medians."""
         G = self.grid()
         dbg = torch.zeros((PH_END + 1) * G * 2, dtype=torch.int64, device=self.device)
         self.ctx.set_debug_times(dbg.data_ptr())
