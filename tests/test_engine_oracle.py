@@ -374,3 +374,23 @@ def test_partition_calibration_converges_on_a_two_speed_machine():
     assert spread[0] > 1.18 and max(spread[2:]) < 1.15
     assert abs(speeds[G // 2:].mean() / speeds[:G // 2].mean() - 0.85) < 0.03
     assert abs(speeds.mean() - 1.0) < 1e-9 and speeds.min() >= 0.5 * 0.9 and speeds.max() <= 2.0 * 1.1
+
+
+def test_phase_cuts_property_any_speeds_any_plan():
+    """The kernel trusts the host-computed cuts blindly: for any plan, grid and speed vector every phase class must tile
+    [0, n_tiles) with non-decreasing cut positions."""
+    import numpy as np
+    from hypothesis import given, settings, strategies as st
+    from deepreduce_b200.parallel import BucketPlan
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.lists(st.integers(1, 300000), min_size=1, max_size=12), st.sampled_from([2, 37, 148, 296]),
+           st.integers(0, 2 ** 31 - 1))
+    def check(numels, grid, seed):
+        plan = BucketPlan(numels, compress_ratio=0.01)
+        rng = np.random.default_rng(seed)
+        sp = np.exp(rng.uniform(np.log(0.05), np.log(30.0), size=(4, grid)))
+        c = plan.phase_cuts(grid, sp).numpy().astype(np.int64)
+        assert c.shape == (4, grid + 1)
+        assert (c[:, 0] == 0).all() and (c[:, -1] == plan.n_tiles).all() and (np.diff(c, axis=1) >= 0).all()
+    check()
